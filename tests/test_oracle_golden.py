@@ -1,0 +1,160 @@
+"""Pin the CPU oracle against fixtures produced by the UNMODIFIED reference
+(tests/golden/make_golden.py) and the known-answer vectors of SURVEY.md §8(c)."""
+
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import LossCfg
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+KINDS = ["drgrpo", "drgrpo-negclipped", "rloo", "opo"]
+
+
+def load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+# ----------------------------------------------------------------- advantages
+def test_advantages_known_answers():
+    # KAT-A, SURVEY §8c (docstring of orchestrator/advantage.py:13-16,27-30)
+    r, ln = [0.0, 0.0, 1.0, 1.0], [1, 2, 3, 4]
+    np.testing.assert_array_equal(oracle.advantages(r, ln, 4, "drgrpo"), np.float32([-0.5, -0.5, 0.5, 0.5]))
+    np.testing.assert_array_equal(oracle.advantages(r, ln, 4, "drgrpo-negclipped"), np.float32([0, 0, 0.5, 0.5]))
+    np.testing.assert_array_equal(
+        oracle.advantages(r, ln, 4, "rloo"), np.float32([-0.6666666865, -0.6666666865, 0.6666666865, 0.6666666865])
+    )
+    np.testing.assert_array_equal(
+        oracle.advantages(r, ln, 4, "opo"), np.float32([-0.6999999881, -0.6999999881, 0.3000000119, 0.3000000119])
+    )
+
+
+def test_advantages_vs_reference_fixtures():
+    d = load("advantages.npz")
+    for name in d["names"]:
+        r, ln, grp = d[f"{name}/rewards"], d[f"{name}/lengths"], int(d[f"{name}/group"])
+        for k in KINDS:
+            got = oracle.advantages(r, ln, grp, k)
+            ref = d[f"{name}/{k}"]
+            if name.startswith("tol_"):
+                # reduction order differs from ATen's for these group sizes: <= 1e-6 rel (north_star)
+                np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-6 * np.abs(r).max())
+            else:
+                np.testing.assert_array_equal(got, ref, err_msg=f"{name}/{k}")  # bit-exact (nan == nan)
+
+
+def test_advantages_bad_group():
+    with pytest.raises(AssertionError):
+        oracle.advantages([1.0, 2.0, 3.0], [1, 1, 1], 2, "drgrpo")
+
+
+# ------------------------------------------------------------------- segments
+def test_segments_vs_reference_fixtures():
+    d = load("segments.npz")
+    for name in d["names"]:
+        assert oracle.response_lengths(d[f"{name}/position_ids"]) == d[f"{name}/lengths"].tolist(), name
+    # KAT-2
+    assert oracle.response_lengths([0, 1, 2, 0, 1, 2, 3, 0, 1]) == [3, 4, 2]
+    assert oracle.response_lengths([0, 1, 2, 0, 0, 1, 2]) == [7]
+
+
+# ----------------------------------------------------------------------- loss
+CFG = {
+    "token": LossCfg("token", False, 8.0),
+    "token_c2": LossCfg("token", False, 2.0),
+    "seq": LossCfg("sequence", False, 8.0),
+    "seqnorm": LossCfg("sequence", True, 8.0),
+}
+
+
+def test_loss_vs_reference_fixtures():
+    d = load("loss.npz")
+    n = 0
+    for name in d["names"]:
+        logp, old, adv, mask = (d[f"{name}/{k}"] for k in ("logp", "old", "adv", "mask"))
+        lens = d[f"{name}/lens"].tolist()
+        for cname in d["cfgs"]:
+            keys = [k for k in d.files if k.startswith(f"{name}/{cname}/S") and k.endswith("/loss")]
+            for k in keys:
+                scale = int(k.split("/")[2][1:])
+                pre = f"{name}/{cname}/S{scale}"
+                loss, ratio, clipped, flag, dlogp = oracle.loss_fwd_bwd(logp, old, adv, mask, lens, CFG[cname], scale, np.float64)
+                np.testing.assert_allclose(loss, d[pre + "/loss"], rtol=1e-5, atol=1e-6)
+                np.testing.assert_allclose(ratio, d[pre + "/ratio"], rtol=2e-5)
+                np.testing.assert_allclose(clipped, d[pre + "/clipped"], rtol=2e-5)
+                np.testing.assert_array_equal(flag, d[pre + "/is_clipped"])
+                np.testing.assert_allclose(dlogp, d[pre + "/dlogp"], rtol=2e-5, atol=1e-7)
+                n += 1
+    assert n >= 40
+
+
+def test_loss_known_answers():
+    # KAT-3 / KAT-4
+    logp, old = [-1, -2, -0.5, -3, -0.1], [-1.5, -1, -3, -3, -0.2]
+    adv, mask, lens = [0.5, 0.5, 0.5, -1, -1], [1, 1, 1, 0, 1], [3, 2]
+    loss, ratio, clipped, flag, dlogp = oracle.loss_fwd_bwd(logp, old, adv, mask, lens, CFG["token"], 4)
+    assert abs(loss - (-0.9757823348)) < 1e-6
+    np.testing.assert_allclose(ratio, [1.6487212, 0.3678795, 12.1824942, 1.0, 1.1051710], rtol=1e-6)
+    assert clipped[2] == 8.0 and flag.tolist() == [0, 0, 1, 0, 0]
+    np.testing.assert_allclose(dlogp, [-0.2060902, -0.0459849, 0, 0, 0.2762927], rtol=1e-5, atol=1e-7)
+    loss, ratio, *_, dlogp = oracle.loss_fwd_bwd(logp, old, adv, mask, lens, CFG["seq"], 2)
+    assert abs(loss - (-1.2946784496)) < 1e-6
+    np.testing.assert_allclose(ratio, [7.3890562, 1.1051710], rtol=1e-6)
+    np.testing.assert_allclose(dlogp, [-1.8472641] * 3 + [0, 0.5525855], rtol=1e-5)
+    loss, ratio, *_, dlogp = oracle.loss_fwd_bwd(logp, old, adv, mask, lens, CFG["seqnorm"], 2)
+    assert abs(loss - 0.0656519234) < 1e-6
+    np.testing.assert_allclose(dlogp, [-0.1623112] * 3 + [0, 0.5525855], rtol=1e-5)
+    # loss_scale = 0 behaves as 1
+    l0 = oracle.loss_fwd_bwd(logp, old, adv, mask, lens, CFG["token"], 0)[0]
+    l1 = oracle.loss_fwd_bwd(logp, old, adv, mask, lens, CFG["token"], 1)[0]
+    assert l0 == l1
+
+
+# -------------------------------------------------------------------- LM head
+def test_kat1_shift_logp_entropy():
+    d = load("lmhead.npz")
+    logits, ids = d["kat1/logits"], d["kat1/ids"]
+    for tau in (1.0, 2.0):
+        lp, ent, _ = oracle.logprobs_entropy(oracle.shift_rows(logits), ids, tau)
+        np.testing.assert_allclose(lp, d[f"kat1/tau{tau}/logp"], atol=1e-6)
+        np.testing.assert_allclose(ent, d[f"kat1/tau{tau}/entropy"], atol=1e-6)
+    lp, ent, _ = oracle.logprobs_entropy(oracle.shift_rows(logits), ids, 1.0)
+    np.testing.assert_allclose(lp, [-1.3862944, -0.4401898, -1.3862944], atol=1e-6)
+    np.testing.assert_allclose(ent, [1.3862944, 0.9475369, 1.3862944], atol=1e-6)
+
+
+def rel_l2(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def test_lmhead_chain_vs_reference_fixtures():
+    d = load("lmhead.npz")
+    for key in d["names"]:
+        name, tau_s, cname = key.split("/")
+        tau = float(tau_s[3:])
+        is_bf16 = bool(d[f"{name}/is_bf16"])
+        cfg = LossCfg() if cname == "token" else LossCfg("sequence", True, 8.0)
+        res = oracle.micro_step(
+            d[f"{name}/hidden"], d[f"{name}/weight"], d[f"{name}/ids"], d[f"{name}/pos"], d[f"{key}/old"],
+            d[f"{name}/adv"], d[f"{name}/mask"], tau, cfg, int(d[f"{key}/scale"]), round_bf16=is_bf16,
+        )
+        assert res["lengths"] == d[f"{key}/lens"].tolist()
+        # bf16 CPU matmul accumulates in a different order than fp64: a logit can land on the
+        # other side of a bf16 rounding boundary (<= 1 bf16 ulp of the logit) -> looser atol.
+        atol = 3e-2 if is_bf16 else 2e-5
+        np.testing.assert_allclose(res["logp"], d[f"{key}/logp"], atol=atol)
+        np.testing.assert_allclose(res["entropy"], d[f"{key}/entropy"], atol=atol)
+        assert np.mean(np.abs(res["logp"] - d[f"{key}/logp"]) < 1e-3) > 0.97
+        np.testing.assert_allclose(res["loss"], d[f"{key}/loss"], rtol=5e-3 if is_bf16 else 1e-4, atol=1e-5)
+        assert rel_l2(res["d_hidden"], d[f"{key}/d_hidden"]) < 1e-2
+        assert rel_l2(res["d_weight"], d[f"{key}/d_weight"]) < 1e-2
+
+
+def test_bf16_round_matches_torch():
+    import torch
+
+    x = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 37
+    ref = torch.from_numpy(x).to(torch.bfloat16).float().numpy()
+    np.testing.assert_array_equal(oracle.bf16_round(x), ref)
