@@ -1,0 +1,172 @@
+/*
+ * prl_b200.h — C ABI of the B200-native PRIME-RL per-token RL loss hot path.
+ *
+ * The reference (pmahdavi/prime-rl-cse) is pure Python and has no FFI; every
+ * entry point below replaces a Python-level interface of the reference, cited
+ * as file:line relative to the reference root.  The Python host layer in
+ * prime_rl_cse_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     stated otherwise; the caller owns all memory (inputs, outputs, workspace);
+ *     the library never allocates, frees or retains device memory.
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and
+ *     the call returns without synchronising.
+ *   - return value: PRL_OK (0) or a negative PRL_ERR_* code; nothing is thrown
+ *     across the ABI.  prl_strerror() names the code, prl_last_error_detail()
+ *     gives the thread-local detail string (e.g. the cudaGetErrorString text).
+ *   - sm_100a only.  There is no CPU fallback: on a machine without a B200 every
+ *     compute entry point returns PRL_ERR_CUDA.
+ */
+#ifndef PRL_B200_H_
+#define PRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRL_OK 0
+#define PRL_ERR_BAD_ARG (-1)     /* null pointer, negative size, n % group != 0 ...        */
+#define PRL_ERR_UNSUPPORTED (-2) /* shape outside what the kernels handle (e.g. H % 8 != 0) */
+#define PRL_ERR_CUDA (-3)        /* launch / driver error, see prl_last_error_detail()      */
+#define PRL_ERR_WORKSPACE (-4)   /* workspace too small                                     */
+
+/* advantage kinds: REGISTRY of src/prime_rl/orchestrator/advantage.py:63-68 */
+#define PRL_ADV_DRGRPO 0
+#define PRL_ADV_DRGRPO_NEGCLIPPED 1
+#define PRL_ADV_RLOO 2
+#define PRL_ADV_OPO 3
+
+/* ratio types: LossConfig.ratio_type, src/prime_rl/trainer/rl/config.py:22 */
+#define PRL_RATIO_TOKEN 0
+#define PRL_RATIO_SEQUENCE 1
+
+/* dtype tags for gradient outputs */
+#define PRL_DT_BF16 0
+#define PRL_DT_F32 1
+
+int prl_version(void);
+const char* prl_strerror(int code);
+const char* prl_last_error_detail(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Group-relative advantages.
+ * Replaces compute_advantages(), src/prime_rl/orchestrator/advantage.py:71-103 (per-group maths
+ * :18, :32, :41-43, :55-57).  rewards[n] fp32, lengths[n] int64 (read only for PRL_ADV_OPO, may
+ * be NULL otherwise), n % group == 0.  out[n] fp32.  One warp per group; the fp32 sum uses 8
+ * strided lane accumulators combined left to right, then the tail (DESIGN.md "advantages").
+ * If token_out != NULL also broadcasts out[i] over the tokens of rollout i:
+ *   token_out[t] = out[i] for tok_offsets[i] <= t < tok_offsets[i+1]
+ * (replaces prepare_sample's `.repeat(len)`, src/prime_rl/orchestrator/batch.py:44).
+ * ---------------------------------------------------------------------------------------- */
+int prl_advantages_f32(const float* rewards, const int64_t* lengths, int64_t n, int32_t group, int32_t kind,
+                       float* out, const int64_t* tok_offsets, float* token_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Segment boundaries of a packed row.
+ * Replaces get_response_lengths(), src/prime_rl/trainer/utils.py:36-69 (boundary rule :54-60).
+ * position_ids[T] int64.  Writes cu_seqlens[0..nseg] (int32, cu_seqlens[0]=0, cu_seqlens[nseg]=T)
+ * and *nseg (int32, device).  max_seg bounds the segment count that will be written; if more
+ * boundaries exist *nseg is set to -(true count) and only max_seg are written.
+ * ---------------------------------------------------------------------------------------- */
+int prl_segments_from_position_ids(const int64_t* position_ids, int64_t T, int32_t* cu_seqlens, int32_t* nseg,
+                                   int32_t max_seg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Packed clipped importance-ratio loss, forward (also emits d loss / d logp).
+ * Replaces compute_loss(), src/prime_rl/trainer/rl/loss.py:61-124, on the packed layout of
+ * MicroBatch (src/prime_rl/trainer/rl/data.py:13-23): logp/old/adv fp32 [T], mask uint8 [T]
+ * (torch.bool storage), cu_seqlens int32 [nseg+1] (device).
+ *   mode PRL_RATIO_TOKEN:    ratio/clipped/is_clipped are [T];
+ *   mode PRL_RATIO_SEQUENCE: they are [nseg] (loss.py:92-96,107-108).
+ * loss_scale is the caller's `loss_scale` (max(.,1) applied inside, loss.py:118).
+ * loss: 1 float.  dlogp[T]: d loss / d logp (autograd equivalent).
+ * workspace: prl_loss_workspace_bytes(T, nseg) bytes.
+ * ---------------------------------------------------------------------------------------- */
+size_t prl_loss_workspace_bytes(int64_t T, int32_t nseg);
+int prl_loss_packed_fwd(const float* logp, const float* old_logp, const float* adv, const uint8_t* mask,
+                        const int32_t* cu_seqlens, int32_t nseg, int64_t T, int32_t mode, int32_t length_norm,
+                        float clip_ratio, double loss_scale, float* loss, float* ratio, float* clipped,
+                        float* is_clipped, float* dlogp, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[i] = a[i] * (*scale)   (backward of the scalar loss: dlogp * grad_output; scale is a device scalar) */
+int prl_scale_f32(const float* a, const float* scale, float* out, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Unfused API-compat kernel on MATERIALISED logits: one pass over logits[R,V] fp32 giving
+ *   logp[r] = z[r, ids[r]] - logsumexp(z[r]),  entropy[r] = logsumexp(z[r]) - sum softmax(z[r]) z[r]
+ * with z = logits * inv_temp.  Replaces selective_log_softmax() (rl/loss.py:13-39, fp32 branch
+ * :26-30) and compute_entropy() (rl/loss.py:43-47).  ids may be NULL (entropy only); logp / entropy
+ * may be NULL.  If shift != 0 row r reads logits row r-1 and row 0 is all zeros (shift_logits,
+ * rl/loss.py:51-58, applied per batch row of `seq` positions).
+ * ---------------------------------------------------------------------------------------- */
+int prl_logits_stats_f32(const float* logits, const int64_t* ids, int64_t rows, int64_t seq, int64_t V,
+                         float inv_temp, int32_t shift, float* logp, float* entropy, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused LM head: hidden[T,H] x W[V,H]^T with an online (max, sum-exp, sum exp*z, target) epilogue;
+ * the [T,V] logits never reach HBM.  Replaces the chain
+ *   forward(model).logits  (src/prime_rl/trainer/model.py:250-254, HF lm_head nn.Linear)
+ *   .float().contiguous()  (src/prime_rl/trainer/rl/train.py:285)
+ *   shift_logits           (rl/loss.py:51-58)         [shift != 0]
+ *   / temperature          (rl/train.py:287)          [inv_temp = 1/temperature]
+ *   selective_log_softmax  (rl/loss.py:13-39)         -> logp[T]
+ *   compute_entropy        (rl/loss.py:43-47)         -> entropy[T]
+ * hidden, W: bf16 row-major (H contiguous), H % 8 == 0.  ids[T] int64 are GLOBAL vocab ids;
+ * W holds vocab rows [v_offset, v_offset + V) of a vocabulary of V_total rows (V_total == V and
+ * v_offset == 0 when not vocab-sharded).  round_bf16 != 0 rounds each accumulator to bf16 before the
+ * softmax statistics (the reference's bf16 logits).
+ * Outputs (each may be NULL): logp[T], entropy[T], lse[T] fp32 — final values, only meaningful when
+ * the shard is the whole vocabulary; partials[T,4] fp32 = (m, s, u, z_target) of THIS shard, to be
+ * exchanged across vocab shards and merged with prl_lmhead_merge_partials.
+ * ---------------------------------------------------------------------------------------- */
+size_t prl_lmhead_fwd_workspace_bytes(int64_t T, int32_t H, int64_t V);
+int prl_lmhead_fwd(const void* hidden, const void* weight, const int64_t* ids, int64_t T, int32_t H, int64_t V,
+                   int64_t v_offset, int64_t V_total, float inv_temp, int32_t shift, int32_t round_bf16,
+                   float* logp, float* entropy, float* lse, float* partials, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Merge nparts per-token partials (partials[nparts, T, 4]) into logp / entropy / lse (vocab-sharded
+ * LM head: the only data exchanged between vocab shards, BASELINE.json config 4). */
+int prl_lmhead_merge_partials(const float* partials, int32_t nparts, int64_t T, float* logp, float* entropy,
+                              float* lse, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Recompute-based backward of the fused LM head (autograd through rl/train.py:285-288, executed by
+ * loss.backward() at rl/train.py:310).  Given lse[T] (from the forward) and dlogp[T] = d loss / d logp:
+ *   dz[t,v] = dlogp[t] * (1[v == ids[t]] - exp(z[t,v] - lse[t])),  dlogits[t-shift] = dz[t] * inv_temp
+ * (rounded to bf16 like the reference's bf16 logits gradient), then
+ *   d_hidden[T,H] (bf16)            = dlogits x W
+ *   d_weight[V,H] (bf16 or fp32)  (+)= dlogits^T x hidden      (accumulate_dw != 0 adds to d_weight)
+ * Logits are recomputed tile by tile with the forward's GEMM; a bounded [T, vchunk] bf16 dlogits
+ * block lives in `workspace` (never the whole [T,V]); vchunk == 0 picks the default.
+ * d_hidden may be NULL (W-only) and d_weight may be NULL (hidden-only).  For a vocab shard d_hidden
+ * is the shard's partial sum (reduce across shards by the caller); set d_hidden_f32 != 0 to get it as fp32.
+ * ---------------------------------------------------------------------------------------- */
+size_t prl_lmhead_bwd_workspace_bytes(int64_t T, int32_t H, int64_t V, int64_t vchunk);
+int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, const float* lse,
+                   const float* dlogp, int64_t T, int32_t H, int64_t V, int64_t v_offset, float inv_temp,
+                   int32_t shift, int32_t round_bf16, void* d_hidden, int32_t d_hidden_f32, void* d_weight,
+                   int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Plain bf16 GEMM on the same tcgen05 engine, exposed for tests and bring-up:
+ *   C[M,N] (fp32) = A x B with per-operand major-ness:
+ *   a_mn_major == 0: A is [M,K] row-major (K contiguous); != 0: A is stored [K,M] (M contiguous)
+ *   b_mn_major == 0: B is [N,K] row-major (K contiguous); != 0: B is stored [K,N] (N contiguous)
+ * ---------------------------------------------------------------------------------------- */
+int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn_major,
+                      int32_t b_mn_major, int32_t accumulate, void* stream);
+
+/* number of kernel launches issued by this library on this host thread since the last reset
+ * (bench.py's `gpu_launches`) */
+int64_t prl_launch_count(int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRL_B200_H_ */

@@ -1,0 +1,27 @@
+"""prime_rl_cse_b200 — B200-native (sm_100a) implementation of PRIME-RL's per-token RL loss hot path.
+
+Drop-in surface (same names and call signatures as the reference):
+  compute_advantages                      <- prime_rl.orchestrator.advantage
+  compute_loss, selective_log_softmax,
+  compute_entropy, shift_logits           <- prime_rl.trainer.rl.loss
+  get_response_lengths                    <- prime_rl.trainer.utils
+  LossConfig                              <- prime_rl.trainer.rl.config
+plus the fused fast path `fused_lm_head_logprobs_entropy`, `FusedLMHead`, `rl_micro_step`.
+
+Everything runs on CUDA through the C-ABI library `libprl_b200.so`; there is no CPU fallback.
+"""
+
+from .advantage import compute_advantages, compute_advantages_tensor
+from .config import LossConfig
+from .data import MicroBatch, fake_micro_batch, synthetic_micro_batch, to_device
+from .lm_head import FusedLMHead, fused_lm_head_logprobs_entropy, lm_head_backward_raw, lm_head_forward_raw
+from .loss import compute_entropy, compute_loss, selective_log_softmax, shift_logits, shifted_logprobs_entropy
+from .micro_step import rl_micro_step
+from .segments import get_response_lengths, segments_from_position_ids
+
+__all__ = [
+    "compute_advantages", "compute_advantages_tensor", "LossConfig", "MicroBatch", "fake_micro_batch",
+    "synthetic_micro_batch", "to_device", "FusedLMHead", "fused_lm_head_logprobs_entropy", "lm_head_backward_raw",
+    "lm_head_forward_raw", "compute_entropy", "compute_loss", "selective_log_softmax", "shift_logits",
+    "shifted_logprobs_entropy", "rl_micro_step", "get_response_lengths", "segments_from_position_ids",
+]

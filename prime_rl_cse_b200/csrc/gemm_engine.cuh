@@ -1,0 +1,431 @@
+// Persistent, warp-specialised tcgen05 GEMM engine for sm_100a with pluggable epilogues.
+//
+//   C[M,N] = A x B, bf16 inputs, fp32 accumulation in TMEM, 128 x 256 output tiles, BLOCK_K = 64.
+//   warp 0 (one lane): TMA producer  -> 4-stage smem ring (128B-swizzled tiles)
+//   warp 1 (one lane): tcgen05.mma issuer -> 2 accumulator buffers of 256 TMEM columns
+//   warp 2           : TMEM allocator
+//   warps 4..7       : epilogue; thread i owns accumulator row (lane) i of the tile, so row-wise
+//                      softmax statistics are thread-local (tcgen05.ld 32x32b).
+// Each operand is either K-major (rows of K contiguous) or MN-major (K rows of contiguous M/N), both in
+// the canonical SWIZZLE_128B layouts written directly by TMA.
+//
+// A work item is (m_tile, contiguous range of n_tiles): the epilogue keeps per-row online state across
+// the n-range (forward statistics) and flushes at the end of the item.
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace prl {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int GEMM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr float LOG2E = 1.4426950408889634f;
+
+enum EpiKind { EPI_STATS = 0, EPI_DZ = 1, EPI_STORE = 2 };
+
+// flags of the STORE epilogue
+constexpr int ST_LOAD_F32 = 1;    // C += existing fp32 at c_f32
+constexpr int ST_STORE_F32 = 2;   // write fp32 to c_f32
+constexpr int ST_STORE_BF16 = 4;  // write bf16 to c_bf16
+constexpr int ST_LOAD_BF16 = 8;   // C += existing bf16 at c_bf16
+
+struct EpiParams {
+  int64_t m_rows;  // valid rows of C
+  int64_t n_cols;  // valid columns of C
+  // --- STATS / DZ (LM head) ---
+  const int64_t* ids;  // [T] global vocab ids
+  int64_t T;           // tokens in the packed row; output index t = row + shift
+  int32_t shift;
+  int32_t round_bf16;
+  int64_t col_base;  // global vocab id of column 0 of this GEMM (v_offset + chunk start)
+  float inv_temp;
+  float4* partials;        // STATS: [n_splits][part_stride] (m, s, u, z_target) per source row
+  int64_t part_stride;
+  const float* lse;        // DZ: [T]
+  const float* dlogp;      // DZ: [T]
+  __nv_bfloat16* dz;       // DZ: [rows][ldz] bf16
+  int64_t ldz;
+  // --- STORE ---
+  float* c_f32;
+  __nv_bfloat16* c_bf16;
+  int64_t ldc;
+  int32_t flags;
+};
+
+struct GemmParams {
+  CUtensorMap tma_a;
+  CUtensorMap tma_b;
+  int32_t m_tiles, n_tiles, k_blocks;
+  int32_t tiles_per_split, n_splits, group_m, num_items;
+  uint64_t a_desc_hi, b_desc_hi;  // smem descriptor templates (everything but the start address)
+  uint32_t a_kstep, b_kstep;      // byte advance of the start address per UMMA_K step
+  EpiParams epi;
+};
+
+struct Item {
+  int m_tile, split, n_begin, n_count;
+};
+
+__device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
+  const int per_band = p.group_m * p.n_splits;
+  const int band = item / per_band;
+  const int m0 = band * p.group_m;
+  const int rows = min(p.group_m, p.m_tiles - m0);
+  const int idx = item - band * per_band;
+  Item it;
+  it.split = idx / rows;
+  it.m_tile = m0 + idx % rows;
+  it.n_begin = it.split * p.tiles_per_split;
+  it.n_count = min(p.tiles_per_split, p.n_tiles - it.n_begin);
+  return it;
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogue pieces (one thread = one accumulator row)
+// ------------------------------------------------------------------------------------------------
+struct RowStats {
+  float m, s, u, zt;
+};
+
+template <bool PARTIAL>
+__device__ __forceinline__ void stats_chunk(const uint32_t (&v)[32], RowStats& st, float inv_temp, bool round, int n_valid_in_chunk,
+                                            int tj) {
+  float z[32];
+  if (round) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) z[j] = ptx::round_bf16(__uint_as_float(v[j])) * inv_temp;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) * inv_temp;
+  }
+  float cmax = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (!PARTIAL || j < n_valid_in_chunk) cmax = fmaxf(cmax, z[j]);
+  const float m_new = fmaxf(st.m, cmax);
+  const float sc = ptx::ex2((st.m - m_new) * LOG2E);  // st.m == -inf -> 0
+  st.s *= sc;
+  st.u *= sc;
+  st.m = m_new;
+  const float mneg = -m_new * LOG2E;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (!PARTIAL || j < n_valid_in_chunk) {
+      const float e = ptx::ex2(fmaf(z[j], LOG2E, mneg));
+      st.s += e;
+      st.u = fmaf(e, z[j], st.u);
+    }
+  }
+  if ((unsigned)tj < 32u) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == tj) st.zt = z[j];
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// dz = coef * (1[j == tj] - exp(z - lse)), written as bf16
+__device__ __forceinline__ void dz_chunk(const uint32_t (&v)[32], float inv_temp, bool round, float coef, float nlse2, int tj,
+                                         __nv_bfloat16* dst, int n_valid_in_chunk) {
+  float d[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a = __uint_as_float(v[j]);
+    if (round) a = ptx::round_bf16(a);
+    const float p = ptx::ex2(fmaf(a * inv_temp, LOG2E, nlse2));
+    d[j] = -coef * p;
+  }
+  if ((unsigned)tj < 32u) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == tj) d[j] += coef;
+  }
+  if (n_valid_in_chunk >= 32) {
+    uint4* o = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 w;
+      w.x = pack_bf16x2(d[8 * q + 0], d[8 * q + 1]);
+      w.y = pack_bf16x2(d[8 * q + 2], d[8 * q + 3]);
+      w.z = pack_bf16x2(d[8 * q + 4], d[8 * q + 5]);
+      w.w = pack_bf16x2(d[8 * q + 6], d[8 * q + 7]);
+      o[q] = w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_valid_in_chunk) dst[j] = __float2bfloat16_rn(d[j]);
+  }
+}
+
+__device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], const EpiParams& e, int64_t row, int64_t col0, int n_valid_in_chunk) {
+  float c[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) c[j] = __uint_as_float(v[j]);
+  const int64_t off = row * e.ldc + col0;
+  const bool vec = (n_valid_in_chunk >= 32) && ((e.ldc & 7) == 0);
+  if (vec) {
+    if (e.flags & ST_LOAD_F32) {
+      const float4* src = reinterpret_cast<const float4*>(e.c_f32 + off);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 x = src[q];
+        c[4 * q + 0] += x.x;
+        c[4 * q + 1] += x.y;
+        c[4 * q + 2] += x.z;
+        c[4 * q + 3] += x.w;
+      }
+    }
+    if (e.flags & ST_LOAD_BF16) {
+      const uint4* src = reinterpret_cast<const uint4*>(e.c_bf16 + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 x = src[q];
+        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          c[8 * q + 2 * k + 0] += __uint_as_float(w[k] << 16);
+          c[8 * q + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+        }
+      }
+    }
+    if (e.flags & ST_STORE_F32) {
+      float4* dst = reinterpret_cast<float4*>(e.c_f32 + off);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dst[q] = make_float4(c[4 * q + 0], c[4 * q + 1], c[4 * q + 2], c[4 * q + 3]);
+    }
+    if (e.flags & ST_STORE_BF16) {
+      uint4* dst = reinterpret_cast<uint4*>(e.c_bf16 + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 w;
+        w.x = pack_bf16x2(c[8 * q + 0], c[8 * q + 1]);
+        w.y = pack_bf16x2(c[8 * q + 2], c[8 * q + 3]);
+        w.z = pack_bf16x2(c[8 * q + 4], c[8 * q + 5]);
+        w.w = pack_bf16x2(c[8 * q + 6], c[8 * q + 7]);
+        dst[q] = w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (j < n_valid_in_chunk) {
+        float x = c[j];
+        if (e.flags & ST_LOAD_F32) x += e.c_f32[off + j];
+        if (e.flags & ST_LOAD_BF16) x += __bfloat162float(e.c_bf16[off + j]);
+        if (e.flags & ST_STORE_F32) e.c_f32[off + j] = x;
+        if (e.flags & ST_STORE_BF16) e.c_bf16[off + j] = __float2bfloat16_rn(x);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.tma_a);
+    ptx::prefetch_tensormap(&p.tma_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(&full_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull_bar[i], 1);
+      ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        for (int nt = it.n_begin; nt < it.n_begin + it.n_count; ++nt) {
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
+            uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+            if (!A_MN) {
+              ptx::tma_load_2d(sa, &p.tma_a, &full_bar[stage], kb * BLOCK_K, it.m_tile * BLOCK_M);
+            } else {
+#pragma unroll
+              for (int s = 0; s < BLOCK_M / 64; ++s)
+                ptx::tma_load_2d(sa + s * (BLOCK_K * 128), &p.tma_a, &full_bar[stage], it.m_tile * BLOCK_M + s * 64, kb * BLOCK_K);
+            }
+            if (!B_MN) {
+              ptx::tma_load_2d(sb, &p.tma_b, &full_bar[stage], kb * BLOCK_K, nt * BLOCK_N);
+            } else {
+#pragma unroll
+              for (int s = 0; s < BLOCK_N / 64; ++s)
+                ptx::tma_load_2d(sb + s * (BLOCK_K * 128), &p.tma_b, &full_bar[stage], nt * BLOCK_N + s * 64, kb * BLOCK_K);
+            }
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  k-step of 16 elements = +32 B.
+      // MN-major SW128: 64-element MN slabs BLOCK_K*128 B apart (LBO); 8-k-row groups 1024 B apart (SBO);
+      //                 k-step of 16 rows = +2048 B.
+      // (the host fills these defaults into GemmParams, see make_desc_defaults)
+      const uint64_t a_hi = p.a_desc_hi, b_hi = p.b_desc_hi;
+      const uint32_t a_kstep = p.a_kstep, b_kstep = p.b_kstep;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        for (int nt = 0; nt < it.n_count; ++nt) {
+          ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t sa = ptx::smem_u32(smem_a + stage * A_STAGE_BYTES);
+            const uint32_t sb = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t ad = ptx::smem_desc(a_hi, sa + k * a_kstep);
+              const uint64_t bd = ptx::smem_desc(b_hi, sb + k * b_kstep);
+              ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          ptx::umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const EpiParams& e = p.epi;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const Item it = decode_item(p, item);
+      const int64_t row = (int64_t)it.m_tile * BLOCK_M + row_in_tile;
+      const bool row_ok = row < e.m_rows;
+      // per-item row state
+      RowStats st = {-INFINITY, 0.f, 0.f, 0.f};
+      int64_t tcol = -1;  // target column of this row, local to this GEMM's column space
+      float coef = 0.f, nlse2 = 0.f;
+      if (EPI == EPI_STATS || EPI == EPI_DZ) {
+        const int64_t t = row + e.shift;
+        if (row_ok && t < e.T) {
+          tcol = e.ids[t] - e.col_base;
+          if (EPI == EPI_DZ) {
+            coef = e.dlogp[t] * e.inv_temp;
+            nlse2 = -e.lse[t] * LOG2E;
+          }
+        }
+      }
+      for (int nt = it.n_begin; nt < it.n_begin + it.n_count; ++nt) {
+        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        const int64_t n0 = (int64_t)nt * BLOCK_N;
+        const int64_t n_left = e.n_cols - n0;  // > 0
+#pragma unroll 1
+        for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+          const int64_t c0 = n0 + ch * 32;
+          const int64_t valid64 = n_left - ch * 32;
+          if (valid64 <= 0) break;  // uniform across the CTA
+          const int n_valid = valid64 >= 32 ? 32 : (int)valid64;
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(tmem_base + lane_addr + acc * BLOCK_N + ch * 32, v);
+          ptx::tmem_ld_wait();
+          const int64_t tj64 = tcol - c0;
+          const int tj = (tj64 >= 0 && tj64 < 32) ? (int)tj64 : -1;
+          if (EPI == EPI_STATS) {
+            if (n_valid == 32)
+              stats_chunk<false>(v, st, e.inv_temp, e.round_bf16 != 0, 32, tj);
+            else
+              stats_chunk<true>(v, st, e.inv_temp, e.round_bf16 != 0, n_valid, tj);
+          } else if (EPI == EPI_DZ) {
+            if (row < e.T) dz_chunk(v, e.inv_temp, e.round_bf16 != 0, coef, nlse2, tj, e.dz + row * e.ldz + c0, n_valid);
+          } else {
+            if (row_ok) store_chunk(v, e, row, c0, n_valid);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (EPI == EPI_STATS) {
+        if (row_ok) e.partials[(int64_t)it.split * e.part_stride + row] = make_float4(st.m, st.s, st.u, st.zt);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace prl

@@ -1,0 +1,367 @@
+// Fused LM head (forward statistics + recompute-based backward) and the plain bring-up GEMM, host side:
+// TMA tensor maps, work decomposition, kernel launches, C ABI.  The device code is gemm_engine.cuh.
+#include <stdlib.h>
+
+#include "gemm_engine.cuh"
+
+namespace prl {
+
+// ------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 matrix with `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements; 128B-swizzled boxes.
+static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(PRL_ERR_CUDA, "%s", "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(PRL_ERR_UNSUPPORTED, "%s", "TMA operand needs a 16-byte aligned base and a row pitch that is a multiple of 8 elements");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PRL_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %s%lld)", "", (long long)r);
+  return PRL_OK;
+}
+
+// operand description: K-major => stored [rows, K]; MN-major => stored [K, rows]
+static int make_operand_map(CUtensorMap* map, const void* base, bool mn_major, int64_t rows, int64_t K, int64_t ld, int block_rows) {
+  if (!mn_major) return make_tmap(map, base, K, rows, ld, BLOCK_K, block_rows);
+  return make_tmap(map, base, rows, K, ld, 64, BLOCK_K);
+}
+
+static long env_long(const char* name, long dflt) {
+  const char* s = getenv(name);
+  return s ? strtol(s, nullptr, 0) : dflt;
+}
+
+static void make_desc_defaults(GemmParams& p, bool a_mn, bool b_mn) {
+  // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused (16 B); one UMMA_K step = +32 B.
+  // MN-major SW128: 64-element MN slabs BLOCK_K*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
+  //                 one UMMA_K step (16 k rows) = +2048 B.
+  const uint32_t mn_lbo = (uint32_t)env_long("PRL_DEBUG_MN_LBO", BLOCK_K * 128);
+  const uint32_t mn_sbo = (uint32_t)env_long("PRL_DEBUG_MN_SBO", 1024);
+  const uint32_t mn_kstep = (uint32_t)env_long("PRL_DEBUG_MN_KSTEP", UMMA_K * 128);
+  p.a_desc_hi = a_mn ? ptx::make_smem_desc_hi_sw128(mn_lbo, mn_sbo) : ptx::make_smem_desc_hi_sw128(16, 1024);
+  p.b_desc_hi = b_mn ? ptx::make_smem_desc_hi_sw128(mn_lbo, mn_sbo) : ptx::make_smem_desc_hi_sw128(16, 1024);
+  p.a_kstep = a_mn ? mn_kstep : UMMA_K * 2;
+  p.b_kstep = b_mn ? mn_kstep : UMMA_K * 2;
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const GemmParams& p, cudaStream_t st, const char* name) {
+  static bool attr_set = false;
+  auto kern = gemm_kernel<A_MN, B_MN, EPI>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    attr_set = true;
+  }
+  int grid = sm_count();
+  if (grid > p.num_items) grid = p.num_items;
+  if (grid < 1) return PRL_OK;
+  kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
+  return check_launch(name);
+}
+
+static void set_tiling(GemmParams& p, int64_t M, int64_t N, int64_t K) {
+  p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  p.n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
+  p.k_blocks = (int)((K + BLOCK_K - 1) / BLOCK_K);
+}
+
+// one item per output tile, m-tiles in bands of 8 for L2 reuse of the B operand
+static void schedule_tiles(GemmParams& p) {
+  p.tiles_per_split = 1;
+  p.n_splits = p.n_tiles;
+  p.group_m = (int)env_long("PRL_GROUP_M", 8);
+  p.num_items = p.m_tiles * p.n_splits;
+}
+
+// items = (m_tile, n-range): pick the number of vocab splits that minimises the static makespan
+static void schedule_sweeps(GemmParams& p, int max_splits) {
+  const int sms = sm_count();
+  int best_ns = 1;
+  long best = -1;
+  const int hi = p.n_tiles < max_splits ? p.n_tiles : max_splits;
+  for (int ns = 1; ns <= hi; ++ns) {
+    const int tps = (p.n_tiles + ns - 1) / ns;
+    const int ns_eff = (p.n_tiles + tps - 1) / tps;
+    const long items = (long)p.m_tiles * ns_eff;
+    const long makespan = ((items + sms - 1) / sms) * tps;
+    if (best < 0 || makespan < best) {
+      best = makespan;
+      best_ns = ns_eff;
+    }
+  }
+  p.tiles_per_split = (p.n_tiles + best_ns - 1) / best_ns;
+  p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.group_m = (int)env_long("PRL_SWEEP_GROUP_M", 32);
+  p.num_items = p.m_tiles * p.n_splits;
+}
+
+constexpr int MAX_SPLITS = 64;
+
+// ------------------------------------------------------------------------------------------------
+// merge of per-split partials -> logp / entropy / lse (or one merged partial per token)
+// ------------------------------------------------------------------------------------------------
+__global__ void merge_partials_kernel(const float4* __restrict__ parts, int nparts, int64_t stride, int64_t T, int shift, float v_shard,
+                                      float* __restrict__ logp, float* __restrict__ entropy, float* __restrict__ lse,
+                                      float4* __restrict__ merged) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t - shift;
+    float m, s, u, zt;
+    if (r < 0) {
+      // shift_logits' all-zero row (rl/loss.py:55-56): z == 0 over the whole shard
+      m = 0.f, s = v_shard, u = 0.f, zt = 0.f;
+    } else {
+      m = -INFINITY, s = 0.f, u = 0.f, zt = 0.f;
+      for (int i = 0; i < nparts; ++i) {
+        const float4 q = parts[(int64_t)i * stride + r];
+        const float mn = fmaxf(m, q.x);
+        if (mn == -INFINITY) continue;
+        const float ea = __expf(m - mn), eb = __expf(q.x - mn);
+        s = s * ea + q.y * eb;
+        u = u * ea + q.z * eb;
+        zt += q.w;
+        m = mn;
+      }
+    }
+    if (merged) merged[t] = make_float4(m, s, u, zt);
+    const float l = m + logf(s);
+    if (lse) lse[t] = l;
+    if (logp) logp[t] = zt - l;
+    if (entropy) entropy[t] = l - u / s;
+  }
+}
+
+static int launch_merge(const float4* parts, int nparts, int64_t stride, int64_t T, int shift, float v_shard, float* logp, float* entropy,
+                        float* lse, float4* merged, cudaStream_t st) {
+  if (T <= 0) return PRL_OK;
+  const int64_t need = (T + 255) / 256, cap = (int64_t)sm_count() * 4;
+  merge_partials_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(parts, nparts, stride, T, shift, v_shard, logp, entropy, lse, merged);
+  return check_launch("merge_partials_kernel");
+}
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace prl
+
+using namespace prl;
+
+extern "C" {
+
+size_t prl_lmhead_fwd_workspace_bytes(int64_t T, int32_t H, int64_t V) {
+  (void)H;
+  (void)V;
+  return (size_t)MAX_SPLITS * (size_t)round_up(T > 0 ? T : 1, BLOCK_M) * sizeof(float4) + 256;
+}
+
+int prl_lmhead_fwd(const void* hidden, const void* weight, const int64_t* ids, int64_t T, int32_t H, int64_t V, int64_t v_offset,
+                   int64_t V_total, float inv_temp, int32_t shift, int32_t round_bf16, float* logp, float* entropy, float* lse,
+                   float* partials, void* workspace, size_t workspace_bytes, void* stream) {
+  PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_fwd: bad sizes");
+  PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_fwd: shift must be 0 or 1");
+  PRL_REQUIRE(v_offset >= 0 && v_offset + V <= V_total, PRL_ERR_BAD_ARG, "lmhead_fwd: vocab shard outside [0, V_total)");
+  if (T == 0) return PRL_OK;
+  PRL_REQUIRE(hidden && weight && ids && workspace, PRL_ERR_BAD_ARG, "lmhead_fwd: null pointer");
+  PRL_REQUIRE(H % 8 == 0, PRL_ERR_UNSUPPORTED, "lmhead_fwd: H must be a multiple of 8 (16-byte TMA row pitch)");
+  PRL_REQUIRE(workspace_bytes >= prl_lmhead_fwd_workspace_bytes(T, H, V), PRL_ERR_WORKSPACE, "lmhead_fwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = T - shift;  // source rows that feed an output position
+  float4* parts = reinterpret_cast<float4*>(workspace);
+  const int64_t stride = round_up(T, BLOCK_M);
+  int nparts = 0;
+  if (rows > 0) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = make_operand_map(&p.tma_a, hidden, false, rows, H, H, BLOCK_M);
+    if (rc) return rc;
+    rc = make_operand_map(&p.tma_b, weight, false, V, H, H, BLOCK_N);
+    if (rc) return rc;
+    set_tiling(p, rows, V, H);
+    schedule_sweeps(p, MAX_SPLITS);
+    make_desc_defaults(p, false, false);
+    p.epi.m_rows = rows;
+    p.epi.n_cols = V;
+    p.epi.ids = ids;
+    p.epi.T = T;
+    p.epi.shift = shift;
+    p.epi.round_bf16 = round_bf16;
+    p.epi.col_base = v_offset;
+    p.epi.inv_temp = inv_temp;
+    p.epi.partials = parts;
+    p.epi.part_stride = stride;
+    rc = launch_gemm<false, false, EPI_STATS>(p, st, "lmhead_fwd_kernel");
+    if (rc) return rc;
+    nparts = p.n_splits;
+  }
+  return launch_merge(parts, nparts, stride, T, shift, (float)V, logp, entropy, lse, reinterpret_cast<float4*>(partials), st);
+}
+
+int prl_lmhead_merge_partials(const float* partials, int32_t nparts, int64_t T, float* logp, float* entropy, float* lse, void* stream) {
+  PRL_REQUIRE(nparts >= 1 && T >= 0, PRL_ERR_BAD_ARG, "merge_partials: bad sizes");
+  if (T == 0) return PRL_OK;
+  PRL_REQUIRE(partials, PRL_ERR_BAD_ARG, "merge_partials: null pointer");
+  PRL_REQUIRE((reinterpret_cast<uintptr_t>(partials) & 15) == 0, PRL_ERR_BAD_ARG, "merge_partials: partials must be 16-byte aligned");
+  return launch_merge(reinterpret_cast<const float4*>(partials), nparts, T, T, 0, 0.f, logp, entropy, lse, nullptr, (cudaStream_t)stream);
+}
+
+static int64_t pick_vchunk(int64_t V, int64_t vchunk) {
+  if (vchunk <= 0) vchunk = env_long("PRL_VCHUNK", 8192);
+  vchunk = round_up(vchunk, BLOCK_N);
+  const int64_t vpad = round_up(V, BLOCK_N);
+  return vchunk < vpad ? vchunk : vpad;
+}
+
+size_t prl_lmhead_bwd_workspace_bytes(int64_t T, int32_t H, int64_t V, int64_t vchunk) {
+  const int64_t vc = pick_vchunk(V, vchunk);
+  const size_t dz = (size_t)round_up(T > 0 ? T : 1, BLOCK_M) * (size_t)vc * 2;
+  const size_t dh = (size_t)(T > 0 ? T : 1) * (size_t)H * 4;
+  return round_up((int64_t)dz, 1024) + round_up((int64_t)dh, 1024) + 1024;
+}
+
+int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T, int32_t H,
+                   int64_t V, int64_t v_offset, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden, int32_t d_hidden_f32,
+                   void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_bwd: bad sizes");
+  PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_bwd: shift must be 0 or 1");
+  PRL_REQUIRE(d_weight_dtype == PRL_DT_BF16 || d_weight_dtype == PRL_DT_F32, PRL_ERR_BAD_ARG, "lmhead_bwd: bad d_weight dtype");
+  if (T == 0) return PRL_OK;
+  PRL_REQUIRE(hidden && weight && ids && lse && dlogp && workspace, PRL_ERR_BAD_ARG, "lmhead_bwd: null pointer");
+  PRL_REQUIRE(H % 8 == 0, PRL_ERR_UNSUPPORTED, "lmhead_bwd: H must be a multiple of 8 (16-byte TMA row pitch)");
+  PRL_REQUIRE(workspace_bytes >= prl_lmhead_bwd_workspace_bytes(T, H, V, vchunk), PRL_ERR_WORKSPACE, "lmhead_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t vc = pick_vchunk(V, vchunk);
+  const int64_t nchunks = (V + vc - 1) / vc;
+  const int64_t t_pad = round_up(T, BLOCK_M);
+  __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(workspace);
+  float* dh_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + round_up(t_pad * vc * 2, 1024));
+  const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(weight);
+
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int64_t c0 = c * vc;
+    const int64_t vce = (V - c0) < vc ? (V - c0) : vc;
+    // ---- K1: recompute the logits tile by tile, emit dlogits (bf16) for this vocab chunk ----
+    {
+      GemmParams p;
+      memset(&p, 0, sizeof(p));
+      int rc = make_operand_map(&p.tma_a, hidden, false, T, H, H, BLOCK_M);
+      if (rc) return rc;
+      rc = make_operand_map(&p.tma_b, W + c0 * H, false, vce, H, H, BLOCK_N);
+      if (rc) return rc;
+      set_tiling(p, T, vce, H);
+      schedule_sweeps(p, MAX_SPLITS);
+      make_desc_defaults(p, false, false);
+      p.epi.m_rows = T;
+      p.epi.n_cols = vce;
+      p.epi.ids = ids;
+      p.epi.T = T;
+      p.epi.shift = shift;
+      p.epi.round_bf16 = round_bf16;
+      p.epi.col_base = v_offset + c0;
+      p.epi.inv_temp = inv_temp;
+      p.epi.lse = lse;
+      p.epi.dlogp = dlogp;
+      p.epi.dz = dz;
+      p.epi.ldz = vc;
+      rc = launch_gemm<false, false, EPI_DZ>(p, st, "lmhead_bwd_dz_kernel");
+      if (rc) return rc;
+    }
+    // ---- K2: d_hidden[T,H] += dz[T,vce] x W[c0:c0+vce, :]   (A K-major, B MN-major) ----
+    if (d_hidden) {
+      GemmParams p;
+      memset(&p, 0, sizeof(p));
+      int rc = make_operand_map(&p.tma_a, dz, false, T, vce, vc, BLOCK_M);
+      if (rc) return rc;
+      rc = make_operand_map(&p.tma_b, W + c0 * H, true, H, vce, H, BLOCK_N);
+      if (rc) return rc;
+      set_tiling(p, T, H, vce);
+      schedule_tiles(p);
+      make_desc_defaults(p, false, true);
+      p.epi.m_rows = T;
+      p.epi.n_cols = H;
+      p.epi.ldc = H;
+      const bool first = (c == 0), last = (c == nchunks - 1);
+      if (d_hidden_f32) {
+        p.epi.c_f32 = reinterpret_cast<float*>(d_hidden);
+        p.epi.flags = ST_STORE_F32 | (first ? 0 : ST_LOAD_F32);
+      } else {
+        p.epi.c_f32 = dh_acc;
+        p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_hidden);
+        p.epi.flags = (first ? 0 : ST_LOAD_F32) | (last ? ST_STORE_BF16 : ST_STORE_F32);
+      }
+      rc = launch_gemm<false, true, EPI_STORE>(p, st, "lmhead_bwd_dhidden_kernel");
+      if (rc) return rc;
+    }
+    // ---- K3: d_weight[c0:c0+vce, H] (+)= dz^T x hidden   (both MN-major) ----
+    if (d_weight) {
+      GemmParams p;
+      memset(&p, 0, sizeof(p));
+      int rc = make_operand_map(&p.tma_a, dz, true, vce, T, vc, BLOCK_M);
+      if (rc) return rc;
+      rc = make_operand_map(&p.tma_b, hidden, true, H, T, H, BLOCK_N);
+      if (rc) return rc;
+      set_tiling(p, vce, H, T);
+      schedule_tiles(p);
+      make_desc_defaults(p, true, true);
+      p.epi.m_rows = vce;
+      p.epi.n_cols = H;
+      p.epi.ldc = H;
+      if (d_weight_dtype == PRL_DT_F32) {
+        p.epi.c_f32 = reinterpret_cast<float*>(d_weight) + c0 * H;
+        p.epi.flags = ST_STORE_F32 | (accumulate_dw ? ST_LOAD_F32 : 0);
+      } else {
+        p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_weight) + c0 * H;
+        p.epi.flags = ST_STORE_BF16 | (accumulate_dw ? ST_LOAD_BF16 : 0);
+      }
+      rc = launch_gemm<true, true, EPI_STORE>(p, st, "lmhead_bwd_dweight_kernel");
+      if (rc) return rc;
+    }
+  }
+  return PRL_OK;
+}
+
+int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn_major, int32_t b_mn_major,
+                      int32_t accumulate, void* stream) {
+  PRL_REQUIRE(M >= 1 && N >= 1 && K >= 1, PRL_ERR_BAD_ARG, "gemm: bad sizes");
+  PRL_REQUIRE(A && B && C, PRL_ERR_BAD_ARG, "gemm: null pointer");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = make_operand_map(&p.tma_a, A, a_mn_major != 0, M, K, a_mn_major ? M : K, BLOCK_M);
+  if (rc) return rc;
+  rc = make_operand_map(&p.tma_b, B, b_mn_major != 0, N, K, b_mn_major ? N : K, BLOCK_N);
+  if (rc) return rc;
+  set_tiling(p, M, N, K);
+  schedule_tiles(p);
+  make_desc_defaults(p, a_mn_major != 0, b_mn_major != 0);
+  p.epi.m_rows = M;
+  p.epi.n_cols = N;
+  p.epi.ldc = N;
+  p.epi.c_f32 = C;
+  p.epi.flags = ST_STORE_F32 | (accumulate ? ST_LOAD_F32 : 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!a_mn_major && !b_mn_major) return launch_gemm<false, false, EPI_STORE>(p, st, "gemm_kk");
+  if (!a_mn_major && b_mn_major) return launch_gemm<false, true, EPI_STORE>(p, st, "gemm_km");
+  if (a_mn_major && !b_mn_major) return launch_gemm<true, false, EPI_STORE>(p, st, "gemm_mk");
+  return launch_gemm<true, true, EPI_STORE>(p, st, "gemm_mm");
+}
+
+}  // extern "C"

@@ -1,0 +1,510 @@
+// HBM/latency-bound kernels of the RL loss path: group advantages, segment boundaries, packed clipped
+// importance-ratio loss (+ its gradient), and the API-compat row statistics on materialised logits.
+// Reference behaviour (file:line relative to the reference root) is cited at each kernel.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace prl {
+
+ErrState& err_state() {
+  static thread_local ErrState s = {{0}, 0};
+  return s;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// advantages: one warp per group.  src/prime_rl/orchestrator/advantage.py:18,32,41-43,55-57.
+// fp32 sum order ("L8"): lane accumulators acc[j] = x[j] + x[j+8] + ... (j < 8, left to right), then
+// acc[0] + acc[1] + ... + acc[7], then the len%8 tail left to right.  Explicit __fadd_rn/__fmul_rn/
+// __fdiv_rn keep nvcc from contracting into FMAs, so the result is bit-identical to the oracle.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum_l8(const float* __restrict__ x, int G, int lane, bool weighted,
+                                             const int64_t* __restrict__ w) {
+  const int n8 = (G / 8) * 8;
+  float acc = 0.f;
+  bool first = true;
+  for (int c = 0; c < n8; c += 32) {
+    const int i = c + lane;
+    float v = 0.f;
+    if (i < n8) {
+      v = x[i];
+      if (weighted) v = __fmul_rn(v, (float)w[i]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float t = __shfl_sync(FULL, v, (lane & 7) + 8 * q);
+      if (c + 8 * q < n8) {
+        acc = first ? t : __fadd_rn(acc, t);
+        first = false;
+      }
+    }
+  }
+  float s;
+  if (n8 > 0) {
+    s = __shfl_sync(FULL, acc, 0);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) s = __fadd_rn(s, __shfl_sync(FULL, acc, j));
+  } else {
+    s = 0.f;
+  }
+  for (int i = n8; i < G; ++i) {
+    float v = x[i];
+    if (weighted) v = __fmul_rn(v, (float)w[i]);
+    s = __fadd_rn(s, v);
+  }
+  return s;
+}
+
+__global__ void __launch_bounds__(256) advantages_kernel(const float* __restrict__ rewards, const int64_t* __restrict__ lengths,
+                                                         int64_t ngroups, int G, int kind, float* __restrict__ out,
+                                                         const int64_t* __restrict__ tok_offsets, float* __restrict__ token_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups; g += warps_total) {
+    const float* r = rewards + g * G;
+    float base;
+    if (kind == PRL_ADV_OPO) {
+      const int64_t* w = lengths + g * G;
+      const float num = warp_sum_l8(r, G, lane, true, w);
+      // weights.sum(): same order on the fp32-converted lengths
+      const int n8 = (G / 8) * 8;
+      float acc = 0.f;
+      bool first = true;
+      for (int c = 0; c < n8; c += 32) {
+        const int i = c + lane;
+        float v = (i < n8) ? (float)w[i] : 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float t = __shfl_sync(FULL, v, (lane & 7) + 8 * q);
+          if (c + 8 * q < n8) {
+            acc = first ? t : __fadd_rn(acc, t);
+            first = false;
+          }
+        }
+      }
+      float den = 0.f;
+      if (n8 > 0) {
+        den = __shfl_sync(FULL, acc, 0);
+#pragma unroll
+        for (int j = 1; j < 8; ++j) den = __fadd_rn(den, __shfl_sync(FULL, acc, j));
+      }
+      for (int i = n8; i < G; ++i) den = __fadd_rn(den, (float)w[i]);
+      base = __fdiv_rn(num, den);
+    } else {
+      base = __fdiv_rn(warp_sum_l8(r, G, lane, false, nullptr), (float)G);
+    }
+    for (int i = lane; i < G; i += 32) {
+      float a = __fsub_rn(r[i], base);
+      if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = fmaxf(a, 0.f);
+      if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
+      out[g * G + i] = a;
+    }
+    if (token_out != nullptr) {
+      __syncwarp();
+      for (int i = 0; i < G; ++i) {
+        const int64_t idx = g * G + i;
+        float a = __fsub_rn(r[i], base);
+        if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = fmaxf(a, 0.f);
+        if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
+        const int64_t t0 = tok_offsets[idx], t1 = tok_offsets[idx + 1];
+        for (int64_t t = t0 + lane; t < t1; t += 32) token_out[t] = a;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// segment boundaries: src/prime_rl/trainer/utils.py:36-69.  Boundary at i iff pos[i]==0 && pos[i-1]!=0
+// && i+1<T && pos[i+1]==1 (:54-60).  One CTA walks the row in 1024-token strips and appends the
+// boundaries in order (ballot + warp-count prefix), so the reference's O(T) host/device syncs become
+// one launch.  T <= a few 10^4: latency-bound by design, one CTA is the right size.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) segments_kernel(const int64_t* __restrict__ pos, int64_t T, int32_t* __restrict__ cu,
+                                                        int32_t* __restrict__ nseg, int32_t max_seg) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    base = 1;
+    cu[0] = 0;
+  }
+  __syncthreads();
+  for (int64_t s0 = 0; s0 < T; s0 += 1024) {
+    const int64_t i = s0 + threadIdx.x;
+    bool b = false;
+    if (i >= 1 && i + 1 < T) b = (pos[i] == 0) && (pos[i - 1] != 0) && (pos[i + 1] == 1);
+    const unsigned bal = __ballot_sync(FULL, b);
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < wid; ++w) off += warp_cnt[w];
+    if (b) {
+      const int slot = off + __popc(bal & ((1u << lane) - 1));
+      if (slot <= max_seg - 1) cu[slot] = (int32_t)i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 32; ++w) tot += warp_cnt[w];
+      base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int n = base;  // number of segments
+    if (n <= max_seg) {
+      cu[n] = (int32_t)T;
+      *nseg = n;
+    } else {
+      *nseg = -n;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// packed loss.  src/prime_rl/trainer/rl/loss.py:61-124.
+// token mode (:98-104): flat grid-stride pass, 29 B/token, per-CTA partial sums reduced in a fixed order.
+// sequence mode (:92-96,107-108): one CTA per segment, two passes over the segment (second hits L1/L2).
+// dlogp is what autograd would produce (clamp(max=) passes gradient at equality).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+  __syncthreads();
+  if (lane == 0) sh[wid] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+  return t;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256) loss_token_kernel(const float* __restrict__ logp, const float* __restrict__ old,
+                                                         const float* __restrict__ adv, const uint8_t* __restrict__ mask, int64_t T,
+                                                         float clip, float inv_scale, float* __restrict__ ratio,
+                                                         float* __restrict__ clipped, float* __restrict__ is_clipped,
+                                                         float* __restrict__ dlogp, double* __restrict__ partial) {
+  __shared__ double sh[8];
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t T4 = T / 4;
+  const bool vec_ok = ((((uintptr_t)logp | (uintptr_t)old | (uintptr_t)adv | (uintptr_t)ratio | (uintptr_t)clipped |
+                         (uintptr_t)is_clipped | (uintptr_t)dlogp) &
+                        15) == 0) &&
+                      (((uintptr_t)mask & 3) == 0);
+  int64_t done = 0;
+  if (vec_ok) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < T4; q += stride) {
+      const float4 lp = reinterpret_cast<const float4*>(logp)[q];
+      const float4 ol = reinterpret_cast<const float4*>(old)[q];
+      const float4 av = reinterpret_cast<const float4*>(adv)[q];
+      const uchar4 mk = reinterpret_cast<const uchar4*>(mask)[q];
+      const float l[4] = {lp.x, lp.y, lp.z, lp.w}, o[4] = {ol.x, ol.y, ol.z, ol.w}, a[4] = {av.x, av.y, av.z, av.w};
+      const bool m[4] = {mk.x != 0, mk.y != 0, mk.z != 0, mk.w != 0};
+      float r[4], c[4], f[4], g[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        r[k] = expf(l[k] - o[k]);
+        c[k] = fminf(r[k], clip);
+        f[k] = (r[k] > clip) ? 1.f : 0.f;
+        g[k] = (m[k] && r[k] <= clip) ? (-a[k] * r[k]) * inv_scale : 0.f;
+        if (m[k]) acc += (double)(-c[k] * a[k]);
+      }
+      reinterpret_cast<float4*>(ratio)[q] = make_float4(r[0], r[1], r[2], r[3]);
+      reinterpret_cast<float4*>(clipped)[q] = make_float4(c[0], c[1], c[2], c[3]);
+      reinterpret_cast<float4*>(is_clipped)[q] = make_float4(f[0], f[1], f[2], f[3]);
+      reinterpret_cast<float4*>(dlogp)[q] = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    done = T4 * 4;
+  }
+  for (int64_t t = done + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += stride) {
+    const float r = expf(logp[t] - old[t]);
+    const float c = fminf(r, clip);
+    const bool m = mask[t] != 0;
+    ratio[t] = r;
+    clipped[t] = c;
+    is_clipped[t] = (r > clip) ? 1.f : 0.f;
+    dlogp[t] = (m && r <= clip) ? (-adv[t] * r) * inv_scale : 0.f;
+    if (m) acc += (double)(-c * adv[t]);
+  }
+  const double tot = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(512) loss_seq_kernel(const float* __restrict__ logp, const float* __restrict__ old,
+                                                       const float* __restrict__ adv, const uint8_t* __restrict__ mask,
+                                                       const int32_t* __restrict__ cu, int length_norm, float clip, float inv_scale,
+                                                       float* __restrict__ ratio, float* __restrict__ clipped,
+                                                       float* __restrict__ is_clipped, float* __restrict__ dlogp,
+                                                       double* __restrict__ partial) {
+  __shared__ double sh[16];
+  __shared__ float coef_sh;
+  const int seg = blockIdx.x;
+  const int t0 = cu[seg], t1 = cu[seg + 1];
+  double sd = 0.0, sa = 0.0, sn = 0.0;
+  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+    if (mask[t]) {
+      sd += (double)(logp[t] - old[t]);
+      sa += (double)adv[t];
+      sn += 1.0;
+    }
+  }
+  const double Sd = block_sum(sd, sh);
+  const double Sa = block_sum(sa, sh);
+  const double Sn = block_sum(sn, sh);
+  if (threadIdx.x == 0) {
+    const float n = fmaxf((float)Sn, 1.f);
+    float L = (float)Sd;
+    if (length_norm) L = L / n;
+    const float pre = L;
+    L = fminf(L, 10.f);
+    const float r = expf(L);
+    const float c = fminf(r, clip);
+    ratio[seg] = r;
+    clipped[seg] = c;
+    is_clipped[seg] = (r > clip) ? 1.f : 0.f;
+    const float mean_a = (float)Sa / n;
+    partial[seg] = (double)(-c * mean_a);
+    float coef = -mean_a * r;
+    if (!(r <= clip) || !(pre <= 10.f)) coef = 0.f;
+    if (length_norm) coef = coef / n;
+    coef_sh = coef * inv_scale;
+  }
+  __syncthreads();
+  const float coef = coef_sh;
+  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) dlogp[t] = mask[t] ? coef : 0.f;
+}
+
+// sums partial[0..n) left to right (the reference adds segment losses in order, loss.py:110) and scales
+__global__ void loss_finalize_kernel(const double* __restrict__ partial, int n, double inv_scale, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += partial[i];
+    *loss = (float)(t * inv_scale);
+  }
+}
+
+__global__ void scale_kernel(const float* __restrict__ a, const float* __restrict__ scale, float* __restrict__ out, int64_t n) {
+  const float s = *scale;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] * s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// API-compat statistics on materialised fp32 logits: one CTA per row, one pass (4 B/logit), online
+// (max, sum-exp, sum exp*z).  rl/loss.py:26-30 (logp), :43-47 (entropy), :51-58 (shift).
+// ------------------------------------------------------------------------------------------------
+struct Stat {
+  float m, s, u;
+};
+__device__ __forceinline__ Stat stat_merge(Stat a, Stat b) {
+  const float m = fmaxf(a.m, b.m);
+  if (m == -INFINITY) return a;
+  const float ea = __expf(a.m - m), eb = __expf(b.m - m);
+  Stat r;
+  r.m = m;
+  r.s = a.s * ea + b.s * eb;
+  r.u = a.u * ea + b.u * eb;
+  return r;
+}
+__device__ __forceinline__ void stat_push(Stat& st, float z) {
+  if (z > st.m) {
+    const float e = __expf(st.m - z);
+    st.s = st.s * e + 1.f;
+    st.u = st.u * e + z;
+    st.m = z;
+  } else {
+    const float e = __expf(z - st.m);
+    st.s += e;
+    st.u += e * z;
+  }
+}
+
+__global__ void __launch_bounds__(256) logits_stats_kernel(const float* __restrict__ logits, const int64_t* __restrict__ ids,
+                                                           int64_t rows, int64_t seq, int64_t V, float inv_temp, int shift,
+                                                           float* __restrict__ logp, float* __restrict__ entropy) {
+  __shared__ Stat sh[8];
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int64_t p = row % seq;
+    if (shift && p == 0) {
+      if (threadIdx.x == 0) {
+        const float l = logf((float)V);
+        if (logp) logp[row] = -l;
+        if (entropy) entropy[row] = l;
+      }
+      continue;
+    }
+    const float* src = logits + (row - (shift ? 1 : 0)) * V;
+    Stat st = {-INFINITY, 0.f, 0.f};
+    if ((((uintptr_t)src) & 15) == 0) {
+      const int64_t V4 = V / 4;
+      for (int64_t q = threadIdx.x; q < V4; q += blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(src)[q];
+        stat_push(st, x.x * inv_temp);
+        stat_push(st, x.y * inv_temp);
+        stat_push(st, x.z * inv_temp);
+        stat_push(st, x.w * inv_temp);
+      }
+      for (int64_t v = V4 * 4 + threadIdx.x; v < V; v += blockDim.x) stat_push(st, src[v] * inv_temp);
+    } else {
+      for (int64_t v = threadIdx.x; v < V; v += blockDim.x) stat_push(st, src[v] * inv_temp);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Stat other;
+      other.m = __shfl_down_sync(FULL, st.m, o);
+      other.s = __shfl_down_sync(FULL, st.s, o);
+      other.u = __shfl_down_sync(FULL, st.u, o);
+      st = stat_merge(st, other);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = st;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      Stat t = sh[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = stat_merge(t, sh[w]);
+      const float lse = t.m + logf(t.s);
+      if (logp && ids) logp[row] = src[ids[row]] * inv_temp - lse;
+      if (entropy) entropy[row] = lse - t.u / t.s;
+    }
+  }
+}
+
+}  // namespace prl
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+using namespace prl;
+
+extern "C" {
+
+int prl_version(void) { return 100; }
+
+const char* prl_strerror(int code) {
+  switch (code) {
+    case PRL_OK: return "ok";
+    case PRL_ERR_BAD_ARG: return "bad argument";
+    case PRL_ERR_UNSUPPORTED: return "unsupported shape or configuration";
+    case PRL_ERR_CUDA: return "CUDA error";
+    case PRL_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown error";
+  }
+}
+
+const char* prl_last_error_detail(void) { return err_state().detail; }
+
+int64_t prl_launch_count(int32_t reset) {
+  const int64_t n = err_state().launches;
+  if (reset) err_state().launches = 0;
+  return n;
+}
+
+int prl_advantages_f32(const float* rewards, const int64_t* lengths, int64_t n, int32_t group, int32_t kind, float* out,
+                       const int64_t* tok_offsets, float* token_out, void* stream) {
+  PRL_REQUIRE(n >= 0 && group >= 1, PRL_ERR_BAD_ARG, "advantages: n >= 0 and group >= 1 required");
+  PRL_REQUIRE(n % group == 0, PRL_ERR_BAD_ARG, "advantages: len(rewards) % samples_per_problem != 0");
+  PRL_REQUIRE(kind >= 0 && kind <= 3, PRL_ERR_BAD_ARG, "advantages: unknown advantage kind");
+  if (n == 0) return PRL_OK;
+  PRL_REQUIRE(rewards && out, PRL_ERR_BAD_ARG, "advantages: null pointer");
+  PRL_REQUIRE(kind != PRL_ADV_OPO || lengths, PRL_ERR_BAD_ARG, "advantages: opo needs completion lengths");
+  PRL_REQUIRE((token_out == nullptr) || tok_offsets, PRL_ERR_BAD_ARG, "advantages: token_out needs tok_offsets");
+  const int64_t ngroups = n / group;
+  const int64_t blocks_needed = (ngroups + 7) / 8;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  advantages_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rewards, lengths, ngroups, group, kind, out, tok_offsets, token_out);
+  return check_launch("advantages_kernel");
+}
+
+int prl_segments_from_position_ids(const int64_t* position_ids, int64_t T, int32_t* cu_seqlens, int32_t* nseg, int32_t max_seg,
+                                   void* stream) {
+  PRL_REQUIRE(position_ids && cu_seqlens && nseg, PRL_ERR_BAD_ARG, "segments: null pointer");
+  PRL_REQUIRE(T >= 1 && T < (int64_t)1 << 31 && max_seg >= 1, PRL_ERR_BAD_ARG, "segments: 1 <= T < 2^31 and max_seg >= 1 required");
+  segments_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(position_ids, T, cu_seqlens, nseg, max_seg);
+  return check_launch("segments_kernel");
+}
+
+static inline int loss_token_grid(int64_t T) {
+  const int64_t need = (T / 4 + 255) / 256 + 1;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(need < cap ? need : cap);
+}
+
+size_t prl_loss_workspace_bytes(int64_t T, int32_t nseg) {
+  const int64_t a = (int64_t)148 * 8 * 2, b = nseg > 0 ? nseg : 1;
+  (void)T;
+  return sizeof(double) * (size_t)(a > b ? a : b);
+}
+
+int prl_loss_packed_fwd(const float* logp, const float* old_logp, const float* adv, const uint8_t* mask, const int32_t* cu_seqlens,
+                        int32_t nseg, int64_t T, int32_t mode, int32_t length_norm, float clip_ratio, double loss_scale, float* loss,
+                        float* ratio, float* clipped, float* is_clipped, float* dlogp, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  PRL_REQUIRE(T >= 0 && nseg >= 0, PRL_ERR_BAD_ARG, "loss: negative size");
+  PRL_REQUIRE(loss && workspace, PRL_ERR_BAD_ARG, "loss: null loss/workspace pointer");
+  PRL_REQUIRE(mode == PRL_RATIO_TOKEN || mode == PRL_RATIO_SEQUENCE, PRL_ERR_BAD_ARG, "loss: unknown ratio_type");
+  PRL_REQUIRE(workspace_bytes >= prl_loss_workspace_bytes(T, nseg), PRL_ERR_WORKSPACE, "loss: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const double S = loss_scale > 1.0 ? loss_scale : 1.0;  // max(loss_scale, 1), loss.py:118
+  double* partial = reinterpret_cast<double*>(workspace);
+  if (T == 0) {
+    loss_finalize_kernel<<<1, 32, 0, st>>>(partial, 0, 1.0 / S, loss);
+    return check_launch("loss_finalize_kernel");
+  }
+  PRL_REQUIRE(logp && old_logp && adv && mask && ratio && clipped && is_clipped && dlogp, PRL_ERR_BAD_ARG, "loss: null pointer");
+  int nparts;
+  if (mode == PRL_RATIO_TOKEN) {
+    nparts = loss_token_grid(T);
+    loss_token_kernel<<<nparts, 256, 0, st>>>(logp, old_logp, adv, mask, T, clip_ratio, (float)(1.0 / S), ratio, clipped,
+                                              is_clipped, dlogp, partial);
+    int rc = check_launch("loss_token_kernel");
+    if (rc) return rc;
+  } else {
+    PRL_REQUIRE(cu_seqlens && nseg >= 1, PRL_ERR_BAD_ARG, "loss: sequence mode needs cu_seqlens and nseg >= 1");
+    nparts = nseg;
+    loss_seq_kernel<<<nseg, 512, 0, st>>>(logp, old_logp, adv, mask, cu_seqlens, length_norm, clip_ratio, (float)(1.0 / S), ratio,
+                                          clipped, is_clipped, dlogp, partial);
+    int rc = check_launch("loss_seq_kernel");
+    if (rc) return rc;
+  }
+  loss_finalize_kernel<<<1, 32, 0, st>>>(partial, nparts, 1.0 / S, loss);
+  return check_launch("loss_finalize_kernel");
+}
+
+int prl_scale_f32(const float* a, const float* scale, float* out, int64_t n, void* stream) {
+  PRL_REQUIRE(n >= 0, PRL_ERR_BAD_ARG, "scale: negative size");
+  if (n == 0) return PRL_OK;
+  PRL_REQUIRE(a && scale && out, PRL_ERR_BAD_ARG, "scale: null pointer");
+  const int64_t need = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  scale_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(a, scale, out, n);
+  return check_launch("scale_kernel");
+}
+
+int prl_logits_stats_f32(const float* logits, const int64_t* ids, int64_t rows, int64_t seq, int64_t V, float inv_temp,
+                         int32_t shift, float* logp, float* entropy, void* stream) {
+  PRL_REQUIRE(rows >= 0 && seq >= 1 && V >= 1, PRL_ERR_BAD_ARG, "logits_stats: bad sizes");
+  if (rows == 0) return PRL_OK;
+  PRL_REQUIRE(logits, PRL_ERR_BAD_ARG, "logits_stats: null logits");
+  PRL_REQUIRE(logp == nullptr || ids != nullptr, PRL_ERR_BAD_ARG, "logits_stats: logp needs ids");
+  const int64_t cap = (int64_t)sm_count() * 16;
+  logits_stats_kernel<<<(int)(rows < cap ? rows : cap), 256, 0, (cudaStream_t)stream>>>(logits, ids, rows, seq, V, inv_temp, shift,
+                                                                                        logp, entropy);
+  return check_launch("logits_stats_kernel");
+}
+
+}  // extern "C"

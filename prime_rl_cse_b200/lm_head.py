@@ -1,0 +1,155 @@
+"""Fused LM head: hidden x W_lm^T -> (log-prob of the sampled token, entropy) without materialising
+the [T, V] logits, with a recompute-based backward.  Replaces rl/train.py:285-288,302-303 of the
+reference (src/prime_rl/trainer/rl/train.py) and the autograd chain behind `loss.backward()` (:310)."""
+
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def lm_head_forward_raw(hidden, weight, ids, inv_temp, shift=True, round_bf16=True, v_offset=0, v_total=None,
+                        want_partials=False):
+    """hidden [T,H] bf16, weight [V,H] bf16, ids [T] int64 -> (logp, entropy, lse, partials|None)."""
+    lib = _lib.load()
+    T, H = hidden.shape
+    V = weight.shape[0]
+    v_total = V if v_total is None else v_total
+    dev = hidden.device
+    logp = torch.empty(T, dtype=torch.float32, device=dev)
+    ent = torch.empty(T, dtype=torch.float32, device=dev)
+    lse = torch.empty(T, dtype=torch.float32, device=dev)
+    parts = torch.empty(T, 4, dtype=torch.float32, device=dev) if want_partials else None
+    nb = lib.prl_lmhead_fwd_workspace_bytes(T, H, V)
+    ws = _ws(nb, dev)
+    rc = lib.prl_lmhead_fwd(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), T, H, V, v_offset, v_total, float(inv_temp),
+                            1 if shift else 0, 1 if round_bf16 else 0, _lib.ptr(logp), _lib.ptr(ent), _lib.ptr(lse),
+                            _lib.ptr(parts), _lib.ptr(ws), nb, _lib.stream())
+    _lib.check(rc, "prl_lmhead_fwd")
+    return logp, ent, lse, parts
+
+
+def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, round_bf16=True, v_offset=0,
+                         want_dhidden=True, dweight=None, dweight_accumulate=False, want_dweight=True, vchunk=0,
+                         dhidden_f32=False):
+    """Returns (d_hidden [T,H] bf16|fp32|None, d_weight [V,H]).  `dweight` may be a preallocated bf16 or
+    fp32 [V,H] buffer (with `dweight_accumulate` the kernel adds into it: fused gradient accumulation)."""
+    lib = _lib.load()
+    T, H = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    dh = None
+    if want_dhidden:
+        dh = torch.empty(T, H, dtype=torch.float32 if dhidden_f32 else torch.bfloat16, device=dev)
+    if want_dweight and dweight is None:
+        dweight = torch.empty(V, H, dtype=torch.bfloat16, device=dev)
+        dweight_accumulate = False
+    dt = _lib.PRL_DT_BF16
+    if dweight is not None:
+        if dweight.dtype == torch.float32:
+            dt = _lib.PRL_DT_F32
+        elif dweight.dtype != torch.bfloat16:
+            raise ValueError("d_weight must be bf16 or fp32")
+        if tuple(dweight.shape) != (V, H) or not dweight.is_contiguous():
+            raise ValueError("d_weight must be a contiguous [V, H] tensor")
+    nb = lib.prl_lmhead_bwd_workspace_bytes(T, H, V, vchunk)
+    ws = _ws(nb, dev)
+    rc = lib.prl_lmhead_bwd(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), _lib.ptr(lse), _lib.ptr(dlogp), T, H, V, v_offset,
+                            float(inv_temp), 1 if shift else 0, 1 if round_bf16 else 0, _lib.ptr(dh), 1 if dhidden_f32 else 0,
+                            _lib.ptr(dweight), dt, 1 if dweight_accumulate else 0, vchunk, _lib.ptr(ws), nb, _lib.stream())
+    _lib.check(rc, "prl_lmhead_bwd")
+    return dh, dweight
+
+
+class _FusedLMHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, weight, ids, inv_temp, shift, round_bf16, main_grad):
+        lead = hidden.shape[:-1]
+        h2 = hidden.detach().reshape(-1, hidden.shape[-1]).contiguous()
+        w2 = weight.detach().contiguous()
+        i2 = ids.detach().reshape(-1).contiguous().to(torch.int64)
+        logp, ent, lse, _ = lm_head_forward_raw(h2, w2, i2, inv_temp, shift, round_bf16)
+        ctx.save_for_backward(h2, w2, i2, lse)
+        ctx.cfg = (inv_temp, shift, round_bf16, hidden.shape, main_grad)
+        ctx.mark_non_differentiable(ent)
+        return logp.reshape(lead), ent.reshape(lead)
+
+    @staticmethod
+    def backward(ctx, g_logp, _g_ent):
+        h2, w2, i2, lse = ctx.saved_tensors
+        inv_temp, shift, round_bf16, hshape, main_grad = ctx.cfg
+        g = g_logp.detach().reshape(-1).contiguous().float()
+        need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if main_grad is not None and need_w:
+            dh, _ = lm_head_backward_raw(h2, w2, i2, lse, g, inv_temp, shift, round_bf16, want_dhidden=need_h,
+                                         dweight=main_grad, dweight_accumulate=True)
+            dw = None
+        else:
+            dh, dw = lm_head_backward_raw(h2, w2, i2, lse, g, inv_temp, shift, round_bf16, want_dhidden=need_h,
+                                          want_dweight=need_w)
+        return (dh.reshape(hshape) if dh is not None else None), dw, None, None, None, None, None
+
+
+def fused_lm_head_logprobs_entropy(
+    hidden: torch.Tensor,
+    weight: torch.Tensor,
+    input_ids: torch.Tensor,
+    temperature: float,
+    *,
+    shift: bool = True,
+    round_bf16: bool = True,
+    main_grad: torch.Tensor | None = None,
+) -> tuple[torch.Tensor, torch.Tensor]:
+    """hidden [..., T, H] bf16 (final-norm output), weight [V, H] bf16 (`lm_head.weight`), input_ids
+    [..., T] -> (logprobs [..., T] fp32, differentiable w.r.t. hidden and weight; entropy [..., T] fp32,
+    detached).  Equivalent to the reference's
+        logits = lm_head(hidden).float(); shifted = shift_logits(logits) / temperature
+        logprobs = selective_log_softmax(shifted, input_ids); entropy = compute_entropy(shifted)
+    (rl/train.py:285-288,302-303) for one packed row.  `shift` applies to the whole flattened row as the
+    reference's `shift_logits` does for batch size 1 (packed micro-batches, rl/data.py:13-23).
+    `main_grad`: optional fp32/bf16 [V,H] buffer; the weight gradient is then ACCUMULATED into it by the
+    kernel and `weight.grad` is left untouched (fused gradient accumulation across micro-batches)."""
+    _lib.require_cuda(hidden, weight, input_ids)
+    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise ValueError("fused_lm_head_logprobs_entropy needs bf16 hidden and weight (FSDP param_dtype=bf16, model.py:103)")
+    if hidden.shape[:-1] != input_ids.shape:
+        raise ValueError("hidden [..., T, H] and input_ids [..., T] disagree")
+    if hidden.dim() > 2 and hidden.shape[:-2].numel() != 1:
+        raise ValueError("only one packed row per call (micro_batch_size == 1 for packed batches)")
+    return _FusedLMHead.apply(hidden, weight, input_ids, 1.0 / float(temperature), bool(shift), bool(round_bf16), main_grad)
+
+
+class FusedLMHead(nn.Module):
+    """Drop-in replacement MODULE for `model.lm_head` (SURVEY §7 "FSDP integration"): it owns the same
+    `weight` Parameter, so FSDP2's `[lm_head, norm]` group hooks (model.py:126-131) keep firing, and its
+    `forward(hidden)` returns a `[..., T, 2]` tensor (logprob, entropy) where the reference returns
+    logits.  Call `set_context(input_ids, temperature)` right before the model forward."""
+
+    def __init__(self, weight: nn.Parameter, main_grad: torch.Tensor | None = None):
+        super().__init__()
+        self.weight = weight
+        self.main_grad = main_grad
+        self._ctx: tuple[torch.Tensor, float] | None = None
+
+    @classmethod
+    def from_linear(cls, linear: nn.Linear) -> "FusedLMHead":
+        if linear.bias is not None:
+            raise ValueError("lm_head with bias is not supported (Qwen3/Llama heads are bias-free)")
+        return cls(linear.weight)
+
+    def set_context(self, input_ids: torch.Tensor, temperature: float) -> None:
+        self._ctx = (input_ids, float(temperature))
+
+    def forward(self, hidden: torch.Tensor) -> torch.Tensor:
+        if self._ctx is None:
+            raise RuntimeError("FusedLMHead.set_context(input_ids, temperature) must be called before forward")
+        ids, temp = self._ctx
+        self._ctx = None
+        logp, ent = fused_lm_head_logprobs_entropy(hidden, self.weight, ids, temp, main_grad=self.main_grad)
+        return torch.stack([logp, ent], dim=-1)

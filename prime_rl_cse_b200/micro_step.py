@@ -1,0 +1,58 @@
+"""One RL micro-step of the hot path, mirroring src/prime_rl/trainer/rl/train.py:275-310 of the
+reference with the fused kernels: segment detection, fused LM head (log-probs + entropy), packed
+clipped-ratio loss, backward to d_hidden / d_W_lm."""
+
+from __future__ import annotations
+
+from typing import Any
+
+import torch
+
+from .lm_head import fused_lm_head_logprobs_entropy
+from .loss import compute_loss
+from .segments import get_response_lengths
+
+
+def rl_micro_step(
+    hidden: torch.Tensor,
+    lm_head_weight: torch.Tensor,
+    micro_batch: dict[str, Any],
+    loss_config: Any,
+    loss_scale: int,
+    *,
+    backward: bool = True,
+    main_grad: torch.Tensor | None = None,
+    response_lengths: list[int] | None = None,
+) -> dict[str, torch.Tensor]:
+    """`hidden` [1,T,H] bf16 is what the transformer body hands to `lm_head` (requires_grad as the
+    caller wishes); `micro_batch` is a `MicroBatch` (rl/data.py:13-23) whose tensors are already on the
+    device (train.py:275-279).  Returns loss, logprobs, entropy and the three logging tensors of
+    `compute_loss`; with `backward=True` also runs `loss.backward()` (train.py:310)."""
+    input_ids = micro_batch["input_ids"]
+    position_ids = micro_batch["position_ids"]
+    advantages = micro_batch["advantages"]
+    loss_mask = micro_batch["loss_mask"]
+    old_logprobs = micro_batch["logprobs"]
+    temperature = micro_batch["temperature"]
+
+    # train.py:291 -- done first so its single D2H sync happens before the heavy kernels are queued
+    if response_lengths is None:
+        response_lengths = get_response_lengths(position_ids)
+
+    # train.py:285-288 + 302-303
+    logprobs, entropy = fused_lm_head_logprobs_entropy(hidden, lm_head_weight, input_ids, temperature, main_grad=main_grad)
+
+    # train.py:292-299
+    loss, loss_tensors = compute_loss(
+        logprobs=logprobs.squeeze().split(response_lengths),
+        old_logprobs=old_logprobs.squeeze().split(response_lengths),
+        advantages=advantages.squeeze().split(response_lengths),
+        loss_mask=loss_mask.squeeze().split(response_lengths),
+        loss_config=loss_config,
+        loss_scale=loss_scale,
+    )
+    if backward:
+        loss.backward()  # train.py:310
+    out = {"loss": loss.detach(), "logprobs": logprobs.detach(), "entropy": entropy}
+    out.update(loss_tensors)
+    return out

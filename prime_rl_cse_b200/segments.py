@@ -1,0 +1,35 @@
+"""Segment boundaries of a packed row on the GPU (replaces `get_response_lengths`,
+src/prime_rl/trainer/utils.py:36-69, whose host loop costs O(T) device syncs)."""
+
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def segments_from_position_ids(position_ids: torch.Tensor, max_segments: int | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """Returns (cu_seqlens int32 [max_segments+1], nseg int32 [1]) on the device; no host sync."""
+    _lib.require_cuda(position_ids)
+    lib = _lib.load()
+    pos = position_ids.reshape(-1).contiguous().to(torch.int64)
+    T = pos.numel()
+    if max_segments is None:
+        max_segments = max(T // 2 + 1, 1)
+    cu = torch.empty(max_segments + 1, dtype=torch.int32, device=pos.device)
+    nseg = torch.empty(1, dtype=torch.int32, device=pos.device)
+    rc = lib.prl_segments_from_position_ids(_lib.ptr(pos), T, _lib.ptr(cu), _lib.ptr(nseg), max_segments, _lib.stream())
+    _lib.check(rc, "prl_segments_from_position_ids")
+    return cu, nseg
+
+
+def get_response_lengths(position_ids: torch.Tensor) -> list[int]:
+    """Drop-in for the reference function: python list of segment lengths (one D2H copy, one sync)."""
+    if position_ids.numel() == 0:
+        return [0]
+    cu, nseg = segments_from_position_ids(position_ids)
+    n = int(nseg.item())
+    if n < 0:
+        raise RuntimeError("segment table overflow")
+    b = cu[: n + 1].cpu().tolist()
+    return [b[i + 1] - b[i] for i in range(n)]

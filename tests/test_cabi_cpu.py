@@ -1,0 +1,88 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/prl_b200.h declares, validates arguments without a GPU, and the host layer fails loudly
+(no CPU fallback)."""
+
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from prime_rl_cse_b200 import _lib
+
+    return _lib
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "prl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(prl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    L = lib.load()
+    declared = header_symbols()
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/prl_b200.h but not exported"
+    assert sorted(lib.exported_symbols()) == declared, "ctypes signature table and header disagree"
+
+
+def test_version_and_strerror(lib):
+    L = lib.load()
+    assert L.prl_version() >= 100
+    assert L.prl_strerror(0) == b"ok"
+    assert b"argument" in L.prl_strerror(-1)
+    assert b"workspace" in L.prl_strerror(-4)
+
+
+def test_argument_validation_needs_no_gpu(lib):
+    L = lib.load()
+    # n % group != 0 -> PRL_ERR_BAD_ARG before any CUDA call (advantage.py:90's assert)
+    assert L.prl_advantages_f32(None, None, 3, 2, 0, None, None, None, None) == -1
+    assert L.prl_advantages_f32(None, None, 4, 2, 9, None, None, None, None) == -1
+    assert L.prl_advantages_f32(None, None, 0, 2, 0, None, None, None, None) == 0
+    assert L.prl_lmhead_fwd(None, None, None, 8, 12, 100, 0, 100, 1.0, 1, 1, None, None, None, None, None, 0, None) == -1
+    assert L.prl_loss_packed_fwd(None, None, None, None, None, 1, 8, 7, 0, 8.0, 1.0, None, None, None, None, None, None, 0, None) == -1
+    assert L.prl_lmhead_fwd_workspace_bytes(16384, 4096, 151936) >= 64 * 16384 * 16
+    assert L.prl_lmhead_bwd_workspace_bytes(16384, 4096, 151936, 8192) >= 16384 * 8192 * 2
+
+
+def test_no_cpu_fallback():
+    import prime_rl_cse_b200 as P
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.get_response_lengths(torch.arange(8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.compute_loss([torch.zeros(4)], [torch.zeros(4)], [torch.zeros(4)], [torch.ones(4, dtype=torch.bool)], P.LossConfig(), 1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        P.fused_lm_head_logprobs_entropy(torch.zeros(1, 4, 8, dtype=torch.bfloat16), torch.zeros(16, 8, dtype=torch.bfloat16),
+                                         torch.zeros(1, 4, dtype=torch.long), 1.0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "prime_rl_cse_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_loss_config_mirror():
+    import prime_rl_cse_b200 as P
+
+    c = P.LossConfig()
+    assert (c.ratio_type, c.ratio_length_norm, c.clip_ratio) == ("token", False, 8.0)  # rl/config.py:22-27
+    with pytest.raises(ValueError):
+        P.LossConfig(ratio_type="gae")
+    with pytest.raises(ValueError):
+        P.LossConfig(clip_ratio=-1.0)

@@ -1,0 +1,327 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  The CUDA path is called through the
+C-ABI library and compared with the CPU oracle (`oracle/`) and with the golden fixtures produced by
+the unmodified reference.  Tolerances are the ones BASELINE.json's north_star states:
+advantages bit-exact; logp / entropy <= 1e-3 abs; loss <= 1e-4 rel; gradients <= 1e-2 rel-L2."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import LossCfg
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+KINDS = ["drgrpo", "drgrpo-negclipped", "rloo", "opo"]
+
+
+@pytest.fixture(scope="module")
+def P():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import prime_rl_cse_b200 as p
+
+    return p
+
+
+def load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def cu(x, dtype=None):
+    t = torch.as_tensor(np.asarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+# ------------------------------------------------------------------------------- advantages
+def test_advantages_fixtures_bit_exact(P):
+    d = load("advantages.npz")
+    for name in d["names"]:
+        r, ln, grp = d[f"{name}/rewards"], d[f"{name}/lengths"], int(d[f"{name}/group"])
+        for k in KINDS:
+            got = np.float32(P.compute_advantages(r.tolist(), ln.tolist(), grp, k))
+            np.testing.assert_array_equal(got, oracle.advantages(r, ln, grp, k), err_msg=f"{name}/{k} vs oracle")
+            if name.startswith("tol_"):
+                np.testing.assert_allclose(got, d[f"{name}/{k}"], rtol=1e-6, atol=1e-6 * np.abs(r).max())
+            else:
+                np.testing.assert_array_equal(got, d[f"{name}/{k}"], err_msg=f"{name}/{k} vs reference")
+
+
+def test_advantages_large_and_broadcast(P):
+    rng = np.random.default_rng(5)
+    for grp, n in [(16, 1 << 16), (32, 1 << 12), (7, 7 * 100), (1, 5)]:
+        r = rng.standard_normal(n).astype(np.float32)
+        ln = rng.integers(1, 5000, n)
+        for k in KINDS:
+            got = P.compute_advantages_tensor(cu(r), cu(ln), grp, k).cpu().numpy()
+            np.testing.assert_array_equal(got, oracle.advantages(r, ln, grp, k))
+    # fused per-token broadcast (orchestrator/batch.py:44)
+    n, grp = 64, 8
+    r = rng.standard_normal(n).astype(np.float32)
+    ln = rng.integers(1, 50, n)
+    offs = np.concatenate([[0], np.cumsum(ln)])
+    adv, tok = P.compute_advantages_tensor(cu(r), cu(ln), grp, "drgrpo", token_offsets=cu(offs))
+    np.testing.assert_array_equal(tok.cpu().numpy(), np.repeat(adv.cpu().numpy(), ln))
+
+
+def test_advantages_errors(P):
+    with pytest.raises(AssertionError):
+        P.compute_advantages([1.0, 2.0, 3.0], [1, 1, 1], 2, "drgrpo")
+    with pytest.raises(KeyError):
+        P.compute_advantages([1.0, 2.0], [1, 1], 2, "gae")
+    assert P.compute_advantages([], [], 4, "drgrpo") == []
+
+
+# ------------------------------------------------------------------------------- segments
+def test_segments_fixtures(P):
+    d = load("segments.npz")
+    for name in d["names"]:
+        got = P.get_response_lengths(cu(d[f"{name}/position_ids"]))
+        assert got == d[f"{name}/lengths"].tolist(), name
+
+
+def test_segments_long_rows(P):
+    rng = np.random.default_rng(3)
+    for T_target in (4096, 16384, 32768 + 77):
+        lens, tot = [], 0
+        while tot < T_target:
+            n = int(rng.integers(1, 3000))
+            lens.append(n)
+            tot += n
+        pos = np.concatenate([np.arange(n) for n in lens] + [np.zeros(int(rng.integers(0, 9)), dtype=np.int64)])
+        assert P.get_response_lengths(cu(pos).unsqueeze(0)) == oracle.response_lengths(pos)
+
+
+# ------------------------------------------------------------------------------- loss
+CFG = {
+    "token": ("token", False, 8.0),
+    "token_c2": ("token", False, 2.0),
+    "seq": ("sequence", False, 8.0),
+    "seqnorm": ("sequence", True, 8.0),
+}
+
+
+@pytest.mark.parametrize("as_views", [True, False])
+def test_loss_fixtures(P, as_views):
+    d = load("loss.npz")
+    for name in d["names"]:
+        logp, old, adv, mask = (d[f"{name}/{k}"] for k in ("logp", "old", "adv", "mask"))
+        lens = d[f"{name}/lens"].tolist()
+        for cname in d["cfgs"]:
+            cfg = P.LossConfig(*CFG[cname])
+            for k in [k for k in d.files if k.startswith(f"{name}/{cname}/S") and k.endswith("/loss")]:
+                scale = int(k.split("/")[2][1:])
+                pre = f"{name}/{cname}/S{scale}"
+                lp = cu(logp).requires_grad_(True)
+                if as_views:  # what the trainer passes: split views of one tensor (train.py:293-296)
+                    items = [lp.split(lens), cu(old).split(lens), cu(adv).split(lens), cu(mask).split(lens)]
+                else:  # what the reference's unit tests pass: independent tensors
+                    items = [[t.clone() for t in x.split(lens)] for x in (lp, cu(old), cu(adv), cu(mask))]
+                loss, tens = P.compute_loss(*items, cfg, scale)
+                assert loss.shape == ()
+                loss.backward()
+                np.testing.assert_allclose(loss.item(), d[pre + "/loss"], rtol=1e-4, atol=1e-6, err_msg=pre)
+                np.testing.assert_allclose(tens["importance_ratio"].cpu().numpy(), d[pre + "/ratio"], rtol=1e-4)
+                np.testing.assert_allclose(tens["clipped_importance_ratio"].cpu().numpy(), d[pre + "/clipped"], rtol=1e-4)
+                np.testing.assert_array_equal(tens["is_clipped"].cpu().numpy(), d[pre + "/is_clipped"])
+                np.testing.assert_allclose(lp.grad.cpu().numpy(), d[pre + "/dlogp"], rtol=1e-4, atol=1e-7, err_msg=pre)
+
+
+def test_loss_reference_unit_test_shapes(P):
+    # tests/unit/train/rl/test_loss.py:10-42 of the reference, with values checked against the oracle
+    torch.manual_seed(0)
+    for ratio_type, lens in (("token", [50, 30]), ("sequence", [40, 60])):
+        logprobs = [torch.randn(n).cuda() for n in lens]
+        old = [torch.randn(n).cuda() for n in lens]
+        adv = [torch.randn(n).cuda() for n in lens]
+        mask = [torch.ones(n, dtype=torch.bool).cuda() for n in lens]
+        loss, _ = P.compute_loss(logprobs, old, adv, loss_mask=mask, loss_config=P.LossConfig(ratio_type=ratio_type, clip_ratio=10.0),
+                                 loss_scale=1.0)
+        assert loss.shape == ()
+        want = oracle.loss_fwd_bwd(torch.cat(logprobs).cpu().numpy(), torch.cat(old).cpu().numpy(), torch.cat(adv).cpu().numpy(),
+                                   torch.cat(mask).cpu().numpy(), lens, LossCfg(ratio_type, False, 10.0), 1.0, np.float64)[0]
+        np.testing.assert_allclose(loss.item(), want, rtol=1e-4)
+
+
+def test_loss_all_masked_and_big(P):
+    # padding micro-batches: all-False mask, zero advantages, loss_scale 0 (orchestrator/batch.py:153-161)
+    T = 1000
+    z = torch.zeros(T).cuda()
+    loss, tens = P.compute_loss([z.clone().requires_grad_(True)], [z], [z], [torch.zeros(T, dtype=torch.bool).cuda()], P.LossConfig(), 0)
+    assert loss.item() == 0.0 and tens["importance_ratio"].shape == (T,)
+    # config-5 sized row, sequence mode, one 32k segment; token mode 2^20 tokens
+    rng = np.random.default_rng(11)
+    for mode, T, lens in (("sequence", 32768, [32768]), ("token", 1 << 20, [1 << 19, (1 << 19) - 3, 3])):
+        logp = -np.abs(rng.standard_normal(T)).astype(np.float32)
+        old = (logp + 0.02 * rng.standard_normal(T) / (50 if mode == "sequence" else 1)).astype(np.float32)
+        adv = rng.standard_normal(T).astype(np.float32)
+        mask = rng.random(T) < 0.8
+        cfg = P.LossConfig(mode, True, 8.0)
+        lp = cu(logp).requires_grad_(True)
+        loss, tens = P.compute_loss(lp.split(lens), cu(old).split(lens), cu(adv).split(lens), cu(mask).split(lens), cfg, int(mask.sum()))
+        loss.backward()
+        want = oracle.loss_fwd_bwd(logp, old, adv, mask, lens, LossCfg(mode, True, 8.0), int(mask.sum()), np.float64)
+        np.testing.assert_allclose(loss.item(), want[0], rtol=1e-4)
+        np.testing.assert_allclose(tens["importance_ratio"].cpu().numpy(), want[1], rtol=1e-4)
+        assert rel_l2(lp.grad.cpu().numpy(), want[4]) < 1e-4
+
+
+# ------------------------------------------------------------------------------- materialised-logits helpers
+def test_logits_stats_vs_oracle(P):
+    d = load("lmhead.npz")
+    logits, ids = d["kat1/logits"], d["kat1/ids"]
+    for tau in (1.0, 2.0):
+        lp, ent = P.shifted_logprobs_entropy(cu(logits).unsqueeze(0), cu(ids).unsqueeze(0), tau)
+        np.testing.assert_allclose(lp[0].cpu().numpy(), d[f"kat1/tau{tau}/logp"], atol=1e-5)
+        np.testing.assert_allclose(ent[0].cpu().numpy(), d[f"kat1/tau{tau}/entropy"], atol=1e-5)
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal((3, 17, 5003)) * 3).astype(np.float32)
+    ids = rng.integers(0, 5003, (3, 17))
+    lp = P.selective_log_softmax(cu(x), cu(ids)).cpu().numpy()
+    ent = P.compute_entropy(cu(x)).cpu().numpy()
+    assert ent.shape == (3, 17)
+    for b in range(3):
+        wl, we, _ = oracle.logprobs_entropy(x[b], ids[b], 1.0)
+        np.testing.assert_allclose(lp[b], wl, atol=1e-4)
+        np.testing.assert_allclose(ent[b], we, atol=1e-4)
+    sh = P.shift_logits(cu(x)).cpu().numpy()
+    for b in range(3):
+        np.testing.assert_array_equal(sh[b], oracle.shift_rows(x[b]))
+
+
+# ------------------------------------------------------------------------------- tcgen05 GEMM engine
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 520, 200), (1024, 768, 4096)])
+def test_gemm_engine(P, a_mn, b_mn, M, N, K):
+    from prime_rl_cse_b200 import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(M + N + K)
+    # pitches must be multiples of 8 elements for TMA; pad logical sizes where needed
+    M8, N8, K8 = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8
+    A = torch.randn(M8, K8, device="cuda").bfloat16()
+    B = torch.randn(N8, K8, device="cuda").bfloat16()
+    a_st = A.t().contiguous() if a_mn else A
+    b_st = B.t().contiguous() if b_mn else B
+    C = torch.full((M8, N8), float("nan"), device="cuda")
+    rc = lib.prl_gemm_bf16_f32(_lib.ptr(a_st), _lib.ptr(b_st), _lib.ptr(C), M8, N8, K8, a_mn, b_mn, 0, _lib.stream())
+    _lib.check(rc, "gemm")
+    want = A.float() @ B.float().t()
+    torch.cuda.synchronize()
+    err = (C - want).abs().max().item()
+    assert err <= 2e-3 * max(1.0, want.abs().max().item()), f"max err {err}"
+    rc = lib.prl_gemm_bf16_f32(_lib.ptr(a_st), _lib.ptr(b_st), _lib.ptr(C), M8, N8, K8, a_mn, b_mn, 1, _lib.stream())
+    _lib.check(rc, "gemm acc")
+    assert (C - 2 * want).abs().max().item() <= 4e-3 * max(1.0, want.abs().max().item())
+
+
+# ------------------------------------------------------------------------------- fused LM head
+def _mk(T, H, V, seed, peaked=False):
+    g = torch.Generator().manual_seed(seed)
+    hidden = torch.randn(T, H, generator=g).bfloat16()
+    weight = (torch.randn(V, H, generator=g) * (3.0 / H**0.5)).bfloat16()
+    ids = torch.randint(0, V, (T,), generator=g)
+    if peaked:  # make the sampled token likely: add its embedding direction to the previous hidden state
+        hidden[:-1] = (hidden[:-1].float() + 4.0 * weight[ids[1:]].float() / weight[ids[1:]].float().norm(dim=-1, keepdim=True) ).bfloat16()
+    return hidden, weight, ids
+
+
+@pytest.mark.parametrize("T,H,V,tau", [(48, 32, 160, 1.0), (300, 256, 5000, 0.6), (1000, 512, 3333 * 8, 1.0), (129, 1024, 151936, 0.6)])
+def test_lmhead_forward_vs_oracle(P, T, H, V, tau):
+    hidden, weight, ids = _mk(T, H, V, T + V, peaked=(T == 300))
+    lp, ent = P.fused_lm_head_logprobs_entropy(hidden.cuda().unsqueeze(0), weight.cuda(), ids.cuda().unsqueeze(0), tau)
+    logits = oracle.lm_head_logits(hidden.float().numpy(), weight.float().numpy(), True)
+    wl, we, _ = oracle.logprobs_entropy(oracle.shift_rows(logits), ids.numpy(), tau)
+    dl = np.abs(lp[0].cpu().numpy() - wl)
+    de = np.abs(ent[0].cpu().numpy() - we)
+    # tcgen05 and the fp64 oracle accumulate in different orders: a logit that sits on a bf16 rounding
+    # boundary may round the other way (SURVEY §7 "bf16 rounding"), moving logp by <= 1 bf16 ulp of the logit.
+    assert np.mean(dl < 1e-3) >= 0.995 and dl.max() < 0.07, (dl.max(), np.mean(dl < 1e-3))
+    assert de.max() < 1e-3, de.max()
+    # closed-form first row (shift_logits' zero row): logp = -ln V, entropy = ln V
+    assert abs(lp[0, 0].item() + np.log(V)) < 1e-5 and abs(ent[0, 0].item() - np.log(V)) < 1e-5
+
+
+def test_lmhead_forward_exact_rounding_free(P):
+    # without bf16 rounding of the accumulator there is no boundary effect: every token within 1e-3 (in fact ~1e-5)
+    T, H, V, tau = 257, 128, 4096 + 64, 0.7
+    hidden, weight, ids = _mk(T, H, V, 9)
+    from prime_rl_cse_b200 import lm_head_forward_raw
+
+    lp, ent, lse, _ = lm_head_forward_raw(hidden.cuda(), weight.cuda(), ids.cuda(), 1.0 / tau, shift=True, round_bf16=False)
+    logits = oracle.lm_head_logits(hidden.float().numpy(), weight.float().numpy(), False)
+    wl, we, wlse = oracle.logprobs_entropy(oracle.shift_rows(logits), ids.numpy(), tau)
+    np.testing.assert_allclose(lp.cpu().numpy(), wl, atol=1e-4)
+    np.testing.assert_allclose(ent.cpu().numpy(), we, atol=1e-4)
+    np.testing.assert_allclose(lse.cpu().numpy(), wlse, atol=1e-4)
+
+
+def test_lmhead_fixtures_from_reference(P):
+    d = load("lmhead.npz")
+    for key in d["names"]:
+        name, tau_s, cname = key.split("/")
+        if not bool(d[f"{name}/is_bf16"]):
+            continue
+        tau = float(tau_s[3:])
+        hidden, weight = cu(d[f"{name}/hidden"], torch.bfloat16), cu(d[f"{name}/weight"], torch.bfloat16)
+        hidden.requires_grad_(True)
+        weight.requires_grad_(True)
+        mb = dict(input_ids=cu(d[f"{name}/ids"]).unsqueeze(0), position_ids=cu(d[f"{name}/pos"]).unsqueeze(0),
+                  advantages=cu(d[f"{name}/adv"]).unsqueeze(0), logprobs=cu(d[f"{key}/old"]).unsqueeze(0),
+                  loss_mask=cu(d[f"{name}/mask"]).unsqueeze(0), temperature=tau)
+        cfg = P.LossConfig() if cname == "token" else P.LossConfig("sequence", True, 8.0)
+        out = P.rl_micro_step(hidden.unsqueeze(0), weight, mb, cfg, int(d[f"{key}/scale"]))
+        dl = np.abs(out["logprobs"][0].cpu().numpy() - d[f"{key}/logp"])
+        assert np.mean(dl < 1e-3) > 0.97 and dl.max() < 0.07, (key, dl.max())
+        np.testing.assert_allclose(out["loss"].item(), d[f"{key}/loss"], rtol=5e-3, atol=1e-5)
+        assert rel_l2(hidden.grad.float().cpu().numpy(), d[f"{key}/d_hidden"]) < 1e-2, key
+        assert rel_l2(weight.grad.float().cpu().numpy(), d[f"{key}/d_weight"]) < 1e-2, key
+
+
+@pytest.mark.parametrize("T,H,V,tau,mode,vchunk", [
+    (48, 32, 160, 1.0, "token", 0),
+    (300, 256, 5000, 0.6, "token", 1024),
+    (640, 512, 20000, 1.0, "sequence", 8192),
+    (200, 1024, 151936, 0.6, "token", 0),
+])
+def test_micro_step_vs_oracle(P, T, H, V, tau, mode, vchunk):
+    os.environ["PRL_VCHUNK"] = str(vchunk) if vchunk else "8192"
+    try:
+        hidden, weight, ids = _mk(T, H, V, T + H, peaked=True)
+        rng = np.random.default_rng(T)
+        lens = [T // 3, T // 4, T - T // 3 - T // 4]
+        pos = np.concatenate([np.arange(n) for n in lens])
+        adv = np.concatenate([np.full(n, rng.standard_normal(), dtype=np.float32) for n in lens])
+        mask = rng.random(T) < 0.75
+        cfg_o = LossCfg(mode, mode == "sequence", 8.0)
+        scale = int(mask.sum()) if mode == "token" else 1
+        logits = oracle.lm_head_logits(hidden.float().numpy(), weight.float().numpy(), True)
+        lp_true, _, _ = oracle.logprobs_entropy(oracle.shift_rows(logits), ids.numpy(), tau)
+        old = (lp_true + 0.3 * rng.standard_normal(T) / (20 if mode == "sequence" else 1)).astype(np.float32)
+        want = oracle.micro_step(hidden.float().numpy(), weight.float().numpy(), ids.numpy(), pos, old, adv, mask, tau, cfg_o, scale)
+
+        h = hidden.cuda().requires_grad_(True)
+        w = weight.cuda().requires_grad_(True)
+        mb = dict(input_ids=ids.cuda().unsqueeze(0), position_ids=cu(pos).unsqueeze(0), advantages=cu(adv).unsqueeze(0),
+                  logprobs=cu(old).unsqueeze(0), loss_mask=cu(mask).unsqueeze(0), temperature=tau)
+        out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(mode, mode == "sequence", 8.0), scale)
+        dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
+        assert np.mean(dl < 1e-3) >= 0.99 and dl.max() < 0.07, (dl.max(), np.mean(dl < 1e-3))
+        assert np.abs(out["entropy"][0].cpu().numpy() - want["entropy"]).max() < 2e-3
+        np.testing.assert_allclose(out["loss"].item(), want["loss"], rtol=5e-3, atol=1e-6)
+        assert rel_l2(h.grad.float().cpu().numpy(), want["d_hidden"]) < 1e-2
+        assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1e-2
+        assert h.grad.dtype == torch.bfloat16 and w.grad.dtype == torch.bfloat16
+        assert float(h.grad[-1].abs().max()) == 0.0  # the dropped last position gets no gradient (loss.py:54)
+    finally:
+        os.environ.pop("PRL_VCHUNK", None)
