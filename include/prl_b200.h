@@ -145,13 +145,15 @@ int prl_lmhead_merge_partials(const float* partials, int32_t nparts, int64_t T, 
  * block lives in `workspace` (never the whole [T,V]); vchunk == 0 picks the default.
  * d_hidden may be NULL (W-only) and d_weight may be NULL (hidden-only).  For a vocab shard d_hidden
  * is the shard's partial sum (reduce across shards by the caller); set d_hidden_f32 != 0 to get it as fp32.
+ * phase_mask selects the sub-steps to run per vocab chunk (profiling aid): bit 0 = dlogits recompute,
+ * bit 1 = d_hidden GEMM, bit 2 = d_weight GEMM; 0 means all three.
  * ---------------------------------------------------------------------------------------- */
 size_t prl_lmhead_bwd_workspace_bytes(int64_t T, int32_t H, int64_t V, int64_t vchunk);
 int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, const float* lse,
                    const float* dlogp, int64_t T, int32_t H, int64_t V, int64_t v_offset, float inv_temp,
                    int32_t shift, int32_t round_bf16, void* d_hidden, int32_t d_hidden_f32, void* d_weight,
-                   int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, void* workspace,
-                   size_t workspace_bytes, void* stream);
+                   int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, int32_t phase_mask,
+                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Plain bf16 GEMM on the same tcgen05 engine, exposed for tests and bring-up:

@@ -239,8 +239,8 @@ size_t prl_lmhead_bwd_workspace_bytes(int64_t T, int32_t H, int64_t V, int64_t v
 
 int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T, int32_t H,
                    int64_t V, int64_t v_offset, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden, int32_t d_hidden_f32,
-                   void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, void* workspace, size_t workspace_bytes,
-                   void* stream) {
+                   void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, int32_t phase_mask, void* workspace,
+                   size_t workspace_bytes, void* stream) {
   PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_bwd: bad sizes");
   PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_bwd: shift must be 0 or 1");
   PRL_REQUIRE(d_weight_dtype == PRL_DT_BF16 || d_weight_dtype == PRL_DT_F32, PRL_ERR_BAD_ARG, "lmhead_bwd: bad d_weight dtype");
@@ -256,11 +256,12 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
   float* dh_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + round_up(t_pad * vc * 2, 1024));
   const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(weight);
 
+  if ((phase_mask & 7) == 0) phase_mask = 7;
   for (int64_t c = 0; c < nchunks; ++c) {
     const int64_t c0 = c * vc;
     const int64_t vce = (V - c0) < vc ? (V - c0) : vc;
     // ---- K1: recompute the logits tile by tile, emit dlogits (bf16) for this vocab chunk ----
-    {
+    if (phase_mask & 1) {
       GemmParams p;
       memset(&p, 0, sizeof(p));
       int rc = make_operand_map(&p.tma_a, hidden, false, T, H, H, BLOCK_M);
@@ -286,7 +287,7 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
       if (rc) return rc;
     }
     // ---- K2: d_hidden[T,H] += dz[T,vce] x W[c0:c0+vce, :]   (A K-major, B MN-major) ----
-    if (d_hidden) {
+    if (d_hidden && (phase_mask & 2)) {
       GemmParams p;
       memset(&p, 0, sizeof(p));
       int rc = make_operand_map(&p.tma_a, dz, false, T, vce, vc, BLOCK_M);
@@ -312,7 +313,7 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
       if (rc) return rc;
     }
     // ---- K3: d_weight[c0:c0+vce, H] (+)= dz^T x hidden   (both MN-major) ----
-    if (d_weight) {
+    if (d_weight && (phase_mask & 4)) {
       GemmParams p;
       memset(&p, 0, sizeof(p));
       int rc = make_operand_map(&p.tma_a, dz, true, vce, T, vc, BLOCK_M);

