@@ -166,7 +166,7 @@ def run_b200(args):
     H, V, T, n_mb = wl["H"], wl["V"], wl["T"], wl["n_mb"] if args.micro_batches <= 0 else args.micro_batches
     cfg = P.LossConfig(ratio_type=wl["ratio_type"], ratio_length_norm=False, clip_ratio=8.0)
     mode = 0 if cfg.ratio_type == "token" else 1
-    W = wl["weight"].to(dev)
+    W = wl["weight"].to(dev).requires_grad_(True)  # lm_head.weight is a trainable parameter
     main_grad = torch.zeros(V, H, dtype=torch.float32, device=dev)  # fp32 accumulation across micro-batches
     rs_out = torch.empty((V // world) * H, dtype=torch.float32, device=dev) if world > 1 and V % world == 0 else None
     dev_mbs = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in mb.items()} for mb in wl["mbs"]]
@@ -181,6 +181,8 @@ def run_b200(args):
     ws_f = torch.empty(lib.prl_lmhead_fwd_workspace_bytes(T, H, V), dtype=torch.uint8, device=dev)
     ws_b = torch.empty(lib.prl_lmhead_bwd_workspace_bytes(T, H, V, 0), dtype=torch.uint8, device=dev)
 
+    Wd = W.detach()
+
     def step_resident():
         """inputs already in HBM; raw C-ABI calls, no autograd bookkeeping"""
         adv_all, = (P.compute_advantages_tensor(rewards_d, lengths_d, wl["group"], "drgrpo"),)
@@ -189,11 +191,11 @@ def run_b200(args):
             mb = dev_mbs[i % len(dev_mbs)]
             hid = mb["hidden"][0]
             ids = mb["input_ids"][0]
-            logp, ent, lse, _ = P.lm_head_forward_raw(hid, W, ids, 1.0 / mb["temperature"], workspace=ws_f)
+            logp, ent, lse, _ = P.lm_head_forward_raw(hid, Wd, ids, 1.0 / mb["temperature"], workspace=ws_f)
             loss, ratio, clipped, is_clipped, dlogp = _loss_packed_raw(
                 logp, mb["logprobs"][0], mb["advantages"][0], mb["loss_mask"][0].view(torch.uint8), cu, nseg, mode,
                 cfg.ratio_length_norm, cfg.clip_ratio, loss_scale)
-            P.lm_head_backward_raw(hid, W, ids, lse, dlogp, 1.0 / mb["temperature"], dweight=main_grad, dweight_accumulate=True,
+            P.lm_head_backward_raw(hid, Wd, ids, lse, dlogp, 1.0 / mb["temperature"], dweight=main_grad, dweight_accumulate=True,
                                    workspace=ws_b)
             last = loss
         if dist is not None and rs_out is not None:
@@ -275,7 +277,7 @@ def run_b200(args):
     if rank == 0 and not args.no_breakdown:
         mb = dev_mbs[0]
         hid, ids = mb["hidden"][0], mb["input_ids"][0]
-        logp, ent, lse, _ = P.lm_head_forward_raw(hid, W, ids, 1.0, workspace=ws_f)
+        logp, ent, lse, _ = P.lm_head_forward_raw(hid, Wd, ids, 1.0, workspace=ws_f)
         dlogp = torch.randn(T, device=dev) / T
 
         def ev_time(fn, reps):
@@ -291,10 +293,10 @@ def run_b200(args):
 
         vc = 8192
         nchunks = (V + vc - 1) // vc
-        fam["lmhead_fwd_kernel"] = dict(ms_per_launch=ev_time(lambda: P.lm_head_forward_raw(hid, W, ids, 1.0, workspace=ws_f), 8),
+        fam["lmhead_fwd_kernel"] = dict(ms_per_launch=ev_time(lambda: P.lm_head_forward_raw(hid, Wd, ids, 1.0, workspace=ws_f), 8),
                                         launches_per_mb=1, flops_per_launch=2.0 * T * H * V)
         for name, mask in (("lmhead_bwd_dz_kernel", 1), ("lmhead_bwd_dhidden_kernel", 2), ("lmhead_bwd_dweight_kernel", 4)):
-            t_ms = ev_time(lambda: P.lm_head_backward_raw(hid, W, ids, lse, dlogp, 1.0, dweight=main_grad, dweight_accumulate=True,
+            t_ms = ev_time(lambda: P.lm_head_backward_raw(hid, Wd, ids, lse, dlogp, 1.0, dweight=main_grad, dweight_accumulate=True,
                                                           phase_mask=mask, workspace=ws_b), 4)
             fam[name] = dict(ms_per_launch=t_ms / nchunks, launches_per_mb=nchunks, flops_per_launch=2.0 * T * H * V / nchunks)
 

@@ -1,0 +1,20 @@
+"""Short single-GPU case for ncu: one fused forward + one backward at the Qwen3-8B tile shape but a
+reduced vocabulary (2 vocab chunks), so every launch has the same per-launch work as in bench.py."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_forward_raw
+
+T, H, V = 16384, 4096, int(os.environ.get("NCU_V", 16384))
+dev = "cuda"
+torch.manual_seed(0)
+hidden = torch.randn(T, H, device=dev).bfloat16()
+W = (torch.randn(V, H, device=dev) * 0.02).bfloat16()
+ids = torch.randint(0, V, (T,), device=dev)
+dW = torch.zeros(V, H, device=dev)
+for _ in range(int(os.environ.get("NCU_ITERS", 2))):
+    logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, 1.0)
+    g = torch.randn(T, device=dev) / T
+    lm_head_backward_raw(hidden, W, ids, lse, g, 1.0, dweight=dW, dweight_accumulate=True)
+torch.cuda.synchronize()
+print("ok", float(logp.mean()), float(ent.mean()))
