@@ -13,7 +13,7 @@ from ctypes import c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprl_b200.so")
+LIB_PATH = os.environ.get("PRL_LIB_PATH") or os.path.join(_HERE, "libprl_b200.so")
 
 PRL_ADV_KINDS = {"drgrpo": 0, "drgrpo-negclipped": 1, "rloo": 2, "opo": 3}
 PRL_RATIO = {"token": 0, "sequence": 1}

@@ -1,7 +1,8 @@
 // Persistent, warp-specialised tcgen05 GEMM engine for sm_100a with pluggable epilogues.
 //
-//   C[M,N] = A x B, bf16 inputs, fp32 accumulation in TMEM, 128 x 256 output tiles, BLOCK_K = 64.
-//   warp 0 (one lane): TMA producer  -> 4-stage smem ring (128B-swizzled tiles)
+//   C[M,N] = A x B, bf16 inputs, fp32 accumulation in TMEM, 128 x 256 output tiles per CTA (256 x 256 per CTA
+//   pair with cta_group::2), BLOCK_K = 64.
+//   warp 0 (one lane): TMA producer  -> 4-stage (6-stage for CTA pairs) smem ring (128B-swizzled tiles)
 //   warp 1 (one lane): tcgen05.mma issuer -> 2 accumulator buffers of 256 TMEM columns
 //   warp 2           : TMEM allocator
 //   warps 4..7       : epilogue; thread i owns accumulator row (lane) i of the tile, so row-wise
@@ -21,13 +22,11 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+#ifndef PRL_STAGES
+#define PRL_STAGES 4
+#endif
 constexpr int GEMM_THREADS = 256;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr float LOG2E = 1.4426950408889634f;
 
 enum EpiKind { EPI_STATS = 0, EPI_DZ = 1, EPI_STORE = 2 };
@@ -234,77 +233,107 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], const EpiPa
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel
+// the kernel.  CG = 1: one CTA per 128 x 256 tile (cta_group::1).  CG = 2: a CTA pair (cluster of 2, cta_group::2)
+// per 256 x 256 tile: each CTA stages its own 128 rows of A and its own half (128 rows) of B, the leader CTA
+// issues M = 256 MMAs that read both CTAs' shared memory, each CTA's TMEM holds its 128 accumulator rows.
+// Halving the B bytes per SM and k-step gives 6 instead of 4 pipeline stages in the same shared memory.
 // ------------------------------------------------------------------------------------------------
-template <bool A_MN, bool B_MN, int EPI>
+template <int CG>
+struct Cfg {
+  static constexpr int kStages = (CG == 2) ? 6 : PRL_STAGES;
+  static constexpr int kBRows = BLOCK_N / CG;                    // B rows staged by one CTA
+  static constexpr int kAStage = BLOCK_M * BLOCK_K * 2;          // 16 KB
+  static constexpr int kBStage = kBRows * BLOCK_K * 2;           // 32 KB / 16 KB
+  static constexpr int kStage = kAStage + kBStage;
+  static constexpr int kSmem = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int CG, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<CG>;
+  constexpr int NS = C::kStages;
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B tiles need 1024-byte alignment
+  // SWIZZLE_128B tiles need 1024-byte alignment (the dynamic smem base offset is the same in both CTAs of a pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* full_bar = bars;                 // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* smem_b = smem + NS * C::kAStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * C::kStage);
+  uint64_t* full_bar = bars;                  // [NS]   TMA -> MMA          (CG == 2: the leader's is used)
+  uint64_t* empty_bar = bars + NS;            // [NS]   MMA -> TMA          (per CTA)
+  uint64_t* tfull_bar = bars + 2 * NS;        // [2]    MMA -> epilogue     (per CTA)
+  uint64_t* tempty_bar = bars + 2 * NS + 2;   // [2]    epilogue -> MMA     (CG == 2: the leader's is used)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = (CG == 2) ? (int)ptx::cluster_ctarank() : 0;
+  const int worker = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
+  const int n_workers = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tma_a);
     ptx::prefetch_tensormap(&p.tma_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < NS; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tempty_bar[i], 4 * CG);  // one arrive per epilogue warp (of both CTAs)
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (CG == 2) {
+      ptx::tmem_alloc_cg2(tmem_ptr, TMEM_COLS);
+      ptx::tmem_relinquish_cg2();
+    } else {
+      ptx::tmem_alloc(tmem_ptr, TMEM_COLS);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = worker; item < p.num_items; item += n_workers) {
         const Item it = decode_item(p, item);
+        const int m0 = it.m_tile * (BLOCK_M * CG) + rank * BLOCK_M;
         for (int nt = it.n_begin; nt < it.n_begin + it.n_count; ++nt) {
+          const int n0 = nt * BLOCK_N + rank * C::kBRows;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-            uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
-            uint8_t* sb = smem_b + stage * B_STAGE_BYTES;
+            if (CG == 1 || rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStage * CG);
+            uint8_t* sa = smem_a + stage * C::kAStage;
+            uint8_t* sb = smem_b + stage * C::kBStage;
+            auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+              if (CG == 2)
+                ptx::tma_load_2d_cg2(dst, map, &full_bar[stage], c0, c1);
+              else
+                ptx::tma_load_2d(dst, map, &full_bar[stage], c0, c1);
+            };
             if (!A_MN) {
-              ptx::tma_load_2d(sa, &p.tma_a, &full_bar[stage], kb * BLOCK_K, it.m_tile * BLOCK_M);
+              load(sa, &p.tma_a, kb * BLOCK_K, m0);
             } else {
 #pragma unroll
-              for (int s = 0; s < BLOCK_M / 64; ++s)
-                ptx::tma_load_2d(sa + s * (BLOCK_K * 128), &p.tma_a, &full_bar[stage], it.m_tile * BLOCK_M + s * 64, kb * BLOCK_K);
+              for (int s = 0; s < BLOCK_M / 64; ++s) load(sa + s * (BLOCK_K * 128), &p.tma_a, m0 + s * 64, kb * BLOCK_K);
             }
             if (!B_MN) {
-              ptx::tma_load_2d(sb, &p.tma_b, &full_bar[stage], kb * BLOCK_K, nt * BLOCK_N);
+              load(sb, &p.tma_b, kb * BLOCK_K, n0);
             } else {
 #pragma unroll
-              for (int s = 0; s < BLOCK_N / 64; ++s)
-                ptx::tma_load_2d(sb + s * (BLOCK_K * 128), &p.tma_b, &full_bar[stage], nt * BLOCK_N + s * 64, kb * BLOCK_K);
+              for (int s = 0; s < C::kBRows / 64; ++s) load(sb + s * (BLOCK_K * 128), &p.tma_b, n0 + s * 64, kb * BLOCK_K);
             }
-            if (++stage == STAGES) {
+            if (++stage == NS) {
               stage = 0;
               phase ^= 1;
             }
@@ -313,20 +342,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
-      // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  k-step of 16 elements = +32 B.
-      // MN-major SW128: 64-element MN slabs BLOCK_K*128 B apart (LBO); 8-k-row groups 1024 B apart (SBO);
-      //                 k-step of 16 rows = +2048 B.
-      // (the host fills these defaults into GemmParams, see make_desc_defaults)
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * CG, BLOCK_N, A_MN, B_MN);
+      // smem descriptor templates and k-step advances come from the host (make_desc_defaults)
       const uint64_t a_hi = p.a_desc_hi, b_hi = p.b_desc_hi;
       const uint32_t a_kstep = p.a_kstep, b_kstep = p.b_kstep;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = worker; item < p.num_items; item += n_workers) {
         const Item it = decode_item(p, item);
         for (int nt = 0; nt < it.n_count; ++nt) {
           ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -335,37 +361,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
-            const uint32_t sa = ptx::smem_u32(smem_a + stage * A_STAGE_BYTES);
-            const uint32_t sb = ptx::smem_u32(smem_b + stage * B_STAGE_BYTES);
+            const uint32_t sa = ptx::smem_u32(smem_a + stage * C::kAStage);
+            const uint32_t sb = ptx::smem_u32(smem_b + stage * C::kBStage);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint64_t ad = ptx::smem_desc(a_hi, sa + k * a_kstep);
               const uint64_t bd = ptx::smem_desc(b_hi, sb + k * b_kstep);
-              ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (CG == 2)
+                ptx::umma_bf16_cg2(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+              else
+                ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-            if (++stage == STAGES) {
+            // frees the smem slot (in both CTAs) when these MMAs retire
+            if (CG == 2)
+              ptx::umma_commit_cg2(&empty_bar[stage]);
+            else
+              ptx::umma_commit(&empty_bar[stage]);
+            if (++stage == NS) {
               stage = 0;
               phase ^= 1;
             }
           }
-          ptx::umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+          // accumulator ready for the epilogue warps (of both CTAs)
+          if (CG == 2)
+            ptx::umma_commit_cg2(&tfull_bar[acc]);
+          else
+            ptx::umma_commit(&tfull_bar[acc]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
     const int quarter = warp & 3;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
     const EpiParams& e = p.epi;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = worker; item < p.num_items; item += n_workers) {
       const Item it = decode_item(p, item);
-      const int64_t row = (int64_t)it.m_tile * BLOCK_M + row_in_tile;
+      const int64_t row = (int64_t)it.m_tile * (BLOCK_M * CG) + rank * BLOCK_M + row_in_tile;
       const bool row_ok = row < e.m_rows;
       // per-item row state
       RowStats st = {-INFINITY, 0.f, 0.f, 0.f};
@@ -410,7 +447,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        if (lane == 0) {
+          if (CG == 2)
+            ptx::mbar_arrive_leader(&tempty_bar[acc]);
+          else
+            ptx::mbar_arrive(&tempty_bar[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -422,9 +464,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync_all();  // no CTA of the pair may exit while the other can still signal it
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CG == 2)
+      ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    else
+      ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 

@@ -40,8 +40,10 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t 
   return PRL_OK;
 }
 
+static int cta_group_fwd();
 // operand description: K-major => stored [rows, K]; MN-major => stored [K, rows]
 static int make_operand_map(CUtensorMap* map, const void* base, bool mn_major, int64_t rows, int64_t K, int64_t ld, int block_rows) {
+  if (block_rows == BLOCK_N) block_rows = BLOCK_N / cta_group_fwd();  // each CTA of a pair stages half of B's rows
   if (!mn_major) return make_tmap(map, base, K, rows, ld, BLOCK_K, block_rows);
   return make_tmap(map, base, rows, K, ld, 64, BLOCK_K);
 }
@@ -64,24 +66,55 @@ static void make_desc_defaults(GemmParams& p, bool a_mn, bool b_mn) {
   p.b_kstep = b_mn ? mn_kstep : UMMA_K * 2;
 }
 
-template <bool A_MN, bool B_MN, int EPI>
-static int launch_gemm(const GemmParams& p, cudaStream_t st, const char* name) {
+static int cta_group();
+static int cta_group_fwd() { return cta_group(); }
+// 1 = one CTA per 128x256 tile, 2 = CTA pairs (cta_group::2) on 256x256 tiles (default)
+static int cta_group() {
+  static int cg = 0;
+  if (cg == 0) cg = env_long("PRL_CTA_GROUP", 2) == 1 ? 1 : 2;
+  return cg;
+}
+
+template <int CG, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm_cg(const GemmParams& p, cudaStream_t st, const char* name) {
   static bool attr_set = false;
-  auto kern = gemm_kernel<A_MN, B_MN, EPI>;
+  auto kern = gemm_kernel<CG, A_MN, B_MN, EPI>;
+  constexpr int smem = Cfg<CG>::kSmem;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
     attr_set = true;
   }
-  int grid = sm_count();
-  if (grid > p.num_items) grid = p.num_items;
-  if (grid < 1) return PRL_OK;
-  kern<<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(p);
+  if (p.num_items < 1) return PRL_OK;
+  int workers = sm_count() / CG;
+  if (workers > p.num_items) workers = p.num_items;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(workers * CG);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) return fail_cuda(e, name);
   return check_launch(name);
 }
 
+template <bool A_MN, bool B_MN, int EPI>
+static int launch_gemm(const GemmParams& p, cudaStream_t st, const char* name) {
+  if (cta_group() == 2) return launch_gemm_cg<2, A_MN, B_MN, EPI>(p, st, name);
+  return launch_gemm_cg<1, A_MN, B_MN, EPI>(p, st, name);
+}
+
 static void set_tiling(GemmParams& p, int64_t M, int64_t N, int64_t K) {
-  p.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  const int64_t bm = (int64_t)BLOCK_M * cta_group();
+  p.m_tiles = (int)((M + bm - 1) / bm);
   p.n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
   p.k_blocks = (int)((K + BLOCK_K - 1) / BLOCK_K);
 }
@@ -90,13 +123,13 @@ static void set_tiling(GemmParams& p, int64_t M, int64_t N, int64_t K) {
 static void schedule_tiles(GemmParams& p) {
   p.tiles_per_split = 1;
   p.n_splits = p.n_tiles;
-  p.group_m = (int)env_long("PRL_GROUP_M", 8);
+  p.group_m = (int)env_long("PRL_GROUP_M", 8) / cta_group();
   p.num_items = p.m_tiles * p.n_splits;
 }
 
 // items = (m_tile, n-range): pick the number of vocab splits that minimises the static makespan
 static void schedule_sweeps(GemmParams& p, int max_splits) {
-  const int sms = sm_count();
+  const int sms = sm_count() / cta_group();  // workers: CTAs or CTA pairs
   int best_ns = 1;
   long best = -1;
   const int hi = p.n_tiles < max_splits ? p.n_tiles : max_splits;
@@ -112,7 +145,7 @@ static void schedule_sweeps(GemmParams& p, int max_splits) {
   }
   p.tiles_per_split = (p.n_tiles + best_ns - 1) / best_ns;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.group_m = (int)env_long("PRL_SWEEP_GROUP_M", 32);
+  p.group_m = (int)env_long("PRL_SWEEP_GROUP_M", 32) / cta_group();
   p.num_items = p.m_tiles * p.n_splits;
 }
 
