@@ -29,6 +29,8 @@ __all__ = [
     "loss_fwd_bwd",
     "lm_head_backward",
     "micro_step",
+    "shard_partials",
+    "merge_partials",
 ]
 
 ADVANTAGE_KINDS = ("drgrpo", "drgrpo-negclipped", "rloo", "opo")
@@ -298,3 +300,37 @@ def micro_step(
         d_hidden=d_hidden,
         d_weight=d_weight,
     )
+
+
+# --------------------------------------------------------------------------- #
+# vocab-shard partials (online-softmax algebra; SURVEY §8a "single-formula restatement")
+# --------------------------------------------------------------------------- #
+def shard_partials(z_shard: np.ndarray, ids: np.ndarray, v0: int, dtype=np.float64) -> np.ndarray:
+    """Per-token (m, s, u, z_target) of one vocab shard holding columns [v0, v0 + z_shard.shape[1]) of the
+    temperature-scaled shifted logits z.  z_target is 0 when the target lies outside the shard."""
+    z = z_shard.astype(dtype)
+    T, Vs = z.shape
+    if Vs == 0:
+        out = np.zeros((T, 4), dtype=dtype)
+        out[:, 0] = -np.inf
+        return out
+    m = z.max(axis=1)
+    e = np.exp(z - m[:, None])
+    s = e.sum(axis=1)
+    u = (e * z).sum(axis=1)
+    loc = np.asarray(ids).reshape(-1) - v0
+    inside = (loc >= 0) & (loc < Vs)
+    zt = np.where(inside, z[np.arange(T), np.clip(loc, 0, Vs - 1)], 0.0)
+    return np.stack([m, s, u, zt], axis=1)
+
+
+def merge_partials(parts: np.ndarray):
+    """parts [n, T, 4] -> (logp, entropy, lse): rescale s,u by e^{m_i - max m}; lse = m + ln s; H = lse - u/s."""
+    parts = np.asarray(parts, dtype=np.float64)
+    m = parts[:, :, 0].max(axis=0)
+    w = np.exp(parts[:, :, 0] - m[None, :])
+    s = (parts[:, :, 1] * w).sum(axis=0)
+    u = (parts[:, :, 2] * w).sum(axis=0)
+    zt = parts[:, :, 3].sum(axis=0)
+    lse = m + np.log(s)
+    return zt - lse, lse - u / s, lse

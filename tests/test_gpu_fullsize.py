@@ -1,0 +1,153 @@
+"""Full-size (BASELINE.json shapes) GPU checks through size-independent properties, where the CPU oracle
+would take minutes: vocab-partition invariance, determinism, linearity of the backward, bounds, and
+sampled-slice parity against a plain torch fp32 reference (a few token rows of dHidden and a few vocab rows
+of dW recomputed exactly)."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import prime_rl_cse_b200 as p
+
+    return p
+
+
+def make(T, H, V, seed=0, peaked=True):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    hidden = torch.randn(T, H, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(V, H, device="cuda", generator=g) * (2.0 / math.sqrt(H))).bfloat16()
+    ids = torch.randint(0, V, (T,), device="cuda", generator=g)
+    if peaked:
+        tgt = W[ids[1:]].float()
+        hidden[:-1] = (hidden[:-1].float() + 3.0 * tgt / tgt.norm(dim=-1, keepdim=True)).bfloat16()
+    return hidden, W, ids
+
+
+# BASELINE configs[1] (wordle, H=2048, 16k tokens) and configs[2]/[4] (Qwen3-8B, H=4096; 16k and 32k tokens)
+SHAPES = [(16384, 2048, 151936, 1.0), (16384, 4096, 151936, 0.6), (32768, 4096, 151936, 1.0)]
+
+
+@pytest.mark.parametrize("T,H,V,tau", SHAPES[:2])
+def test_forward_properties_full_size(P, T, H, V, tau):
+    from prime_rl_cse_b200 import _lib, lm_head_forward_raw
+
+    hidden, W, ids = make(T, H, V, seed=T + H)
+    logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, 1.0 / tau)
+    logp2, ent2, lse2, _ = lm_head_forward_raw(hidden, W, ids, 1.0 / tau)
+    assert torch.equal(logp, logp2) and torch.equal(ent, ent2) and torch.equal(lse, lse2)  # deterministic
+    assert bool((logp <= 1e-6).all()) and bool((ent >= -1e-4).all()) and bool((ent <= math.log(V) + 1e-3).all())
+    assert abs(logp[0].item() + math.log(V)) < 1e-5 and abs(ent[0].item() - math.log(V)) < 1e-5
+
+    # vocab-partition invariance: merging the partials of 8 FSDP-style vocab shards == the unsharded result
+    lib = _lib.load()
+    parts = []
+    for r in range(8):
+        v0, v1 = P.vocab_shard_bounds(V, 8, r)
+        parts.append(lm_head_forward_raw(hidden, W[v0:v1], ids, 1.0 / tau, v_offset=v0, v_total=V, want_partials=True)[3])
+    gathered = torch.stack(parts).contiguous()
+    lp_m, ent_m, lse_m = (torch.empty(T, device="cuda") for _ in range(3))
+    _lib.check(lib.prl_lmhead_merge_partials(_lib.ptr(gathered), 8, T, _lib.ptr(lp_m), _lib.ptr(ent_m), _lib.ptr(lse_m), _lib.stream()), "merge")
+    assert (lp_m - logp).abs().max().item() < 2e-4 and (ent_m - ent).abs().max().item() < 2e-4 and (lse_m - lse).abs().max().item() < 2e-4
+
+    # sampled rows against torch fp32 on the same bf16-rounded logits
+    rows = torch.randint(1, T, (96,), device="cuda")
+    z = (hidden[rows - 1].float() @ W.float().t()).bfloat16().float() / tau
+    ref_lse = torch.logsumexp(z, -1)
+    ref_lp = z.gather(1, ids[rows].unsqueeze(1)).squeeze(1) - ref_lse
+    ref_ent = ref_lse - (torch.softmax(z, -1) * z).sum(-1)
+    d = (logp[rows] - ref_lp).abs()
+    assert (d < 1e-3).float().mean().item() >= 0.97 and d.max().item() < 0.07, d.max().item()
+    assert (ent[rows] - ref_ent).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("T,H,V,tau", SHAPES[1:])
+def test_backward_sampled_slices_full_size(P, T, H, V, tau):
+    from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_forward_raw
+
+    hidden, W, ids = make(T, H, V, seed=7 * T + H)
+    inv = 1.0 / tau
+    logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, inv)
+    g = (torch.randn(T, device="cuda") / T)
+    g[torch.rand(T, device="cuda") < 0.25] = 0.0  # masked tokens
+    dW = torch.zeros(V, H, device="cuda")
+    dh, _ = lm_head_backward_raw(hidden, W, ids, lse, g, inv, dweight=dW, dweight_accumulate=True)
+    assert float(dh[-1].abs().max()) == 0.0  # dropped last position (loss.py:54)
+
+    # d_hidden rows: dlogits[r] = g[r+1]/tau * (onehot - softmax(z[r+1])) in bf16, then @ W
+    rows = torch.randint(0, T - 1, (64,), device="cuda")
+    z = (hidden[rows].float() @ W.float().t()).bfloat16().float() * inv
+    p = torch.exp(z - lse[rows + 1].unsqueeze(1))
+    dz = -p * g[rows + 1].unsqueeze(1)
+    dz[torch.arange(64, device="cuda"), ids[rows + 1]] += g[rows + 1]
+    dlog = (dz * inv).bfloat16().float()
+    ref_dh = dlog @ W.float()
+    num = (dh[rows].float() - ref_dh).norm().item()
+    assert num / max(ref_dh.norm().item(), 1e-30) < 1e-2
+
+    # d_W rows for a few vocab ids (including ids that occur as targets)
+    vs = torch.cat([ids[1:9], torch.randint(0, V, (24,), device="cuda")]).unique()
+    zc = (hidden[:-1].float() @ W[vs].float().t()).bfloat16().float() * inv  # [T-1, nv]: logits of source rows
+    pc = torch.exp(zc - lse[1:].unsqueeze(1))
+    dzc = -pc * g[1:].unsqueeze(1)
+    dzc += (ids[1:].unsqueeze(1) == vs.unsqueeze(0)).float() * g[1:].unsqueeze(1)
+    dlc = (dzc * inv).bfloat16().float()
+    ref_dw = dlc.t() @ hidden[:-1].float()
+    num = (dW[vs] - ref_dw).norm().item()
+    assert num / max(ref_dw.norm().item(), 1e-30) < 1e-2
+
+    # linearity: a second accumulation doubles dW; scaling dlogp by 4 scales d_hidden by 4 (power of 2: exact in bf16)
+    dh4, _ = lm_head_backward_raw(hidden, W, ids, lse, 4.0 * g, inv, dweight=dW, dweight_accumulate=True, phase_mask=3)
+    assert torch.equal(dh4.float(), 4.0 * dh.float())
+    dW2 = dW.clone()
+    lm_head_backward_raw(hidden, W, ids, lse, g, inv, dweight=dW2, dweight_accumulate=True, want_dhidden=False)
+    sel = dW[vs]
+    assert ((dW2[vs] - 2 * sel).norm() / sel.norm()).item() < 1e-5
+
+
+def test_vocab_sharded_backward_emulated_on_one_gpu(P):
+    """config 4 semantics: per-shard d_hidden partial sums add up to the unsharded d_hidden and the d_W shards
+    concatenate to the unsharded d_W (Qwen3-32B hidden size, reduced T)."""
+    from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_forward_raw
+
+    T, H, V, tau, world = 1024, 5120, 151936, 1.0, 8
+    hidden, W, ids = make(T, H, V, seed=3)
+    logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, 1.0 / tau)
+    g = torch.randn(T, device="cuda") / T
+    dh_full, dw_full = lm_head_backward_raw(hidden, W, ids, lse, g, 1.0 / tau, dhidden_f32=True)
+    dh_sum = torch.zeros(T, H, device="cuda")
+    for r in range(world):
+        v0, v1 = P.vocab_shard_bounds(V, world, r)
+        dh_r, dw_r = lm_head_backward_raw(hidden, W[v0:v1], ids, lse, g, 1.0 / tau, v_offset=v0, dhidden_f32=True)
+        dh_sum += dh_r
+        assert ((dw_r.float() - dw_full[v0:v1].float()).norm() / dw_full[v0:v1].float().norm()).item() < 1e-3
+    assert ((dh_sum - dh_full).norm() / dh_full.norm()).item() < 1e-3
+
+
+def test_sequence_mode_long_context_micro_step(P):
+    """BASELINE configs[4]: one 32k-token sequence, sequence-level ratio with length normalisation."""
+    T, H, V = 32768, 1024, 151936
+    hidden, W, ids = make(T, H, V, seed=11)
+    h = hidden.requires_grad_(True)
+    w = W.requires_grad_(True)
+    mask = torch.rand(T, device="cuda") < 0.9
+    mb = dict(input_ids=ids.unsqueeze(0), position_ids=torch.arange(T, device="cuda").unsqueeze(0),
+              advantages=torch.full((1, T), 0.5, device="cuda"), logprobs=torch.zeros(1, T, device="cuda"),
+              loss_mask=mask.unsqueeze(0), temperature=1.0)
+    with torch.no_grad():
+        lp0, _ = P.fused_lm_head_logprobs_entropy(hidden.detach().unsqueeze(0), W.detach(), ids.unsqueeze(0), 1.0)
+    mb["logprobs"] = lp0 + 1e-4
+    out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig("sequence", True, 8.0), 1)
+    assert out["importance_ratio"].shape == (1,)
+    r = math.exp(float(((out["logprobs"][0] - mb["logprobs"][0])[mask]).sum() / mask.sum()))
+    assert abs(out["importance_ratio"].item() - r) < 1e-4 * r
+    assert abs(out["loss"].item() + 0.5 * r) < 1e-3
+    assert h.grad is not None and w.grad is not None and torch.isfinite(h.grad.float()).all()
