@@ -44,6 +44,26 @@ SHAPES = {
 }
 
 
+# DRAM bytes (read + write) per launch of each GEMM family at the Qwen3-8B shape, from the `ncu --set full` capture
+# summarised in profiles/r1_lmhead_cg2_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum).  The forward
+# capture there is a 16384-row vocabulary slice (1.75 GB per 16384 vocab rows); backward launches are full size.
+NCU_TRAFFIC_BYTES = {
+    "lmhead_bwd_dz_kernel": 0.878e9 + 0.252e9,
+    "lmhead_bwd_dhidden_kernel": 1.710e9 + 0.192e9,
+    "lmhead_bwd_dweight_kernel": 1.709e9 + 0.120e9,
+    "lmhead_fwd_kernel": (1.746e9 + 0.007e9) * 151936 / 16384,
+}
+# algorithmic bytes per launch (operands read once + outputs written once), for comparison with `traffic`
+def algorithmic_bytes(kernel, T, H, V, vc):
+    if kernel == "lmhead_fwd_kernel":
+        return 2.0 * (T * H + V * H) + 16.0 * T
+    if kernel == "lmhead_bwd_dz_kernel":
+        return 2.0 * (T * H + vc * H) + 2.0 * T * vc
+    if kernel == "lmhead_bwd_dhidden_kernel":
+        return 2.0 * (T * vc + vc * H) + 8.0 * T * H
+    return 2.0 * (T * vc + T * H) + 8.0 * vc * H
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -330,13 +350,18 @@ def run_b200(args):
         f = fam[top]
         achieved = f["flops_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e12
         result["roofline"] = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                              "frac": achieved / peaks["sustained"], "traffic": None, "peak_source": peaks["source"] + " sustained",
+                              "frac": achieved / peaks["sustained"],
+                              "traffic": NCU_TRAFFIC_BYTES.get(top) if args.workload == "qwen3-8b-hendrycks" else None,
+                              "traffic_source": "profiles/r1_lmhead_cg2_ncu_summary.txt (dram read+write bytes per launch)",
+                              "algorithmic_bytes": algorithmic_bytes(top, T, H, V, vc),
+                              "flops_per_launch": f["flops_per_launch"], "ms_per_launch": f["ms_per_launch"],
+                              "peak_source": peaks["source"] + " sustained (kernel timed inside a long power-capped step)",
                               "frac_of_burst": achieved / peaks["burst"]}
         result["kernel_breakdown_ms_per_micro_batch"] = {k: v["ms_per_launch"] * v["launches_per_mb"] for k, v in fam.items()}
         result["kernel_tflops"] = {k: v["flops_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e12 for k, v in fam.items()}
     if rank == 0:
         if not args.no_cpu_baseline and world >= 1:
-            result["cpu_baseline"] = cpu_baseline(args.workload, steps=1, warmup=0)
+            result["cpu_baseline"] = cpu_baseline(args.workload, steps=3, warmup=0)
         print(json.dumps(result), flush=True)
     if dist is not None:
         dist.barrier()
@@ -346,7 +371,7 @@ def run_b200(args):
 # ------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the reference's own torch-CPU path (oracle/torch_port.py) on host cores
 # ------------------------------------------------------------------------------------------------
-CPU_SAMPLE_TOKENS = 512
+CPU_SAMPLE_TOKENS = 2048
 
 
 def cpu_step(wl, T_s):
