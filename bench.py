@@ -130,25 +130,27 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # synthetic workload
 # ------------------------------------------------------------------------------------------------
-def make_workload(shape: str, rank: int, n_distinct: int, pin: bool):
-    """Host-side micro-batches of the named shape (SURVEY §8d "D-uniform": W ~ N(0, 0.02^2), hidden ~ N(0,1))."""
+def make_workload(shape: str, rank: int, n_distinct: int, pin: bool, device="cpu"):
+    """Micro-batches of the named shape (SURVEY §8d "D-uniform": W ~ N(0, 0.02^2), hidden ~ N(0,1)), generated on
+    `device` (the GPU for the B200 arm: seconds instead of a single-threaded CPU randn under torchrun) and returned as
+    HOST tensors (pinned when `pin`), exactly what a data loader hands the trainer; `weight` stays on `device`."""
     H, V, T, nseg, n_mb, group, ratio_type = SHAPES[shape]
-    g = torch.Generator().manual_seed(1234 + rank)
-    weight = (torch.randn(V, H, generator=g, dtype=torch.float32) * 0.02).to(torch.bfloat16)
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    weight = (torch.randn(V, H, generator=g, dtype=torch.float32, device=device) * 0.02).to(torch.bfloat16)
     seg = [T // nseg] * nseg
     seg[-1] += T - sum(seg)
     mbs = []
     n_rollouts = nseg * n_mb
     n_rollouts += (-n_rollouts) % group
-    rewards = (torch.rand(n_rollouts, generator=g) < 0.5).float()
+    rewards = (torch.rand(n_rollouts, generator=g, device=device) < 0.5).float().cpu()
     lengths = torch.full((n_rollouts,), T // nseg, dtype=torch.int64)
     adv_r = (rewards.view(-1, group) - rewards.view(-1, group).mean(dim=1, keepdim=True)).reshape(-1)  # drgrpo, data only
     for i in range(n_distinct):
-        hidden = torch.randn(T, H, generator=g, dtype=torch.float32).to(torch.bfloat16)
-        ids = torch.randint(0, V, (T,), generator=g)
+        hidden = torch.randn(T, H, generator=g, dtype=torch.float32, device=device).to(torch.bfloat16).cpu()
+        ids = torch.randint(0, V, (T,), generator=g, device=device).cpu()
         pos = torch.cat([torch.arange(n) for n in seg])
         mask = torch.ones(T, dtype=torch.bool)  # headline: all ones, as FakeDataLoader (rl/data.py:53)
-        old = -11.9 + 0.15 * torch.randn(T, generator=g)  # near ln(1/V): ratios ~ 1 for the near-uniform softmax
+        old = (-11.9 + 0.15 * torch.randn(T, generator=g, device=device)).cpu()  # near ln(1/V): ratios ~ 1 (near-uniform softmax)
         mb = dict(hidden=hidden.unsqueeze(0), input_ids=ids.unsqueeze(0), position_ids=pos.unsqueeze(0),
                   advantages=torch.cat([adv_r[(i * nseg + j) % n_rollouts].repeat(n) for j, n in enumerate(seg)]).unsqueeze(0),
                   logprobs=old.unsqueeze(0), loss_mask=mask.unsqueeze(0), temperature=1.0)
@@ -182,7 +184,7 @@ def run_b200(args):
         dist.init_process_group(backend="nccl", device_id=dev)
     _lib.load()
 
-    wl = make_workload(args.workload, rank, n_distinct=args.distinct, pin=True)
+    wl = make_workload(args.workload, rank, n_distinct=args.distinct, pin=True, device=dev)
     H, V, T, n_mb = wl["H"], wl["V"], wl["T"], wl["n_mb"] if args.micro_batches <= 0 else args.micro_batches
     cfg = P.LossConfig(ratio_type=wl["ratio_type"], ratio_length_norm=False, clip_ratio=8.0)
     mode = 0 if cfg.ratio_type == "token" else 1

@@ -153,3 +153,18 @@ def test_sequence_mode_long_context_micro_step(P):
     assert abs(out["importance_ratio"].item() - r) < 1e-4 * r
     assert abs(out["loss"].item() + 0.5 * r) < 1e-3
     assert h.grad is not None and w.grad is not None and torch.isfinite(h.grad.float()).all()
+
+
+def test_vocab_sharded_two_gpus_nccl():
+    """Real 2-rank NCCL run of the vocab-sharded LM head (skipped on single-GPU boxes)."""
+    import os
+    import subprocess
+    import sys
+
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(root, "tools", "vocab_parallel_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
