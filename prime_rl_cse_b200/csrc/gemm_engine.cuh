@@ -36,6 +36,9 @@ constexpr int ST_LOAD_F32 = 1;    // C += existing fp32 at c_f32
 constexpr int ST_STORE_F32 = 2;   // write fp32 to c_f32
 constexpr int ST_STORE_BF16 = 4;  // write bf16 to c_bf16
 constexpr int ST_LOAD_BF16 = 8;   // C += existing bf16 at c_bf16
+constexpr int ST_TMA = 16;         // epilogue writes through smem staging + TMA store / reduce-add (tma_c)
+constexpr int ST_DEBUG_SKIPB = 1 << 17;
+constexpr int ST_DEBUG_SKIP = 1 << 16;  // profiling aid (PRL_DEBUG_NOSTORE=1): run the GEMM but skip the epilogue's global memory traffic
 
 struct EpiParams {
   int64_t m_rows;  // valid rows of C
@@ -63,10 +66,12 @@ struct EpiParams {
 struct GemmParams {
   CUtensorMap tma_a;
   CUtensorMap tma_b;
+  CUtensorMap tma_c;  // output map for the TMA-store epilogues (fp32 {32 x 32} or bf16 {64 x 32} boxes, 128B swizzle)
   int32_t m_tiles, n_tiles, k_blocks;
   int32_t tiles_per_split, n_splits, group_m, num_items;
   uint64_t a_desc_hi, b_desc_hi;  // smem descriptor templates (everything but the start address)
   uint32_t a_kstep, b_kstep;      // byte advance of the start address per UMMA_K step
+  uint64_t hint_a, hint_b, hint_c;  // L2 eviction priority of the A / B loads and of the epilogue's stores
   EpiParams epi;
 };
 
@@ -170,6 +175,26 @@ __device__ __forceinline__ void dz_chunk(const uint32_t (&v)[32], float inv_temp
   }
 }
 
+// same math as dz_chunk, result packed to 16 x bf16x2 for the TMA-store epilogue
+__device__ __forceinline__ void dz_pack(const uint32_t (&v)[32], float inv_temp, bool round, float coef, float nlse2, int tj,
+                                        uint32_t (&w)[16]) {
+  float d[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a = __uint_as_float(v[j]);
+    if (round) a = ptx::round_bf16(a);
+    const float pr = ptx::ex2(fmaf(a * inv_temp, LOG2E, nlse2));
+    d[j] = -coef * pr;
+  }
+  if ((unsigned)tj < 32u) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j == tj) d[j] += coef;
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(d[2 * j], d[2 * j + 1]);
+}
+
 __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], const EpiParams& e, int64_t row, int64_t col0, int n_valid_in_chunk) {
   float c[32];
 #pragma unroll
@@ -237,15 +262,21 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], const EpiPa
 // per 256 x 256 tile: each CTA stages its own 128 rows of A and its own half (128 rows) of B, the leader CTA
 // issues M = 256 MMAs that read both CTAs' shared memory, each CTA's TMEM holds its 128 accumulator rows.
 // Halving the B bytes per SM and k-step gives 6 instead of 4 pipeline stages in the same shared memory.
+// CG = 4: a cluster of two such pairs stacked along M (512 x 256 per cluster) that share the B tile: every CTA
+// fetches only a quarter of B (64 rows) from L2 and TMA-multicasts it to its counterpart in the other pair, so the
+// L2 -> SM operand traffic per MMA drops by another 25 % (the path is power-bound; section 7 of DESIGN.md).
 // ------------------------------------------------------------------------------------------------
 template <int CG>
 struct Cfg {
-  static constexpr int kStages = (CG == 2) ? 6 : PRL_STAGES;
-  static constexpr int kBRows = BLOCK_N / CG;                    // B rows staged by one CTA
+  static constexpr int kPairs = (CG == 4) ? 2 : 1;               // CTA pairs per cluster
+  static constexpr int kStages = (CG >= 2) ? 6 : PRL_STAGES;
+  static constexpr int kBRows = BLOCK_N / (CG >= 2 ? 2 : 1);     // B rows staged in one CTA's smem
+  static constexpr int kBLoad = kBRows / kPairs;                 // B rows one CTA fetches itself (the rest arrives by multicast)
   static constexpr int kAStage = BLOCK_M * BLOCK_K * 2;          // 16 KB
   static constexpr int kBStage = kBRows * BLOCK_K * 2;           // 32 KB / 16 KB
   static constexpr int kStage = kAStage + kBStage;
-  static constexpr int kSmem = kStages * kStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStaging = 4 /*epilogue warps*/ * 2 /*buffers*/ * 4096;  // 32 rows x 128 B per buffer
+  static constexpr int kSmem = kStages * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int CG, bool A_MN, bool B_MN, int EPI>
@@ -257,18 +288,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + NS * C::kAStage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * C::kStage);
-  uint64_t* full_bar = bars;                  // [NS]   TMA -> MMA          (CG == 2: the leader's is used)
+  uint8_t* smem_stage = smem + NS * C::kStage;  // 1024-byte aligned: the manual 128B swizzle below relies on it
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * C::kStage + C::kStaging);
+  uint64_t* full_bar = bars;                  // [NS]   TMA -> MMA          (CG >= 2: the pair leader's is used)
   uint64_t* empty_bar = bars + NS;            // [NS]   MMA -> TMA          (per CTA)
   uint64_t* tfull_bar = bars + 2 * NS;        // [2]    MMA -> epilogue     (per CTA)
-  uint64_t* tempty_bar = bars + 2 * NS + 2;   // [2]    epilogue -> MMA     (CG == 2: the leader's is used)
+  uint64_t* tempty_bar = bars + 2 * NS + 2;   // [2]    epilogue -> MMA     (CG >= 2: the pair leader's is used)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int rank = (CG == 2) ? (int)ptx::cluster_ctarank() : 0;
-  const int worker = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;
-  const int n_workers = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
+  constexpr bool kPair = CG >= 2;                                   // cta_group::2 MMAs
+  const int crank = kPair ? (int)ptx::cluster_ctarank() : 0;        // rank in the cluster: 0 .. CG-1
+  const int rank = crank & 1;                                       // rank in the CTA pair (0 = leader)
+  const int pair = crank >> 1;                                      // which pair of the cluster
+  const int worker = blockIdx.x / CG;                               // one worker = one cluster
+  const int n_workers = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tma_a);
@@ -277,16 +312,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NS; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], C::kPairs);  // every pair that reads data this CTA wrote must release the slot
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], 4 * CG);  // one arrive per epilogue warp (of both CTAs)
+      ptx::mbar_init(&tempty_bar[i], kPair ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of the pair)
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    if (CG == 2) {
+    if (kPair) {
       ptx::tmem_alloc_cg2(tmem_ptr, TMEM_COLS);
       ptx::tmem_relinquish_cg2();
     } else {
@@ -296,7 +331,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (CG == 2) ptx::cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive
+  if (kPair) ptx::cluster_sync_all();  // the peers' barriers must be initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -307,31 +342,46 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       uint32_t phase = 0;
       for (int item = worker; item < p.num_items; item += n_workers) {
         const Item it = decode_item(p, item);
-        const int m0 = it.m_tile * (BLOCK_M * CG) + rank * BLOCK_M;
+        const int m0 = it.m_tile * (BLOCK_M * CG) + crank * BLOCK_M;
         for (int nt = it.n_begin; nt < it.n_begin + it.n_count; ++nt) {
           const int n0 = nt * BLOCK_N + rank * C::kBRows;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (CG == 1 || rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStage * CG);
+            // profiling aid (PRL_DEBUG_SKIPB=1): skip the B load on odd k-blocks (stale data, WRONG results) to measure how
+            // much of the power budget the L2->SM operand traffic costs
+            const bool skip_b = (p.epi.flags & ST_DEBUG_SKIPB) && (kb & 1);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], (skip_b ? C::kAStage : C::kStage) * (kPair ? 2 : 1));
             uint8_t* sa = smem_a + stage * C::kAStage;
             uint8_t* sb = smem_b + stage * C::kBStage;
-            auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
-              if (CG == 2)
-                ptx::tma_load_2d_cg2(dst, map, &full_bar[stage], c0, c1);
+            auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1, uint64_t hint) {
+              if (kPair)
+                ptx::tma_load_2d_cg2_hint(dst, map, &full_bar[stage], c0, c1, hint);
               else
-                ptx::tma_load_2d(dst, map, &full_bar[stage], c0, c1);
+                ptx::tma_load_2d_hint(dst, map, &full_bar[stage], c0, c1, hint);
+            };
+            // B: with two pairs per cluster this CTA fetches quarter `pair` of the tile and multicasts it to the CTA of
+            // the same pair-rank in both pairs (cluster ranks rank and rank + 2)
+            auto load_b = [&](void* dst, int c0, int c1) {
+              if (CG == 4)
+                ptx::tma_load_2d_cg2_mc_hint(dst, &p.tma_b, &full_bar[stage], c0, c1, (uint16_t)((1u << rank) | (4u << rank)), p.hint_b);
+              else
+                load(dst, &p.tma_b, c0, c1, p.hint_b);
             };
             if (!A_MN) {
-              load(sa, &p.tma_a, kb * BLOCK_K, m0);
+              load(sa, &p.tma_a, kb * BLOCK_K, m0, p.hint_a);
             } else {
 #pragma unroll
-              for (int s = 0; s < BLOCK_M / 64; ++s) load(sa + s * (BLOCK_K * 128), &p.tma_a, m0 + s * 64, kb * BLOCK_K);
+              for (int s = 0; s < BLOCK_M / 64; ++s) load(sa + s * (BLOCK_K * 128), &p.tma_a, m0 + s * 64, kb * BLOCK_K, p.hint_a);
             }
-            if (!B_MN) {
-              load(sb, &p.tma_b, kb * BLOCK_K, n0);
+            if (skip_b) {
+            } else if (!B_MN) {
+              load_b(sb + pair * (C::kBLoad * 128), kb * BLOCK_K, n0 + pair * C::kBLoad);
             } else {
 #pragma unroll
-              for (int s = 0; s < C::kBRows / 64; ++s) load(sb + s * (BLOCK_K * 128), &p.tma_b, n0 + s * 64, kb * BLOCK_K);
+              for (int s = 0; s < C::kBLoad / 64; ++s) {
+                const int slab = pair * (C::kBLoad / 64) + s;
+                load_b(sb + slab * (BLOCK_K * 128), n0 + slab * 64, kb * BLOCK_K);
+              }
             }
             if (++stage == NS) {
               stage = 0;
@@ -344,7 +394,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * CG, BLOCK_N, A_MN, B_MN);
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * (kPair ? 2 : 1), BLOCK_N, A_MN, B_MN);
+      const uint16_t mask_all = (uint16_t)((1u << CG) - 1u), mask_pair = (uint16_t)(3u << (2 * pair));
       // smem descriptor templates and k-step advances come from the host (make_desc_defaults)
       const uint64_t a_hi = p.a_desc_hi, b_hi = p.b_desc_hi;
       const uint32_t a_kstep = p.a_kstep, b_kstep = p.b_kstep;
@@ -367,14 +418,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               const uint64_t ad = ptx::smem_desc(a_hi, sa + k * a_kstep);
               const uint64_t bd = ptx::smem_desc(b_hi, sb + k * b_kstep);
-              if (CG == 2)
+              if (kPair)
                 ptx::umma_bf16_cg2(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
               else
                 ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            // frees the smem slot (in both CTAs) when these MMAs retire
-            if (CG == 2)
-              ptx::umma_commit_cg2(&empty_bar[stage]);
+            // frees the smem slot when these MMAs retire: in every CTA of the cluster that wrote part of it
+            if (kPair)
+              ptx::umma_commit_cg2(&empty_bar[stage], mask_all);
             else
               ptx::umma_commit(&empty_bar[stage]);
             if (++stage == NS) {
@@ -382,9 +433,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               phase ^= 1;
             }
           }
-          // accumulator ready for the epilogue warps (of both CTAs)
-          if (CG == 2)
-            ptx::umma_commit_cg2(&tfull_bar[acc]);
+          // accumulator ready for the epilogue warps (of both CTAs of this pair)
+          if (kPair)
+            ptx::umma_commit_cg2(&tfull_bar[acc], mask_pair);
           else
             ptx::umma_commit(&tfull_bar[acc]);
           acc ^= 1;
@@ -400,9 +451,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     const EpiParams& e = p.epi;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int stage_buf = 0;  // which of this warp's two staging buffers is filled next
     for (int item = worker; item < p.num_items; item += n_workers) {
       const Item it = decode_item(p, item);
-      const int64_t row = (int64_t)it.m_tile * (BLOCK_M * CG) + rank * BLOCK_M + row_in_tile;
+      const int64_t row = (int64_t)it.m_tile * (BLOCK_M * CG) + crank * BLOCK_M + row_in_tile;
       const bool row_ok = row < e.m_rows;
       // per-item row state
       RowStats st = {-INFINITY, 0.f, 0.f, 0.f};
@@ -423,6 +475,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         ptx::tc_fence_after();
         const int64_t n0 = (int64_t)nt * BLOCK_N;
         const int64_t n_left = e.n_cols - n0;  // > 0
+        const bool use_tma = (EPI != EPI_STATS) && (e.flags & ST_TMA) && !(e.flags & ST_DEBUG_SKIP);
+        const bool out_bf16 = (EPI == EPI_DZ) || (e.flags & ST_STORE_BF16);
+        const int row0_warp = it.m_tile * (BLOCK_M * CG) + crank * BLOCK_M + quarter * 32;
 #pragma unroll 1
         for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
           const int64_t c0 = n0 + ch * 32;
@@ -435,20 +490,68 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           const int64_t tj64 = tcol - c0;
           const int tj = (tj64 >= 0 && tj64 < 32) ? (int)tj64 : -1;
           if (EPI == EPI_STATS) {
-            if (n_valid == 32)
+            if (e.flags & ST_DEBUG_SKIP) {
+              st.s += __uint_as_float(v[lane]);  // profiling aid: keep the TMEM load alive, skip the statistics
+            } else if (n_valid == 32)
               stats_chunk<false>(v, st, e.inv_temp, e.round_bf16 != 0, 32, tj);
             else
               stats_chunk<true>(v, st, e.inv_temp, e.round_bf16 != 0, n_valid, tj);
-          } else if (EPI == EPI_DZ) {
-            if (row < e.T) dz_chunk(v, e.inv_temp, e.round_bf16 != 0, coef, nlse2, tj, e.dz + row * e.ldz + c0, n_valid);
+          } else if (!use_tma) {
+            if (EPI == EPI_DZ) {
+              if (row < e.T && !(e.flags & ST_DEBUG_SKIP))
+                dz_chunk(v, e.inv_temp, e.round_bf16 != 0, coef, nlse2, tj, e.dz + row * e.ldz + c0, n_valid);
+            } else {
+              if (row_ok && !(e.flags & ST_DEBUG_SKIP)) store_chunk(v, e, row, c0, n_valid);
+            }
           } else {
-            if (row_ok) store_chunk(v, e, row, c0, n_valid);
+            // ---- registers -> 128B-swizzled smem staging -> TMA store / reduce-add (full-line writes, no SM-side reads)
+            // fp32: one 32 x 32 box per chunk.  bf16: two chunks share one 64 x 32 box (128 B per row).
+            const bool second_half = out_bf16 && (ch & 1);
+            if (!second_half) {
+              // the buffer about to be refilled was handed to TMA two stores ago: wait until it has been read
+              if (lane == 0) ptx::bulk_wait_read<1>();
+              __syncwarp();
+            }
+            const uint32_t sbuf = ptx::smem_u32(smem_stage) + (uint32_t)((quarter * 2 + stage_buf) * 4096) + (uint32_t)lane * 128u;
+            const uint32_t sw = (uint32_t)(lane & 7);
+            if (!out_bf16) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                ptx::st_shared_v4(sbuf + (((uint32_t)q ^ sw) << 4), v[4 * q + 0], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+              uint32_t w[16];
+              if (EPI == EPI_DZ) {
+                dz_pack(v, e.inv_temp, e.round_bf16 != 0, coef, nlse2, tj, w);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              }
+              const uint32_t half = (uint32_t)(ch & 1) * 4u;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                ptx::st_shared_v4(sbuf + (((half + (uint32_t)q) ^ sw) << 4), w[4 * q + 0], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            }
+            const bool last_chunk = (valid64 <= 32) || (ch == BLOCK_N / 32 - 1);
+            if (!out_bf16 || second_half || last_chunk) {
+              ptx::fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                const void* src = smem_stage + (quarter * 2 + stage_buf) * 4096;
+                const int32_t col = (int32_t)(out_bf16 ? (n0 + (ch & ~1) * 32) : c0);
+                if (EPI == EPI_STORE && (e.flags & ST_LOAD_F32))
+                  ptx::tma_reduce_add_2d_hint(&p.tma_c, src, col, row0_warp, p.hint_c);
+                else
+                  ptx::tma_store_2d_hint(&p.tma_c, src, col, row0_warp, p.hint_c);
+                ptx::bulk_commit();
+              }
+              stage_buf ^= 1;
+            }
           }
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (CG == 2)
+          if (kPair)
             ptx::mbar_arrive_leader(&tempty_bar[acc]);
           else
             ptx::mbar_arrive(&tempty_bar[acc]);
@@ -460,14 +563,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         if (row_ok) e.partials[(int64_t)it.split * e.part_stride + row] = make_float4(st.m, st.s, st.u, st.zt);
       }
     }
+    if (EPI != EPI_STATS && lane == 0) ptx::bulk_wait_all();  // staging smem must outlive the last TMA store
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (CG == 2) ptx::cluster_sync_all();  // no CTA of the pair may exit while the other can still signal it
+  if (kPair) ptx::cluster_sync_all();  // no CTA of the cluster may exit while another can still signal it
   if (warp == 2) {
     ptx::tc_fence_after();
-    if (CG == 2)
+    if (kPair)
       ptx::tmem_dealloc_cg2(tmem_base, TMEM_COLS);
     else
       ptx::tmem_dealloc(tmem_base, TMEM_COLS);

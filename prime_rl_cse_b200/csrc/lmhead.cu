@@ -9,6 +9,7 @@ namespace prl {
 // ------------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------------
+static long env_long_fwd(const char* name, long dflt);
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -24,26 +25,38 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 matrix with `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements; 128B-swizzled boxes.
-static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+// matrix with `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements; 128B-swizzled boxes.
+static int make_tmap_t(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer,
+                       bool f32) {
   EncodeTiledFn fn = get_encode_fn();
+  const int64_t esz = f32 ? 4 : 2;
   if (!fn) return fail(PRL_ERR_CUDA, "%s", "cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
-    return fail(PRL_ERR_UNSUPPORTED, "%s", "TMA operand needs a 16-byte aligned base and a row pitch that is a multiple of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * esz) % 16 != 0)
+    return fail(PRL_ERR_UNSUPPORTED, "%s", "TMA tensor needs a 16-byte aligned base and a row pitch that is a multiple of 16 bytes");
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint64_t strides[1] = {(cuuint64_t)(ld * esz)};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PRL_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %s%lld)", "", (long long)r);
   return PRL_OK;
 }
 
 static int cta_group_fwd();
+static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
+  return make_tmap_t(map, base, inner, outer, ld, box_inner, box_outer, false);
+}
+static bool epi_tma_enabled() { return env_long_fwd("PRL_EPI_TMA", 1) != 0; }
+// output map of the TMA-store epilogues: [rows, cols] row-major with pitch ld; fp32 boxes 32 x 32, bf16 boxes 64 x 32 (128 B rows)
+static int make_output_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool f32) {
+  return make_tmap_t(map, base, cols, rows, ld, f32 ? 32 : 64, 32, f32);
+}
 // operand description: K-major => stored [rows, K]; MN-major => stored [K, rows]
 static int make_operand_map(CUtensorMap* map, const void* base, bool mn_major, int64_t rows, int64_t K, int64_t ld, int block_rows) {
-  if (block_rows == BLOCK_N) block_rows = BLOCK_N / cta_group_fwd();  // each CTA of a pair stages half of B's rows
+  // B: a CTA of a pair stages half of the tile's rows; with two pairs per cluster it fetches only a quarter itself
+  if (block_rows == BLOCK_N) block_rows = BLOCK_N / cta_group_fwd();
   if (!mn_major) return make_tmap(map, base, K, rows, ld, BLOCK_K, block_rows);
   return make_tmap(map, base, rows, K, ld, 64, BLOCK_K);
 }
@@ -52,6 +65,7 @@ static long env_long(const char* name, long dflt) {
   const char* s = getenv(name);
   return s ? strtol(s, nullptr, 0) : dflt;
 }
+static long env_long_fwd(const char* name, long dflt) { return env_long(name, dflt); }
 
 static void make_desc_defaults(GemmParams& p, bool a_mn, bool b_mn) {
   // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused (16 B); one UMMA_K step = +32 B.
@@ -68,11 +82,67 @@ static void make_desc_defaults(GemmParams& p, bool a_mn, bool b_mn) {
 
 static int cta_group();
 static int cta_group_fwd() { return cta_group(); }
-// 1 = one CTA per 128x256 tile, 2 = CTA pairs (cta_group::2) on 256x256 tiles (default)
+// CTAs per cluster: 1 = one CTA per 128x256 tile; 2 = a CTA pair (cta_group::2) per 256x256 tile; 4 = two pairs per
+// 512x256 tile sharing B by TMA multicast
 static int cta_group() {
   static int cg = 0;
-  if (cg == 0) cg = env_long("PRL_CTA_GROUP", 2) == 1 ? 1 : 2;
+  if (cg == 0) {
+    const long v = env_long("PRL_CTA_GROUP", 2);
+    cg = (v == 1) ? 1 : (v == 4 ? 4 : 2);
+  }
   return cg;
+}
+
+template <int CG>
+static int cluster_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, cudaStream_t st) {
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<CG>::kSmem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return 0;
+}
+
+// number of clusters that can be co-resident (persistent grid size): all SMs for CG <= 2, fewer for CG = 4 because
+// clusters may not straddle GPCs
+template <int CG>
+static int resident_workers() {
+  static int cached = 0;
+  if (cached == 0) {
+    int n = sm_count() / CG;
+    if (CG > 2) {
+      auto kern = gemm_kernel<CG, false, false, EPI_STORE>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG>::kSmem);
+      cudaLaunchConfig_t cfg;
+      cudaLaunchAttribute attr[1];
+      cluster_launch_config<CG>(cfg, attr, sm_count() / CG * CG, nullptr);
+      int q = 0;
+      if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
+      cudaGetLastError();
+    }
+    cached = n > 0 ? n : 1;
+  }
+  return cached;
+}
+static int workers() { return cta_group() == 4 ? resident_workers<4>() : (cta_group() == 2 ? resident_workers<2>() : resident_workers<1>()); }
+
+// L2 eviction priorities per kernel family; each can be overridden for experiments with PRL_HINT_<FAMILY>_<A|B|C> =
+// 0 (normal) | 1 (evict first) | 2 (evict last)
+static uint64_t hint_value(long v) { return v == 1 ? ptx::kEvictFirst : (v == 2 ? ptx::kEvictLast : ptx::kEvictNormal); }
+static void set_hints(GemmParams& p, const char* family, int a, int b, int c) {
+  char name[64];
+  snprintf(name, sizeof(name), "PRL_HINT_%s_A", family);
+  p.hint_a = hint_value(env_long(name, a));
+  snprintf(name, sizeof(name), "PRL_HINT_%s_B", family);
+  p.hint_b = hint_value(env_long(name, b));
+  snprintf(name, sizeof(name), "PRL_HINT_%s_C", family);
+  p.hint_c = hint_value(env_long(name, c));
 }
 
 template <int CG, bool A_MN, bool B_MN, int EPI>
@@ -86,21 +156,13 @@ static int launch_gemm_cg(const GemmParams& p, cudaStream_t st, const char* name
     attr_set = true;
   }
   if (p.num_items < 1) return PRL_OK;
-  int workers = sm_count() / CG;
-  if (workers > p.num_items) workers = p.num_items;
+  if (env_long("PRL_DEBUG_NOSTORE", 0)) const_cast<GemmParams&>(p).epi.flags |= ST_DEBUG_SKIP;
+  if (env_long("PRL_DEBUG_SKIPB", 0)) const_cast<GemmParams&>(p).epi.flags |= ST_DEBUG_SKIPB;
+  int nw = resident_workers<CG>();
+  if (nw > p.num_items) nw = p.num_items;
   cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(workers * CG);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cluster_launch_config<CG>(cfg, attr, nw * CG, st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return fail_cuda(e, name);
   return check_launch(name);
@@ -108,6 +170,7 @@ static int launch_gemm_cg(const GemmParams& p, cudaStream_t st, const char* name
 
 template <bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const GemmParams& p, cudaStream_t st, const char* name) {
+  if (cta_group() == 4) return launch_gemm_cg<4, A_MN, B_MN, EPI>(p, st, name);
   if (cta_group() == 2) return launch_gemm_cg<2, A_MN, B_MN, EPI>(p, st, name);
   return launch_gemm_cg<1, A_MN, B_MN, EPI>(p, st, name);
 }
@@ -129,7 +192,7 @@ static void schedule_tiles(GemmParams& p) {
 
 // items = (m_tile, n-range): pick the number of vocab splits that minimises the static makespan
 static void schedule_sweeps(GemmParams& p, int max_splits) {
-  const int sms = sm_count() / cta_group();  // workers: CTAs or CTA pairs
+  const int sms = workers();  // CTAs, CTA pairs or clusters of two pairs
   int best_ns = 1;
   long best = -1;
   const int hi = p.n_tiles < max_splits ? p.n_tiles : max_splits;
@@ -182,6 +245,22 @@ __global__ void merge_partials_kernel(const float4* __restrict__ parts, int npar
     if (logp) logp[t] = zt - l;
     if (entropy) entropy[t] = l - u / s;
   }
+}
+
+// fp32 -> bf16 (RN) conversion of the d_hidden accumulator after the last vocab chunk
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n8 = n / 8;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += stride) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * q], b = reinterpret_cast<const float4*>(src)[2 * q + 1];
+    uint4 w;
+    w.x = pack_bf16x2(a.x, a.y);
+    w.y = pack_bf16x2(a.z, a.w);
+    w.z = pack_bf16x2(b.x, b.y);
+    w.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[q] = w;
+  }
+  for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
 static int launch_merge(const float4* parts, int nparts, int64_t stride, int64_t T, int shift, float v_shard, float* logp, float* entropy,
@@ -241,6 +320,7 @@ int prl_lmhead_fwd(const void* hidden, const void* weight, const int64_t* ids, i
     p.epi.inv_temp = inv_temp;
     p.epi.partials = parts;
     p.epi.part_stride = stride;
+    set_hints(p, "FWD", 0, 0, 0);
     rc = launch_gemm<false, false, EPI_STATS>(p, st, "lmhead_fwd_kernel");
     if (rc) return rc;
     nparts = p.n_splits;
@@ -316,6 +396,12 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
       p.epi.dlogp = dlogp;
       p.epi.dz = dz;
       p.epi.ldz = vc;
+      if (epi_tma_enabled()) {
+        rc = make_output_map(&p.tma_c, dz, T, vce, vc, false);
+        if (rc) return rc;
+        p.epi.flags = ST_TMA;
+      }
+      set_hints(p, "DZ", 2, 1, 1);  // hidden band reused across the sweep, W tiles and the dlogits block stream through
       rc = launch_gemm<false, false, EPI_DZ>(p, st, "lmhead_bwd_dz_kernel");
       if (rc) return rc;
     }
@@ -334,16 +420,40 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
       p.epi.n_cols = H;
       p.epi.ldc = H;
       const bool first = (c == 0), last = (c == nchunks - 1);
+      const bool tma = epi_tma_enabled();
       if (d_hidden_f32) {
         p.epi.c_f32 = reinterpret_cast<float*>(d_hidden);
         p.epi.flags = ST_STORE_F32 | (first ? 0 : ST_LOAD_F32);
+        if (tma) {
+          rc = make_output_map(&p.tma_c, d_hidden, T, H, H, true);
+          p.epi.flags |= ST_TMA;
+        }
+      } else if (tma && nchunks == 1) {
+        p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_hidden);
+        p.epi.flags = ST_STORE_BF16 | ST_TMA;
+        rc = make_output_map(&p.tma_c, d_hidden, T, H, H, false);
+      } else if (tma) {
+        // fp32 accumulator in the workspace: TMA store for the first vocab chunk, TMA reduce-add (performed in L2, no
+        // SM-side read) for the others; one conversion pass to bf16 after the last chunk
+        p.epi.c_f32 = dh_acc;
+        p.epi.flags = ST_STORE_F32 | (first ? 0 : ST_LOAD_F32) | ST_TMA;
+        rc = make_output_map(&p.tma_c, dh_acc, T, H, H, true);
       } else {
         p.epi.c_f32 = dh_acc;
         p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_hidden);
         p.epi.flags = (first ? 0 : ST_LOAD_F32) | (last ? ST_STORE_BF16 : ST_STORE_F32);
       }
+      if (rc) return rc;
+      set_hints(p, "DH", 0, 0, 0);
       rc = launch_gemm<false, true, EPI_STORE>(p, st, "lmhead_bwd_dhidden_kernel");
       if (rc) return rc;
+      if (last && tma && !d_hidden_f32 && nchunks > 1) {
+        const int64_t n = T * (int64_t)H;
+        const int64_t need = (n / 8 + 255) / 256 + 1, cap = (int64_t)sm_count() * 8;
+        f32_to_bf16_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(dh_acc, reinterpret_cast<__nv_bfloat16*>(d_hidden), n);
+        rc = check_launch("f32_to_bf16_kernel");
+        if (rc) return rc;
+      }
     }
     // ---- K3: d_weight[c0:c0+vce, H] (+)= dz^T x hidden   (both MN-major) ----
     if (d_weight && (phase_mask & 4)) {
@@ -362,10 +472,21 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
       if (d_weight_dtype == PRL_DT_F32) {
         p.epi.c_f32 = reinterpret_cast<float*>(d_weight) + c0 * H;
         p.epi.flags = ST_STORE_F32 | (accumulate_dw ? ST_LOAD_F32 : 0);
+        if (epi_tma_enabled()) {
+          rc = make_output_map(&p.tma_c, p.epi.c_f32, vce, H, H, true);
+          if (rc) return rc;
+          p.epi.flags |= ST_TMA;
+        }
       } else {
         p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_weight) + c0 * H;
         p.epi.flags = ST_STORE_BF16 | (accumulate_dw ? ST_LOAD_BF16 : 0);
+        if (epi_tma_enabled() && !accumulate_dw) {
+          rc = make_output_map(&p.tma_c, p.epi.c_bf16, vce, H, H, false);
+          if (rc) return rc;
+          p.epi.flags |= ST_TMA;
+        }
       }
+      set_hints(p, "DW", 0, 0, 0);
       rc = launch_gemm<true, true, EPI_STORE>(p, st, "lmhead_bwd_dweight_kernel");
       if (rc) return rc;
     }
@@ -391,6 +512,12 @@ int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t
   p.epi.ldc = N;
   p.epi.c_f32 = C;
   p.epi.flags = ST_STORE_F32 | (accumulate ? ST_LOAD_F32 : 0);
+  if (epi_tma_enabled()) {
+    rc = make_output_map(&p.tma_c, C, M, N, N, true);
+    if (rc) return rc;
+    p.epi.flags |= ST_TMA;
+  }
+  set_hints(p, "GEMM", 0, 0, 0);
   cudaStream_t st = (cudaStream_t)stream;
   if (!a_mn_major && !b_mn_major) return launch_gemm<false, false, EPI_STORE>(p, st, "gemm_kk");
   if (!a_mn_major && b_mn_major) return launch_gemm<false, true, EPI_STORE>(p, st, "gemm_km");
