@@ -354,16 +354,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             uint8_t* sa = smem_a + stage * C::kAStage;
             uint8_t* sb = smem_b + stage * C::kBStage;
             auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1, uint64_t hint) {
-              if (kPair)
-                ptx::tma_load_2d_cg2_hint(dst, map, &full_bar[stage], c0, c1, hint);
-              else
-                ptx::tma_load_2d_hint(dst, map, &full_bar[stage], c0, c1, hint);
+              if (kPair) {
+                if (hint == 0)
+                  ptx::tma_load_2d_cg2(dst, map, &full_bar[stage], c0, c1);
+                else
+                  ptx::tma_load_2d_cg2_hint(dst, map, &full_bar[stage], c0, c1, hint);
+              } else {
+                if (hint == 0)
+                  ptx::tma_load_2d(dst, map, &full_bar[stage], c0, c1);
+                else
+                  ptx::tma_load_2d_hint(dst, map, &full_bar[stage], c0, c1, hint);
+              }
             };
             // B: with two pairs per cluster this CTA fetches quarter `pair` of the tile and multicasts it to the CTA of
             // the same pair-rank in both pairs (cluster ranks rank and rank + 2)
             auto load_b = [&](void* dst, int c0, int c1) {
               if (CG == 4)
-                ptx::tma_load_2d_cg2_mc_hint(dst, &p.tma_b, &full_bar[stage], c0, c1, (uint16_t)((1u << rank) | (4u << rank)), p.hint_b);
+                ptx::tma_load_2d_cg2_mc_hint(dst, &p.tma_b, &full_bar[stage], c0, c1, (uint16_t)((1u << rank) | (4u << rank)),
+                                             p.hint_b ? p.hint_b : ptx::kEvictNormal);
               else
                 load(dst, &p.tma_b, c0, c1, p.hint_b);
             };
@@ -538,10 +546,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               if (lane == 0) {
                 const void* src = smem_stage + (quarter * 2 + stage_buf) * 4096;
                 const int32_t col = (int32_t)(out_bf16 ? (n0 + (ch & ~1) * 32) : c0);
-                if (EPI == EPI_STORE && (e.flags & ST_LOAD_F32))
-                  ptx::tma_reduce_add_2d_hint(&p.tma_c, src, col, row0_warp, p.hint_c);
-                else
-                  ptx::tma_store_2d_hint(&p.tma_c, src, col, row0_warp, p.hint_c);
+                const bool reduce = (EPI == EPI_STORE) && (e.flags & ST_LOAD_F32);
+                if (p.hint_c == 0) {
+                  if (reduce)
+                    ptx::tma_reduce_add_2d(&p.tma_c, src, col, row0_warp);
+                  else
+                    ptx::tma_store_2d(&p.tma_c, src, col, row0_warp);
+                } else {
+                  if (reduce)
+                    ptx::tma_reduce_add_2d_hint(&p.tma_c, src, col, row0_warp, p.hint_c);
+                  else
+                    ptx::tma_store_2d_hint(&p.tma_c, src, col, row0_warp, p.hint_c);
+                }
                 ptx::bulk_commit();
               }
               stage_buf ^= 1;

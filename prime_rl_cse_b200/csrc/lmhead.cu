@@ -133,8 +133,8 @@ static int resident_workers() {
 static int workers() { return cta_group() == 4 ? resident_workers<4>() : (cta_group() == 2 ? resident_workers<2>() : resident_workers<1>()); }
 
 // L2 eviction priorities per kernel family; each can be overridden for experiments with PRL_HINT_<FAMILY>_<A|B|C> =
-// 0 (normal) | 1 (evict first) | 2 (evict last)
-static uint64_t hint_value(long v) { return v == 1 ? ptx::kEvictFirst : (v == 2 ? ptx::kEvictLast : ptx::kEvictNormal); }
+// 0 (no hint) | 1 (evict first) | 2 (evict last) | 3 (explicit evict-normal)
+static uint64_t hint_value(long v) { return v == 1 ? ptx::kEvictFirst : (v == 2 ? ptx::kEvictLast : (v == 3 ? ptx::kEvictNormal : 0)); }
 static void set_hints(GemmParams& p, const char* family, int a, int b, int c) {
   char name[64];
   snprintf(name, sizeof(name), "PRL_HINT_%s_A", family);

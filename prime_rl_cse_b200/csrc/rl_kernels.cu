@@ -69,6 +69,85 @@ __device__ __forceinline__ float warp_sum_l8(const float* __restrict__ x, int G,
   return s;
 }
 
+// G <= 32: floor(32 / G) groups per warp, one rollout per lane, fully coalesced loads and stores.  Every lane of a
+// group evaluates the same L8-ordered sum with ~G/8 + 8 shuffles inside its sub-warp (redundant but branch-free): 8 B of HBM
+// traffic per rollout (16 B for opo), so large batches run at HBM speed instead of one under-filled warp per group.
+constexpr int ADV_U = 4;  // independent group-sets in flight per warp (memory- and shuffle-latency hiding)
+
+__device__ __forceinline__ void subwarp_sum_l8(const float (&x)[ADV_U], int G, int base, float (&s)[ADV_U]) {
+  const int n8 = (G / 8) * 8;
+  // lane accumulators: lane j < 8 of the group gets ((x[j] + x[j+8]) + x[j+16]) + x[j+24]  (other lanes: unused values)
+  float a[ADV_U];
+#pragma unroll
+  for (int u = 0; u < ADV_U; ++u) a[u] = x[u];
+  for (int q = 8; q < n8; q += 8) {
+#pragma unroll
+    for (int u = 0; u < ADV_U; ++u) a[u] = __fadd_rn(a[u], __shfl_down_sync(FULL, x[u], q));
+  }
+#pragma unroll
+  for (int u = 0; u < ADV_U; ++u) s[u] = 0.f;
+  if (n8 > 0) {
+#pragma unroll
+    for (int u = 0; u < ADV_U; ++u) s[u] = __shfl_sync(FULL, a[u], base);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+#pragma unroll
+      for (int u = 0; u < ADV_U; ++u) s[u] = __fadd_rn(s[u], __shfl_sync(FULL, a[u], base + j));
+    }
+  }
+  for (int i = n8; i < G; ++i) {
+#pragma unroll
+    for (int u = 0; u < ADV_U; ++u) s[u] = __fadd_rn(s[u], __shfl_sync(FULL, x[u], base + i));
+  }
+}
+
+__global__ void __launch_bounds__(256) advantages_small_group_kernel(const float* __restrict__ rewards,
+                                                                     const int64_t* __restrict__ lengths, int64_t ngroups, int G,
+                                                                     int kind, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int gpw = 32 / G;                      // groups per warp and group-set
+  const int gl = lane / G;                     // group of this lane inside the warp (>= gpw: idle lane)
+  const int base = gl < gpw ? gl * G : 0;      // idle lanes still take part in the shuffles
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t n_sets = (ngroups + gpw - 1) / gpw;
+  const int64_t n_iter = (n_sets + ADV_U - 1) / ADV_U;
+  for (int64_t it = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < n_iter; it += warps_total) {
+    int64_t idx[ADV_U];
+    bool active[ADV_U];
+    float r[ADV_U], w[ADV_U], num[ADV_U], den[ADV_U];
+#pragma unroll
+    for (int u = 0; u < ADV_U; ++u) {
+      const int64_t g = (it * ADV_U + u) * gpw + gl;
+      active[u] = gl < gpw && g < ngroups;
+      idx[u] = g * G + (lane - gl * G);
+      r[u] = active[u] ? rewards[idx[u]] : 0.f;
+    }
+    if (kind == PRL_ADV_OPO) {
+      float rw[ADV_U];
+#pragma unroll
+      for (int u = 0; u < ADV_U; ++u) {
+        w[u] = active[u] ? (float)lengths[idx[u]] : 0.f;
+        rw[u] = __fmul_rn(r[u], w[u]);
+      }
+      subwarp_sum_l8(rw, G, base, num);
+      subwarp_sum_l8(w, G, base, den);
+    } else {
+      subwarp_sum_l8(r, G, base, num);
+#pragma unroll
+      for (int u = 0; u < ADV_U; ++u) den[u] = (float)G;
+    }
+#pragma unroll
+    for (int u = 0; u < ADV_U; ++u) {
+      if (active[u]) {
+        float a = __fsub_rn(r[u], __fdiv_rn(num[u], den[u]));
+        if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = fmaxf(a, 0.f);
+        if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
+        out[idx[u]] = a;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) advantages_kernel(const float* __restrict__ rewards, const int64_t* __restrict__ lengths,
                                                          int64_t ngroups, int G, int kind, float* __restrict__ out,
                                                          const int64_t* __restrict__ tok_offsets, float* __restrict__ token_out) {
@@ -427,6 +506,13 @@ int prl_advantages_f32(const float* rewards, const int64_t* lengths, int64_t n, 
   const int64_t blocks_needed = (ngroups + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 8;
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  if (group <= 32 && token_out == nullptr) {
+    const int gpw = 32 / group;
+    const int64_t need = (((ngroups + gpw - 1) / gpw + 3) / 4 + 7) / 8;  // 4 group-sets per warp iteration, 8 warps per CTA
+    const int g2 = (int)(need < cap * 4 ? need : cap * 4);
+    advantages_small_group_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(rewards, lengths, ngroups, group, kind, out);
+    return check_launch("advantages_small_group_kernel");
+  }
   advantages_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rewards, lengths, ngroups, group, kind, out, tok_offsets, token_out);
   return check_launch("advantages_kernel");
 }

@@ -325,3 +325,15 @@ def test_micro_step_vs_oracle(P, T, H, V, tau, mode, vchunk):
         assert float(h.grad[-1].abs().max()) == 0.0  # the dropped last position gets no gradient (loss.py:54)
     finally:
         os.environ.pop("PRL_VCHUNK", None)
+
+
+@pytest.mark.parametrize("cta_group,epi_tma", [(1, 1), (2, 0), (4, 1), (1, 0)])
+def test_engine_variants(P, cta_group, epi_tma):
+    """The non-default engine variants (single CTA, two pairs with B multicast, register epilogue) stay correct."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PRL_CTA_GROUP=str(cta_group), PRL_EPI_TMA=str(epi_tma))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "variant_check.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]

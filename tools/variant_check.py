@@ -1,0 +1,45 @@
+"""Correctness of the non-default engine variants, selected by environment before the library is first used:
+PRL_CTA_GROUP=1|2|4 (CTA, CTA pair, two pairs with B multicast) and PRL_EPI_TMA=0|1 (register vs TMA-store epilogue).
+Runs the plain GEMM in all four operand majornesses plus one fused LM-head micro-step against torch fp32."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import prime_rl_cse_b200 as P
+from prime_rl_cse_b200 import _lib, lm_head_backward_raw, lm_head_forward_raw
+
+lib = _lib.load()
+dev = "cuda"
+torch.manual_seed(0)
+ok = True
+for (M, N, K) in [(384, 520, 200), (1024, 768, 1024)]:
+    A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16()
+    want = A.float() @ B.float().t()
+    for a_mn in (0, 1):
+        for b_mn in (0, 1):
+            a_st = A.t().contiguous() if a_mn else A; b_st = B.t().contiguous() if b_mn else B
+            C = torch.full((M, N), float("nan"), device=dev)
+            for acc in (0, 1):
+                _lib.check(lib.prl_gemm_bf16_f32(_lib.ptr(a_st), _lib.ptr(b_st), _lib.ptr(C), M, N, K, a_mn, b_mn, acc, _lib.stream()), "gemm")
+            err = (C - 2 * want).abs().max().item()
+            good = err <= 4e-3 * max(1.0, want.abs().max().item())
+            ok &= good
+            if not good:
+                print(f"GEMM M{M} N{N} K{K} a_mn={a_mn} b_mn={b_mn}: max err {err}")
+T, H, V, tau = 700, 512, 20000 + 64, 0.7
+hidden = torch.randn(T, H, device=dev).bfloat16(); W = (torch.randn(V, H, device=dev) * 0.1).bfloat16()
+ids = torch.randint(0, V, (T,), device=dev); g = torch.randn(T, device=dev) / T
+logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, 1 / tau)
+z = torch.zeros(T, V, device=dev); z[1:] = (hidden[:-1].float() @ W.float().t()).bfloat16().float() / tau
+ref_lse = torch.logsumexp(z, -1); ref_lp = z.gather(1, ids[:, None])[:, 0] - ref_lse
+d = (logp - ref_lp).abs()
+good = (d < 1e-3).float().mean().item() > 0.98 and d.max().item() < 0.07
+ok &= good
+dh, dw = lm_head_backward_raw(hidden, W, ids, lse, g, 1 / tau, vchunk=8192)
+p = torch.exp(z - lse[:, None]); dz = -p * g[:, None]; dz[torch.arange(T), ids] += g
+dl = torch.zeros_like(dz); dl[:-1] = (dz[1:] / tau).bfloat16().float()
+ref_dh, ref_dw = dl @ W.float(), dl.t() @ hidden.float()
+r1 = ((dh.float() - ref_dh).norm() / ref_dh.norm()).item(); r2 = ((dw.float() - ref_dw).norm() / ref_dw.norm()).item()
+ok &= r1 < 1e-2 and r2 < 1e-2
+print(f"CTA_GROUP={os.environ.get('PRL_CTA_GROUP','2')} EPI_TMA={os.environ.get('PRL_EPI_TMA','1')}: logp max err {d.max().item():.2e}, "
+      f"dH rel {r1:.2e}, dW rel {r2:.2e} -> {'OK' if ok else 'FAIL'}")
+sys.exit(0 if ok else 1)
