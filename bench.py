@@ -313,7 +313,7 @@ def run_b200(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps
 
-        vc = 8192
+        vc = 16384  # default vocab chunk of prl_lmhead_bwd
         nchunks = (V + vc - 1) // vc
         fam["lmhead_fwd_kernel"] = dict(ms_per_launch=ev_time(lambda: P.lm_head_forward_raw(hid, Wd, ids, 1.0, workspace=ws_f), 8),
                                         launches_per_mb=1, flops_per_launch=2.0 * T * H * V)

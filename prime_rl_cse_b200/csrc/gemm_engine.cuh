@@ -25,7 +25,6 @@ constexpr int UMMA_K = 16;
 #ifndef PRL_STAGES
 #define PRL_STAGES 4
 #endif
-constexpr int GEMM_THREADS = 256;
 constexpr int TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -266,23 +265,36 @@ __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], const EpiPa
 // fetches only a quarter of B (64 rows) from L2 and TMA-multicasts it to its counterpart in the other pair, so the
 // L2 -> SM operand traffic per MMA drops by another 25 % (the path is power-bound; section 7 of DESIGN.md).
 // ------------------------------------------------------------------------------------------------
-template <int CG>
+// MS = 2 (CG = 2 only): TWO 256-row M sub-tiles per CTA pair share every B k-block (512 x 256 per pair).  A's bytes per
+// MMA stay the same, B's halve: 25 % fewer operand bytes from L2 per MMA, which matters because the path is power-bound
+// (DESIGN.md section 7).  The two sub-tiles use the two 256-column TMEM accumulators, so the epilogue (8 warps: one group
+// of 4 per sub-tile) no longer overlaps the next tile's MMAs; the trade is measured in DESIGN.md.
+template <int CG, int MS, int EPI>
 struct Cfg {
   static constexpr int kPairs = (CG == 4) ? 2 : 1;               // CTA pairs per cluster
-  static constexpr int kStages = (CG >= 2) ? 6 : PRL_STAGES;
   static constexpr int kBRows = BLOCK_N / (CG >= 2 ? 2 : 1);     // B rows staged in one CTA's smem
   static constexpr int kBLoad = kBRows / kPairs;                 // B rows one CTA fetches itself (the rest arrives by multicast)
-  static constexpr int kAStage = BLOCK_M * BLOCK_K * 2;          // 16 KB
+  static constexpr int kASub = BLOCK_M * BLOCK_K * 2;            // 16 KB per M sub-tile
+  static constexpr int kAStage = MS * kASub;
   static constexpr int kBStage = kBRows * BLOCK_K * 2;           // 32 KB / 16 KB
   static constexpr int kStage = kAStage + kBStage;
-  static constexpr int kStaging = 4 /*epilogue warps*/ * 2 /*buffers*/ * 4096;  // 32 rows x 128 B per buffer
-  static constexpr int kSmem = kStages * kStage + kStaging + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiWarps = 4 * MS;
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;
+  // smem staging of the TMA-store epilogues: 2 buffers of 32 rows x 128 B per epilogue warp (none for the statistics epilogue)
+  static constexpr int kStaging = (EPI == EPI_STATS) ? 0 : kEpiWarps * 2 * 4096;
+  static constexpr int kBudget = 232448 - 1024 /*align slack*/ - 256 /*barriers*/ - kStaging;
+  static constexpr int kFit = kBudget / kStage;
+  static constexpr int kStages = (CG == 1) ? PRL_STAGES : (kFit > 8 ? 8 : kFit);
+  static constexpr int kSmem = kStages * kStage + kStaging + 1024 + 256;
+  static constexpr int kRowsPerTile = BLOCK_M * CG * MS;         // rows of C one cluster produces per tile
 };
 
-template <int CG, bool A_MN, bool B_MN, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<CG>;
+template <int CG, int MS, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<CG, MS, EPI>;
   constexpr int NS = C::kStages;
+  static_assert(MS == 1 || CG == 2, "M sub-tiling is implemented for CTA pairs only");
+  static_assert(NS >= 2, "pipeline needs at least two stages");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment (the dynamic smem base offset is the same in both CTAs of a pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -304,6 +316,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   const int pair = crank >> 1;                                      // which pair of the cluster
   const int worker = blockIdx.x / CG;                               // one worker = one cluster
   const int n_workers = gridDim.x / CG;
+  constexpr int kSubRows = BLOCK_M * (kPair ? 2 : 1) * C::kPairs;   // rows between consecutive M sub-tiles of a tile
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.tma_a);
@@ -316,7 +329,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], kPair ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of the pair)
+      ptx::mbar_init(&tempty_bar[i], kPair ? 8 : 4);  // one arrive per epilogue warp of the group (of both CTAs of the pair)
     }
     ptx::fence_barrier_init();
   }
@@ -342,7 +355,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       uint32_t phase = 0;
       for (int item = worker; item < p.num_items; item += n_workers) {
         const Item it = decode_item(p, item);
-        const int m0 = it.m_tile * (BLOCK_M * CG) + crank * BLOCK_M;
+        const int m0 = it.m_tile * C::kRowsPerTile + crank * BLOCK_M;
         for (int nt = it.n_begin; nt < it.n_begin + it.n_count; ++nt) {
           const int n0 = nt * BLOCK_N + rank * C::kBRows;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -375,11 +388,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               else
                 load(dst, &p.tma_b, c0, c1, p.hint_b);
             };
-            if (!A_MN) {
-              load(sa, &p.tma_a, kb * BLOCK_K, m0, p.hint_a);
-            } else {
 #pragma unroll
-              for (int s = 0; s < BLOCK_M / 64; ++s) load(sa + s * (BLOCK_K * 128), &p.tma_a, m0 + s * 64, kb * BLOCK_K, p.hint_a);
+            for (int ms = 0; ms < MS; ++ms) {
+              uint8_t* sas = sa + ms * C::kASub;
+              const int m0s = m0 + ms * kSubRows;
+              if (!A_MN) {
+                load(sas, &p.tma_a, kb * BLOCK_K, m0s, p.hint_a);
+              } else {
+#pragma unroll
+                for (int s = 0; s < BLOCK_M / 64; ++s) load(sas + s * (BLOCK_K * 128), &p.tma_a, m0s + s * 64, kb * BLOCK_K, p.hint_a);
+              }
             }
             if (skip_b) {
             } else if (!B_MN) {
@@ -400,7 +418,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
+    // ===================== MMA issuer (pair leader only) =====================
     if (lane == 0 && rank == 0) {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M * (kPair ? 2 : 1), BLOCK_N, A_MN, B_MN);
       const uint16_t mask_all = (uint16_t)((1u << CG) - 1u), mask_pair = (uint16_t)(3u << (2 * pair));
@@ -409,14 +427,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
       const uint32_t a_kstep = p.a_kstep, b_kstep = p.b_kstep;
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int acc = 0;             // MS == 1: accumulator buffer of the current tile (double buffering)
+      uint32_t acc_phase = 0;  // MS == 2: both buffers belong to every tile, the phase flips per tile
       for (int item = worker; item < p.num_items; item += n_workers) {
         const Item it = decode_item(p, item);
         for (int nt = 0; nt < it.n_count; ++nt) {
-          ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          if (MS == 1) {
+            ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+          } else {
+            ptx::mbar_wait(&tempty_bar[0], acc_phase ^ 1);
+            ptx::mbar_wait(&tempty_bar[1], acc_phase ^ 1);
+          }
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
           for (int kb = 0; kb < p.k_blocks; ++kb) {
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
@@ -424,12 +446,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             const uint32_t sb = ptx::smem_u32(smem_b + stage * C::kBStage);
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t ad = ptx::smem_desc(a_hi, sa + k * a_kstep);
               const uint64_t bd = ptx::smem_desc(b_hi, sb + k * b_kstep);
-              if (kPair)
-                ptx::umma_bf16_cg2(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-              else
-                ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+              for (int ms = 0; ms < MS; ++ms) {
+                const uint64_t ad = ptx::smem_desc(a_hi, sa + ms * C::kASub + k * a_kstep);
+                const uint32_t d_tmem = tmem_base + (MS == 1 ? acc : ms) * BLOCK_N;
+                if (kPair)
+                  ptx::umma_bf16_cg2(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                else
+                  ptx::umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
             }
             // frees the smem slot when these MMAs retire: in every CTA of the cluster that wrote part of it
             if (kPair)
@@ -441,28 +467,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               phase ^= 1;
             }
           }
-          // accumulator ready for the epilogue warps (of both CTAs of this pair)
-          if (kPair)
-            ptx::umma_commit_cg2(&tfull_bar[acc], mask_pair);
-          else
-            ptx::umma_commit(&tfull_bar[acc]);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
+          // accumulator(s) ready for the epilogue warps (of both CTAs of this pair)
+#pragma unroll
+          for (int ms = 0; ms < MS; ++ms) {
+            uint64_t* bar = &tfull_bar[MS == 1 ? acc : ms];
+            if (kPair)
+              ptx::umma_commit_cg2(bar, mask_pair);
+            else
+              ptx::umma_commit(bar);
+          }
+          if (MS == 1) {
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+          } else {
+            acc_phase ^= 1;
+          }
         }
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (every CTA: its own 128 accumulator rows) =====================
+    // ===================== epilogue (every CTA: its own 128 accumulator rows per sub-tile) =====================
     const int quarter = warp & 3;
+    const int group = (warp - 4) >> 2;  // M sub-tile this warp group drains (MS == 2); 0 otherwise
+    const int ewarp = warp - 4;         // index of this warp's staging buffers
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
     const EpiParams& e = p.epi;
-    int acc = 0;
+    int acc = (MS == 1) ? 0 : group;
     uint32_t acc_phase = 0;
     int stage_buf = 0;  // which of this warp's two staging buffers is filled next
     for (int item = worker; item < p.num_items; item += n_workers) {
       const Item it = decode_item(p, item);
-      const int64_t row = (int64_t)it.m_tile * (BLOCK_M * CG) + crank * BLOCK_M + row_in_tile;
+      const int64_t row_base = (int64_t)it.m_tile * C::kRowsPerTile + group * kSubRows + crank * BLOCK_M;
+      const int64_t row = row_base + row_in_tile;
       const bool row_ok = row < e.m_rows;
       // per-item row state
       RowStats st = {-INFINITY, 0.f, 0.f, 0.f};
@@ -485,7 +522,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
         const int64_t n_left = e.n_cols - n0;  // > 0
         const bool use_tma = (EPI != EPI_STATS) && (e.flags & ST_TMA) && !(e.flags & ST_DEBUG_SKIP);
         const bool out_bf16 = (EPI == EPI_DZ) || (e.flags & ST_STORE_BF16);
-        const int row0_warp = it.m_tile * (BLOCK_M * CG) + crank * BLOCK_M + quarter * 32;
+        const int row0_warp = (int)row_base + quarter * 32;
 #pragma unroll 1
         for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
           const int64_t c0 = n0 + ch * 32;
@@ -511,7 +548,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
             } else {
               if (row_ok && !(e.flags & ST_DEBUG_SKIP)) store_chunk(v, e, row, c0, n_valid);
             }
-          } else {
+          } else if (C::kStaging > 0) {
             // ---- registers -> 128B-swizzled smem staging -> TMA store / reduce-add (full-line writes, no SM-side reads)
             // fp32: one 32 x 32 box per chunk.  bf16: two chunks share one 64 x 32 box (128 B per row).
             const bool second_half = out_bf16 && (ch & 1);
@@ -520,7 +557,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               if (lane == 0) ptx::bulk_wait_read<1>();
               __syncwarp();
             }
-            const uint32_t sbuf = ptx::smem_u32(smem_stage) + (uint32_t)((quarter * 2 + stage_buf) * 4096) + (uint32_t)lane * 128u;
+            const uint32_t sbuf = ptx::smem_u32(smem_stage) + (uint32_t)((ewarp * 2 + stage_buf) * 4096) + (uint32_t)lane * 128u;
             const uint32_t sw = (uint32_t)(lane & 7);
             if (!out_bf16) {
 #pragma unroll
@@ -544,7 +581,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
               ptx::fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
-                const void* src = smem_stage + (quarter * 2 + stage_buf) * 4096;
+                const void* src = smem_stage + (ewarp * 2 + stage_buf) * 4096;
                 const int32_t col = (int32_t)(out_bf16 ? (n0 + (ch & ~1) * 32) : c0);
                 const bool reduce = (EPI == EPI_STORE) && (e.flags & ST_LOAD_F32);
                 if (p.hint_c == 0) {
@@ -572,8 +609,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
           else
             ptx::mbar_arrive(&tempty_bar[acc]);
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        if (MS == 1) {
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        } else {
+          acc_phase ^= 1;
+        }
       }
       if (EPI == EPI_STATS) {
         if (row_ok) e.partials[(int64_t)it.split * e.part_stride + row] = make_float4(st.m, st.s, st.u, st.zt);

@@ -93,20 +93,32 @@ static int cta_group() {
   return cg;
 }
 
-template <int CG>
-static int cluster_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, cudaStream_t st) {
+// M sub-tiles per CTA-pair tile: 1 = 256 x 256 tiles with double-buffered accumulators; 2 = 512 x 256 tiles (two sub-tiles
+// share every B k-block: 25 % fewer operand bytes per MMA, no epilogue/mainloop overlap).  Only with PRL_CTA_GROUP=2.
+// Measured: +12..16 % on the d_hidden / d_weight GEMMs (long K loops, cheap epilogue), -1 % on the
+// forward / dlogits sweeps (K = H only, heavy epilogue) -> default 2 for the store-epilogue GEMMs, 1 for the sweeps.
+// PRL_MSUB=1|2 forces one value everywhere.
+static int msub(int epi) {
+  static int forced = -1;
+  if (forced < 0) forced = (int)env_long("PRL_MSUB", 0);
+  if (cta_group() != 2) return 1;
+  if (forced == 1 || forced == 2) return forced;
+  return epi == EPI_STORE ? 2 : 1;
+}
+
+static void cluster_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int cg, int grid, int threads, int smem,
+                                  cudaStream_t st) {
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Cfg<CG>::kSmem;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = cg;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return 0;
 }
 
 // number of clusters that can be co-resident (persistent grid size): all SMs for CG <= 2, fewer for CG = 4 because
@@ -117,11 +129,12 @@ static int resident_workers() {
   if (cached == 0) {
     int n = sm_count() / CG;
     if (CG > 2) {
-      auto kern = gemm_kernel<CG, false, false, EPI_STORE>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CG>::kSmem);
+      using C = Cfg<CG, 1, EPI_STORE>;
+      auto kern = gemm_kernel<CG, 1, false, false, EPI_STORE>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
       cudaLaunchConfig_t cfg;
       cudaLaunchAttribute attr[1];
-      cluster_launch_config<CG>(cfg, attr, sm_count() / CG * CG, nullptr);
+      cluster_launch_config(cfg, attr, CG, sm_count() / CG * CG, C::kThreads, C::kSmem, nullptr);
       int q = 0;
       if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
       cudaGetLastError();
@@ -145,13 +158,13 @@ static void set_hints(GemmParams& p, const char* family, int a, int b, int c) {
   p.hint_c = hint_value(env_long(name, c));
 }
 
-template <int CG, bool A_MN, bool B_MN, int EPI>
+template <int CG, int MS, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm_cg(const GemmParams& p, cudaStream_t st, const char* name) {
+  using C = Cfg<CG, MS, EPI>;
   static bool attr_set = false;
-  auto kern = gemm_kernel<CG, A_MN, B_MN, EPI>;
-  constexpr int smem = Cfg<CG>::kSmem;
+  auto kern = gemm_kernel<CG, MS, A_MN, B_MN, EPI>;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
     attr_set = true;
   }
@@ -162,7 +175,7 @@ static int launch_gemm_cg(const GemmParams& p, cudaStream_t st, const char* name
   if (nw > p.num_items) nw = p.num_items;
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  cluster_launch_config<CG>(cfg, attr, nw * CG, st);
+  cluster_launch_config(cfg, attr, CG, nw * CG, C::kThreads, C::kSmem, st);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return fail_cuda(e, name);
   return check_launch(name);
@@ -170,13 +183,14 @@ static int launch_gemm_cg(const GemmParams& p, cudaStream_t st, const char* name
 
 template <bool A_MN, bool B_MN, int EPI>
 static int launch_gemm(const GemmParams& p, cudaStream_t st, const char* name) {
-  if (cta_group() == 4) return launch_gemm_cg<4, A_MN, B_MN, EPI>(p, st, name);
-  if (cta_group() == 2) return launch_gemm_cg<2, A_MN, B_MN, EPI>(p, st, name);
-  return launch_gemm_cg<1, A_MN, B_MN, EPI>(p, st, name);
+  if (cta_group() == 4) return launch_gemm_cg<4, 1, A_MN, B_MN, EPI>(p, st, name);
+  if (cta_group() == 2 && msub(EPI) == 2) return launch_gemm_cg<2, 2, A_MN, B_MN, EPI>(p, st, name);
+  if (cta_group() == 2) return launch_gemm_cg<2, 1, A_MN, B_MN, EPI>(p, st, name);
+  return launch_gemm_cg<1, 1, A_MN, B_MN, EPI>(p, st, name);
 }
 
-static void set_tiling(GemmParams& p, int64_t M, int64_t N, int64_t K) {
-  const int64_t bm = (int64_t)BLOCK_M * cta_group();
+static void set_tiling(GemmParams& p, int64_t M, int64_t N, int64_t K, int epi) {
+  const int64_t bm = (int64_t)BLOCK_M * cta_group() * msub(epi);
   p.m_tiles = (int)((M + bm - 1) / bm);
   p.n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
   p.k_blocks = (int)((K + BLOCK_K - 1) / BLOCK_K);
@@ -186,12 +200,13 @@ static void set_tiling(GemmParams& p, int64_t M, int64_t N, int64_t K) {
 static void schedule_tiles(GemmParams& p) {
   p.tiles_per_split = 1;
   p.n_splits = p.n_tiles;
-  p.group_m = (int)env_long("PRL_GROUP_M", 8) / cta_group();
+  p.group_m = (int)env_long("PRL_GROUP_M", 8) / (cta_group() * msub(EPI_STORE));
+  if (p.group_m < 1) p.group_m = 1;
   p.num_items = p.m_tiles * p.n_splits;
 }
 
 // items = (m_tile, n-range): pick the number of vocab splits that minimises the static makespan
-static void schedule_sweeps(GemmParams& p, int max_splits) {
+static void schedule_sweeps(GemmParams& p, int max_splits, int epi) {
   const int sms = workers();  // CTAs, CTA pairs or clusters of two pairs
   int best_ns = 1;
   long best = -1;
@@ -208,7 +223,8 @@ static void schedule_sweeps(GemmParams& p, int max_splits) {
   }
   p.tiles_per_split = (p.n_tiles + best_ns - 1) / best_ns;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.group_m = (int)env_long("PRL_SWEEP_GROUP_M", 32) / cta_group();
+  p.group_m = (int)env_long("PRL_SWEEP_GROUP_M", 32) / (cta_group() * msub(epi));
+  if (p.group_m < 1) p.group_m = 1;
   p.num_items = p.m_tiles * p.n_splits;
 }
 
@@ -307,8 +323,8 @@ int prl_lmhead_fwd(const void* hidden, const void* weight, const int64_t* ids, i
     if (rc) return rc;
     rc = make_operand_map(&p.tma_b, weight, false, V, H, H, BLOCK_N);
     if (rc) return rc;
-    set_tiling(p, rows, V, H);
-    schedule_sweeps(p, MAX_SPLITS);
+    set_tiling(p, rows, V, H, EPI_STATS);
+    schedule_sweeps(p, MAX_SPLITS, EPI_STATS);
     make_desc_defaults(p, false, false);
     p.epi.m_rows = rows;
     p.epi.n_cols = V;
@@ -337,7 +353,7 @@ int prl_lmhead_merge_partials(const float* partials, int32_t nparts, int64_t T, 
 }
 
 static int64_t pick_vchunk(int64_t V, int64_t vchunk) {
-  if (vchunk <= 0) vchunk = env_long("PRL_VCHUNK", 8192);
+  if (vchunk <= 0) vchunk = env_long("PRL_VCHUNK", 16384);
   vchunk = round_up(vchunk, BLOCK_N);
   const int64_t vpad = round_up(V, BLOCK_N);
   return vchunk < vpad ? vchunk : vpad;
@@ -381,8 +397,8 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
       if (rc) return rc;
       rc = make_operand_map(&p.tma_b, W + c0 * H, false, vce, H, H, BLOCK_N);
       if (rc) return rc;
-      set_tiling(p, T, vce, H);
-      schedule_sweeps(p, MAX_SPLITS);
+      set_tiling(p, T, vce, H, EPI_DZ);
+      schedule_sweeps(p, MAX_SPLITS, EPI_DZ);
       make_desc_defaults(p, false, false);
       p.epi.m_rows = T;
       p.epi.n_cols = vce;
@@ -413,7 +429,7 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
       if (rc) return rc;
       rc = make_operand_map(&p.tma_b, W + c0 * H, true, H, vce, H, BLOCK_N);
       if (rc) return rc;
-      set_tiling(p, T, H, vce);
+      set_tiling(p, T, H, vce, EPI_STORE);
       schedule_tiles(p);
       make_desc_defaults(p, false, true);
       p.epi.m_rows = T;
@@ -463,7 +479,7 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
       if (rc) return rc;
       rc = make_operand_map(&p.tma_b, hidden, true, H, T, H, BLOCK_N);
       if (rc) return rc;
-      set_tiling(p, vce, H, T);
+      set_tiling(p, vce, H, T, EPI_STORE);
       schedule_tiles(p);
       make_desc_defaults(p, true, true);
       p.epi.m_rows = vce;
@@ -504,7 +520,7 @@ int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t
   if (rc) return rc;
   rc = make_operand_map(&p.tma_b, B, b_mn_major != 0, N, K, b_mn_major ? N : K, BLOCK_N);
   if (rc) return rc;
-  set_tiling(p, M, N, K);
+  set_tiling(p, M, N, K, EPI_STORE);
   schedule_tiles(p);
   make_desc_defaults(p, a_mn_major != 0, b_mn_major != 0);
   p.epi.m_rows = M;

@@ -40,6 +40,6 @@ dl = torch.zeros_like(dz); dl[:-1] = (dz[1:] / tau).bfloat16().float()
 ref_dh, ref_dw = dl @ W.float(), dl.t() @ hidden.float()
 r1 = ((dh.float() - ref_dh).norm() / ref_dh.norm()).item(); r2 = ((dw.float() - ref_dw).norm() / ref_dw.norm()).item()
 ok &= r1 < 1e-2 and r2 < 1e-2
-print(f"CTA_GROUP={os.environ.get('PRL_CTA_GROUP','2')} EPI_TMA={os.environ.get('PRL_EPI_TMA','1')}: logp max err {d.max().item():.2e}, "
+print(f"MSUB={os.environ.get('PRL_MSUB','1')} CTA_GROUP={os.environ.get('PRL_CTA_GROUP','2')} EPI_TMA={os.environ.get('PRL_EPI_TMA','1')}: logp max err {d.max().item():.2e}, "
       f"dH rel {r1:.2e}, dW rel {r2:.2e} -> {'OK' if ok else 'FAIL'}")
 sys.exit(0 if ok else 1)
