@@ -95,43 +95,73 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
 // ------------------------------------------------------------------------------------------------
 // epilogue pieces (one thread = one accumulator row)
 // ------------------------------------------------------------------------------------------------
+// Online softmax state of one accumulator row.  m, u and zt are kept in the ACCUMULATOR domain (a = bf16-rounded
+// <hidden, W[v]>, before the 1/tau scaling) and converted when the partial is flushed: z = a / tau, so
+// m_z = m / tau, u_z = u / tau, zt_z = zt / tau; s = sum 2^{(a - m) c1} with c1 = log2(e) / tau.
 struct RowStats {
   float m, s, u, zt;
 };
 
-template <bool PARTIAL>
-__device__ __forceinline__ void stats_chunk(const uint32_t (&v)[32], RowStats& st, float inv_temp, bool round, int n_valid_in_chunk,
-                                            int tj) {
-  float z[32];
+// bf16 rounding of a pair of accumulators, returned as fp32 (one F2FP + SHF + LOP3 for two elements)
+__device__ __forceinline__ void round_pair(uint32_t v0, uint32_t v1, bool round, float& a0, float& a1) {
   if (round) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) z[j] = ptx::round_bf16(__uint_as_float(v[j])) * inv_temp;
+    const uint32_t pk = ptx::cvt_bf16x2(__uint_as_float(v0), __uint_as_float(v1));
+    a0 = __uint_as_float(pk << 16);
+    a1 = __uint_as_float(pk & 0xFFFF0000u);
   } else {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) z[j] = __uint_as_float(v[j]) * inv_temp;
+    a0 = __uint_as_float(v0);
+    a1 = __uint_as_float(v1);
   }
-  float cmax = -INFINITY;
+}
+
+// 32 columns of one row: packed fp32x2 math (FFMA2 / FADD2), four independent accumulation chains, ~5 issue slots per logit
+template <bool PARTIAL>
+__device__ __forceinline__ void stats_chunk(const uint32_t (&v)[32], RowStats& st, float c1, bool round, int n_valid_in_chunk, int tj) {
+  float a[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j)
-    if (!PARTIAL || j < n_valid_in_chunk) cmax = fmaxf(cmax, z[j]);
-  const float m_new = fmaxf(st.m, cmax);
-  const float sc = ptx::ex2((st.m - m_new) * LOG2E);  // st.m == -inf -> 0
-  st.s *= sc;
-  st.u *= sc;
-  st.m = m_new;
-  const float mneg = -m_new * LOG2E;
+  for (int j = 0; j < 32; j += 2) round_pair(v[j], v[j + 1], round, a[j], a[j + 1]);
+  float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    if (!PARTIAL || j < n_valid_in_chunk) {
-      const float e = ptx::ex2(fmaf(z[j], LOG2E, mneg));
-      st.s += e;
-      st.u = fmaf(e, z[j], st.u);
+  for (int j = 0; j < 32; j += 2) {
+    if (!PARTIAL || j < n_valid_in_chunk) mx0 = fmaxf(mx0, a[j]);
+    if (!PARTIAL || j + 1 < n_valid_in_chunk) mx1 = fmaxf(mx1, a[j + 1]);
+  }
+  const float m_new = fmaxf(st.m, fmaxf(mx0, mx1));
+  const float sc = ptx::ex2((st.m - m_new) * c1);  // st.m == -inf -> 0
+  const float negm = -m_new * c1;
+  const uint64_t C1 = ptx::pack2(c1, c1), NM = ptx::pack2(negm, negm);
+  uint64_t S0 = ptx::pack2(st.s * sc, 0.f), S1 = 0, U0 = ptx::pack2(st.u * sc, 0.f), U1 = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const uint64_t A0 = ptx::pack2(a[j], a[j + 1]), A1 = ptx::pack2(a[j + 2], a[j + 3]);
+    float x0, x1, x2, x3;
+    ptx::unpack2(ptx::fma2(A0, C1, NM), x0, x1);
+    ptx::unpack2(ptx::fma2(A1, C1, NM), x2, x3);
+    float e0 = ptx::ex2(x0), e1 = ptx::ex2(x1), e2 = ptx::ex2(x2), e3 = ptx::ex2(x3);
+    if (PARTIAL) {
+      e0 = (j < n_valid_in_chunk) ? e0 : 0.f;
+      e1 = (j + 1 < n_valid_in_chunk) ? e1 : 0.f;
+      e2 = (j + 2 < n_valid_in_chunk) ? e2 : 0.f;
+      e3 = (j + 3 < n_valid_in_chunk) ? e3 : 0.f;
     }
+    const uint64_t E0 = ptx::pack2(e0, e1), E1 = ptx::pack2(e2, e3);
+    S0 = ptx::add2(S0, E0);
+    S1 = ptx::add2(S1, E1);
+    U0 = ptx::fma2(E0, A0, U0);
+    U1 = ptx::fma2(E1, A1, U1);
   }
+  float s0, s1, s2, s3, u0, u1, u2, u3;
+  ptx::unpack2(S0, s0, s1);
+  ptx::unpack2(S1, s2, s3);
+  ptx::unpack2(U0, u0, u1);
+  ptx::unpack2(U1, u2, u3);
+  st.m = m_new;
+  st.s = (s0 + s1) + (s2 + s3);
+  st.u = (u0 + u1) + (u2 + u3);
   if ((unsigned)tj < 32u) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (j == tj) st.zt = z[j];
+      if (j == tj) st.zt = a[j];
   }
 }
 
@@ -140,31 +170,37 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// dz = coef * (1[j == tj] - exp(z - lse)), written as bf16
-__device__ __forceinline__ void dz_chunk(const uint32_t (&v)[32], float inv_temp, bool round, float coef, float nlse2, int tj,
-                                         __nv_bfloat16* dst, int n_valid_in_chunk) {
-  float d[32];
+// dz = coef * (1[j == tj] - exp(z - lse)) for 32 columns, as fp32 (c1 = log2(e) / tau, nlse2 = -lse * log2(e))
+__device__ __forceinline__ void dz_values(const uint32_t (&v)[32], float c1, bool round, float coef, float nlse2, int tj, float (&d)[32]) {
+  const uint64_t C1 = ptx::pack2(c1, c1), NL = ptx::pack2(nlse2, nlse2), NC = ptx::pack2(-coef, -coef);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float a = __uint_as_float(v[j]);
-    if (round) a = ptx::round_bf16(a);
-    const float p = ptx::ex2(fmaf(a * inv_temp, LOG2E, nlse2));
-    d[j] = -coef * p;
+  for (int j = 0; j < 32; j += 2) {
+    float a0, a1, x0, x1;
+    round_pair(v[j], v[j + 1], round, a0, a1);
+    ptx::unpack2(ptx::fma2(ptx::pack2(a0, a1), C1, NL), x0, x1);
+    ptx::unpack2(ptx::mul2(ptx::pack2(ptx::ex2(x0), ptx::ex2(x1)), NC), d[j], d[j + 1]);
   }
   if ((unsigned)tj < 32u) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j == tj) d[j] += coef;
   }
+}
+
+// register-path store of one 32-column chunk of dlogits (PRL_EPI_TMA=0)
+__device__ __forceinline__ void dz_chunk(const uint32_t (&v)[32], float c1, bool round, float coef, float nlse2, int tj,
+                                         __nv_bfloat16* dst, int n_valid_in_chunk) {
+  float d[32];
+  dz_values(v, c1, round, coef, nlse2, tj, d);
   if (n_valid_in_chunk >= 32) {
     uint4* o = reinterpret_cast<uint4*>(dst);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 w;
-      w.x = pack_bf16x2(d[8 * q + 0], d[8 * q + 1]);
-      w.y = pack_bf16x2(d[8 * q + 2], d[8 * q + 3]);
-      w.z = pack_bf16x2(d[8 * q + 4], d[8 * q + 5]);
-      w.w = pack_bf16x2(d[8 * q + 6], d[8 * q + 7]);
+      w.x = ptx::cvt_bf16x2(d[8 * q + 0], d[8 * q + 1]);
+      w.y = ptx::cvt_bf16x2(d[8 * q + 2], d[8 * q + 3]);
+      w.z = ptx::cvt_bf16x2(d[8 * q + 4], d[8 * q + 5]);
+      w.w = ptx::cvt_bf16x2(d[8 * q + 6], d[8 * q + 7]);
       o[q] = w;
     }
   } else {
@@ -174,24 +210,12 @@ __device__ __forceinline__ void dz_chunk(const uint32_t (&v)[32], float inv_temp
   }
 }
 
-// same math as dz_chunk, result packed to 16 x bf16x2 for the TMA-store epilogue
-__device__ __forceinline__ void dz_pack(const uint32_t (&v)[32], float inv_temp, bool round, float coef, float nlse2, int tj,
-                                        uint32_t (&w)[16]) {
+// same math, result packed to 16 x bf16x2 for the TMA-store epilogue
+__device__ __forceinline__ void dz_pack(const uint32_t (&v)[32], float c1, bool round, float coef, float nlse2, int tj, uint32_t (&w)[16]) {
   float d[32];
+  dz_values(v, c1, round, coef, nlse2, tj, d);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float a = __uint_as_float(v[j]);
-    if (round) a = ptx::round_bf16(a);
-    const float pr = ptx::ex2(fmaf(a * inv_temp, LOG2E, nlse2));
-    d[j] = -coef * pr;
-  }
-  if ((unsigned)tj < 32u) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j == tj) d[j] += coef;
-  }
-#pragma unroll
-  for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(d[2 * j], d[2 * j + 1]);
+  for (int j = 0; j < 16; ++j) w[j] = ptx::cvt_bf16x2(d[2 * j], d[2 * j + 1]);
 }
 
 __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], const EpiParams& e, int64_t row, int64_t col0, int n_valid_in_chunk) {
@@ -493,6 +517,7 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
     const EpiParams& e = p.epi;
+    const float c1 = e.inv_temp * LOG2E;  // accumulator -> log2-domain logit
     int acc = (MS == 1) ? 0 : group;
     uint32_t acc_phase = 0;
     int stage_buf = 0;  // which of this warp's two staging buffers is filled next
@@ -536,15 +561,15 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
           const int tj = (tj64 >= 0 && tj64 < 32) ? (int)tj64 : -1;
           if (EPI == EPI_STATS) {
             if (e.flags & ST_DEBUG_SKIP) {
-              st.s += __uint_as_float(v[lane]);  // profiling aid: keep the TMEM load alive, skip the statistics
+              st.s += __uint_as_float(v[0]) + __uint_as_float(v[31]);  // profiling aid: keep the TMEM load alive, skip the statistics
             } else if (n_valid == 32)
-              stats_chunk<false>(v, st, e.inv_temp, e.round_bf16 != 0, 32, tj);
+              stats_chunk<false>(v, st, c1, e.round_bf16 != 0, 32, tj);
             else
-              stats_chunk<true>(v, st, e.inv_temp, e.round_bf16 != 0, n_valid, tj);
+              stats_chunk<true>(v, st, c1, e.round_bf16 != 0, n_valid, tj);
           } else if (!use_tma) {
             if (EPI == EPI_DZ) {
               if (row < e.T && !(e.flags & ST_DEBUG_SKIP))
-                dz_chunk(v, e.inv_temp, e.round_bf16 != 0, coef, nlse2, tj, e.dz + row * e.ldz + c0, n_valid);
+                dz_chunk(v, c1, e.round_bf16 != 0, coef, nlse2, tj, e.dz + row * e.ldz + c0, n_valid);
             } else {
               if (row_ok && !(e.flags & ST_DEBUG_SKIP)) store_chunk(v, e, row, c0, n_valid);
             }
@@ -566,7 +591,7 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
             } else {
               uint32_t w[16];
               if (EPI == EPI_DZ) {
-                dz_pack(v, e.inv_temp, e.round_bf16 != 0, coef, nlse2, tj, w);
+                dz_pack(v, c1, e.round_bf16 != 0, coef, nlse2, tj, w);
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
@@ -617,7 +642,8 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
         }
       }
       if (EPI == EPI_STATS) {
-        if (row_ok) e.partials[(int64_t)it.split * e.part_stride + row] = make_float4(st.m, st.s, st.u, st.zt);
+        if (row_ok)
+          e.partials[(int64_t)it.split * e.part_stride + row] = make_float4(st.m * e.inv_temp, st.s, st.u * e.inv_temp, st.zt * e.inv_temp);
       }
     }
     if (EPI != EPI_STATS && lane == 0) ptx::bulk_wait_all();  // staging smem must outlive the last TMA store
