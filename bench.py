@@ -44,14 +44,14 @@ SHAPES = {
 }
 
 
-# DRAM bytes (read + write) per launch of each GEMM family at the Qwen3-8B shape, from the `ncu --set full` capture
-# summarised in profiles/r1_lmhead_cg2_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum).  The forward
-# capture there is a 16384-row vocabulary slice (1.75 GB per 16384 vocab rows); backward launches are full size.
+# DRAM bytes (read + write) per launch of each GEMM family at the Qwen3-8B shape (T=16384, H=4096, vocab chunk 16384), from
+# the `ncu --set full` capture summarised in profiles/r1_lmhead_final_ncu_summary.txt (dram__bytes_read.sum +
+# dram__bytes_write.sum).  The forward capture there covers a 32768-row vocabulary slice; it is scaled to V=151936.
 NCU_TRAFFIC_BYTES = {
-    "lmhead_bwd_dz_kernel": 0.878e9 + 0.252e9,
-    "lmhead_bwd_dhidden_kernel": 1.710e9 + 0.192e9,
-    "lmhead_bwd_dweight_kernel": 1.709e9 + 0.120e9,
-    "lmhead_fwd_kernel": (1.746e9 + 0.007e9) * 151936 / 16384,
+    "lmhead_bwd_dz_kernel": 2.81e9 + 0.508e9,
+    "lmhead_bwd_dhidden_kernel": 2.05e9 + 0.245e9,
+    "lmhead_bwd_dweight_kernel": 2.06e9 + 0.242e9,
+    "lmhead_fwd_kernel": (4.75e9 + 0.007e9) * 151936 / 32768,
 }
 # algorithmic bytes per launch (operands read once + outputs written once), for comparison with `traffic`
 def algorithmic_bytes(kernel, T, H, V, vc):
@@ -354,7 +354,7 @@ def run_b200(args):
         result["roofline"] = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
                               "frac": achieved / peaks["sustained"],
                               "traffic": NCU_TRAFFIC_BYTES.get(top) if args.workload == "qwen3-8b-hendrycks" else None,
-                              "traffic_source": "profiles/r1_lmhead_cg2_ncu_summary.txt (dram read+write bytes per launch)",
+                              "traffic_source": "profiles/r1_lmhead_final_ncu_summary.txt (dram read+write bytes per launch)",
                               "algorithmic_bytes": algorithmic_bytes(top, T, H, V, vc),
                               "flops_per_launch": f["flops_per_launch"], "ms_per_launch": f["ms_per_launch"],
                               "peak_source": peaks["source"] + " sustained (kernel timed inside a long power-capped step)",

@@ -15,6 +15,8 @@ dW = torch.zeros(V, H, device=dev)
 for _ in range(int(os.environ.get("NCU_ITERS", 2))):
     logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, 1.0)
     g = torch.randn(T, device=dev) / T
+    if os.environ.get("NCU_FWD_ONLY"):
+        continue
     lm_head_backward_raw(hidden, W, ids, lse, g, 1.0, dweight=dW, dweight_accumulate=True)
 torch.cuda.synchronize()
 print("ok", float(logp.mean()), float(ent.mean()))
