@@ -156,6 +156,18 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * On-device logging statistics ("next" row N1).  Replaces the per-micro-batch boolean-index + blocking .to("cpu")
+ * of src/prime_rl/trainer/rl/train.py:313-333 and the padded all-gather of every masked token in
+ * Tensors.compute_stats (src/prime_rl/trainer/utils.py:228-256) by five running moments per logged key:
+ *   acc[0..4] (fp64, device) = (count, sum, sum of squares, min, max) over the elements with mask != 0
+ * (mask == NULL: all elements) of f(x), f = identity (transform 0) or exp (transform 1, e.g. probs = exp(logprobs)).
+ * acc is UPDATED in place (initialise it to {0, 0, 0, +inf, -inf}); ranks then all-reduce 5 scalars per key.
+ * ---------------------------------------------------------------------------------------- */
+size_t prl_masked_moments_workspace_bytes(void);
+int prl_masked_moments_f32(const float* x, const uint8_t* mask, int64_t n, int32_t transform, double* acc, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Plain bf16 GEMM on the same tcgen05 engine, exposed for tests and bring-up:
  *   C[M,N] (fp32) = A x B with per-operand major-ness:
  *   a_mn_major == 0: A is [M,K] row-major (K contiguous); != 0: A is stored [K,M] (M contiguous)

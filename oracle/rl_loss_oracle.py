@@ -31,6 +31,7 @@ __all__ = [
     "micro_step",
     "shard_partials",
     "merge_partials",
+    "sft_cross_entropy",
 ]
 
 ADVANTAGE_KINDS = ("drgrpo", "drgrpo-negclipped", "rloo", "opo")
@@ -334,3 +335,24 @@ def merge_partials(parts: np.ndarray):
     zt = parts[:, :, 3].sum(axis=0)
     lse = m + np.log(s)
     return zt - lse, lse - u / s, lse
+
+
+# --------------------------------------------------------------------------- #
+# SFT cross-entropy ("next" row N3: src/prime_rl/trainer/sft/train.py:209-216)
+# --------------------------------------------------------------------------- #
+def sft_cross_entropy(hidden, weight, targets, mask, round_bf16: bool, dtype=np.float64):
+    """loss = mean over mask of -log_softmax(hidden @ W^T)[target] (targets pre-shifted, no temperature), and its
+    gradients w.r.t. hidden and W.  Returns (loss, d_hidden, d_weight)."""
+    logits = lm_head_logits(hidden, weight, round_bf16, dtype)
+    t = np.asarray(targets).reshape(-1)
+    mk = np.asarray(mask).reshape(-1).astype(bool)
+    logp, _, lse = logprobs_entropy(logits, t, 1.0, dtype)
+    n = max(int(mk.sum()), 1)
+    loss = -(logp[mk]).sum() / n
+    g = np.where(mk, -1.0 / n, 0.0)
+    p = np.exp(logits - lse[:, None])
+    dz = -p * g[:, None]
+    dz[np.arange(len(t)), t] += g
+    if round_bf16:
+        dz = bf16_round(dz.astype(np.float32)).astype(dtype)
+    return loss, dz @ weight.astype(dtype), dz.T @ hidden.astype(dtype)

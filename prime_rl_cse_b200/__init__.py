@@ -16,8 +16,10 @@ from .config import LossConfig
 from .data import MicroBatch, fake_micro_batch, synthetic_micro_batch, to_device
 from .lm_head import FusedLMHead, fused_lm_head_logprobs_entropy, lm_head_backward_raw, lm_head_forward_raw
 from .loss import compute_entropy, compute_loss, selective_log_softmax, shift_logits, shifted_logprobs_entropy
+from .extras import fused_linear_cross_entropy, recompute_logprobs
 from .micro_step import rl_micro_step
 from .segments import get_response_lengths, segments_from_position_ids
+from .stats import TensorStats
 from .parallel import (exchange_partials, local_loss_scale, shard_micro_batches, vocab_parallel_lm_head_logprobs_entropy,
                        vocab_shard_bounds)
 
@@ -26,5 +28,6 @@ __all__ = [
     "synthetic_micro_batch", "to_device", "FusedLMHead", "fused_lm_head_logprobs_entropy", "lm_head_backward_raw",
     "lm_head_forward_raw", "compute_entropy", "compute_loss", "selective_log_softmax", "shift_logits",
     "shifted_logprobs_entropy", "rl_micro_step", "get_response_lengths", "segments_from_position_ids",
+    "fused_linear_cross_entropy", "recompute_logprobs", "TensorStats",
     "exchange_partials", "local_loss_scale", "shard_micro_batches", "vocab_parallel_lm_head_logprobs_entropy", "vocab_shard_bounds",
 ]

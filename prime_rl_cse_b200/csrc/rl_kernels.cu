@@ -463,6 +463,63 @@ __global__ void __launch_bounds__(256) logits_stats_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// masked running moments for logging (train.py:313-333 + trainer/utils.py:228-256): 5 B/element read, fp64 sums,
+// fixed-order final combine (deterministic), accumulator updated in place.
+// ------------------------------------------------------------------------------------------------
+constexpr int MOM_BLOCKS = 148 * 4;
+
+__global__ void __launch_bounds__(256) masked_moments_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t n,
+                                                             int transform, double* __restrict__ partial) {
+  __shared__ double sh[5][8];
+  double cnt = 0.0, sum = 0.0, sq = 0.0, mn = INFINITY, mx = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (mask == nullptr || mask[i]) {
+      float v = x[i];
+      if (transform == 1) v = expf(v);
+      const double d = (double)v;
+      cnt += 1.0;
+      sum += d;
+      sq += d * d;
+      mn = fmin(mn, d);
+      mx = fmax(mx, d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_down_sync(FULL, cnt, o);
+    sum += __shfl_down_sync(FULL, sum, o);
+    sq += __shfl_down_sync(FULL, sq, o);
+    mn = fmin(mn, __shfl_down_sync(FULL, mn, o));
+    mx = fmax(mx, __shfl_down_sync(FULL, mx, o));
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    sh[0][wid] = cnt, sh[1][wid] = sum, sh[2][wid] = sq, sh[3][wid] = mn, sh[4][wid] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      cnt += sh[0][w], sum += sh[1][w], sq += sh[2][w];
+      mn = fmin(mn, sh[3][w]), mx = fmax(mx, sh[4][w]);
+    }
+    double* o = partial + (int64_t)blockIdx.x * 5;
+    o[0] = cnt, o[1] = sum, o[2] = sq, o[3] = mn, o[4] = mx;
+  }
+}
+
+__global__ void masked_moments_finalize_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ acc) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double cnt = acc[0], sum = acc[1], sq = acc[2], mn = acc[3], mx = acc[4];
+    for (int b = 0; b < nblocks; ++b) {
+      const double* p = partial + (int64_t)b * 5;
+      cnt += p[0], sum += p[1], sq += p[2];
+      mn = fmin(mn, p[3]), mx = fmax(mx, p[4]);
+    }
+    acc[0] = cnt, acc[1] = sum, acc[2] = sq, acc[3] = mn, acc[4] = mx;
+  }
+}
+
 }  // namespace prl
 
 // ================================================================================================
@@ -579,6 +636,25 @@ int prl_scale_f32(const float* a, const float* scale, float* out, int64_t n, voi
   const int64_t need = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
   scale_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(a, scale, out, n);
   return check_launch("scale_kernel");
+}
+
+size_t prl_masked_moments_workspace_bytes(void) { return sizeof(double) * 5 * MOM_BLOCKS; }
+
+int prl_masked_moments_f32(const float* x, const uint8_t* mask, int64_t n, int32_t transform, double* acc, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  PRL_REQUIRE(n >= 0, PRL_ERR_BAD_ARG, "masked_moments: negative size");
+  PRL_REQUIRE(transform == 0 || transform == 1, PRL_ERR_BAD_ARG, "masked_moments: unknown transform");
+  if (n == 0) return PRL_OK;
+  PRL_REQUIRE(x && acc && workspace, PRL_ERR_BAD_ARG, "masked_moments: null pointer");
+  PRL_REQUIRE(workspace_bytes >= prl_masked_moments_workspace_bytes(), PRL_ERR_WORKSPACE, "masked_moments: workspace too small");
+  const int64_t need = (n + 255) / 256;
+  const int grid = (int)(need < MOM_BLOCKS ? need : MOM_BLOCKS);
+  cudaStream_t st = (cudaStream_t)stream;
+  masked_moments_kernel<<<grid, 256, 0, st>>>(x, mask, n, transform, reinterpret_cast<double*>(workspace));
+  int rc = check_launch("masked_moments_kernel");
+  if (rc) return rc;
+  masked_moments_finalize_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, acc);
+  return check_launch("masked_moments_finalize_kernel");
 }
 
 int prl_logits_stats_f32(const float* logits, const int64_t* ids, int64_t rows, int64_t seq, int64_t V, float inv_temp,

@@ -244,3 +244,33 @@ if __name__ == "__main__":
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
+def gen_sft():
+    """SFT cross-entropy call site (src/prime_rl/trainer/sft/train.py:209-216), restated with the same torch call."""
+    from torch.nn.functional import cross_entropy
+
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for name, T, H, V, dt in [("sft_fp32", 64, 32, 200, torch.float32), ("sft_bf16", 96, 64, 520, torch.bfloat16)]:
+        hidden = torch.randn(1, T, H, generator=g).to(dt).requires_grad_(True)
+        weight = (torch.randn(V, H, generator=g) * (4.0 / H**0.5)).to(dt).requires_grad_(True)
+        targets = torch.randint(0, V, (1, T), generator=g)
+        mask = torch.rand(1, T, generator=g) < 0.7
+        logits = hidden @ weight.t()
+        B, L, Vv = logits.shape
+        loss = cross_entropy(logits.view(-1, Vv), targets.view(-1), reduction="none").view(B, L)
+        loss = loss[mask].mean()
+        loss.backward()
+        out[f"{name}/hidden"], out[f"{name}/weight"] = hidden.detach().float().numpy(), weight.detach().float().numpy()
+        out[f"{name}/targets"], out[f"{name}/mask"] = targets.numpy(), mask.numpy()
+        out[f"{name}/loss"] = loss.detach().float().numpy()
+        out[f"{name}/d_hidden"], out[f"{name}/d_weight"] = hidden.grad.float().numpy(), weight.grad.float().numpy()
+        out[f"{name}/is_bf16"] = np.asarray(dt == torch.bfloat16)
+    out["names"] = np.asarray(["sft_fp32", "sft_bf16"])
+    np.savez_compressed(os.path.join(HERE, "sft.npz"), **out)
+
+
+if __name__ == "__main__":
+    gen_sft()
+    print("sft.npz", os.path.getsize(os.path.join(HERE, "sft.npz")), "bytes")

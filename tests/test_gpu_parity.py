@@ -337,3 +337,94 @@ def test_engine_variants(P, cta_group, epi_tma):
     env = dict(os.environ, PRL_CTA_GROUP=str(cta_group), PRL_EPI_TMA=str(epi_tma))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "variant_check.py")], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_fused_lm_head_module_in_hf_qwen3(P):
+    """swap `model.lm_head` of a (tiny, random-init) HF Qwen3 for `FusedLMHead`; the model's
+    `.logits` then carries (logprob, entropy) and matches the reference chain on the unmodified model."""
+    transformers = pytest.importorskip("transformers")
+    cfg = transformers.Qwen3Config(vocab_size=1024, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                                   num_attention_heads=4, num_key_value_heads=2, head_dim=32, max_position_embeddings=512,
+                                   tie_word_embeddings=False)
+    torch.manual_seed(0)
+    model = transformers.Qwen3ForCausalLM(cfg).to(device="cuda", dtype=torch.bfloat16)
+    T, tau = 200, 0.8
+    ids = torch.randint(0, cfg.vocab_size, (1, T), device="cuda")
+    pos = torch.cat([torch.arange(120), torch.arange(80)]).unsqueeze(0).cuda()
+
+    # reference chain on the unmodified model (train.py:285-288, 302-303) in plain torch
+    logits = model(input_ids=ids, position_ids=pos).logits.float().contiguous()
+    shifted = torch.cat([torch.zeros_like(logits[:, :1]), logits[:, :-1]], dim=1) / tau
+    ref_lp = torch.gather(shifted, -1, ids.unsqueeze(-1)).squeeze(-1) - torch.logsumexp(shifted, -1)
+    ref_ent = torch.logsumexp(shifted, -1) - (torch.softmax(shifted, -1) * shifted).sum(-1)
+    (ref_lp * 0.01).sum().backward()
+    ref_gw = model.lm_head.weight.grad.float().clone()
+    ref_ge = model.model.embed_tokens.weight.grad.float().clone()
+    model.zero_grad()
+
+    head = P.FusedLMHead.from_linear(model.lm_head)
+    model.lm_head = head
+    head.set_context(ids, tau)
+    out = model(input_ids=ids, position_ids=pos).logits
+    assert out.shape == (1, T, 2)
+    lp, ent = out[..., 0], out[..., 1].detach()
+    d = (lp - ref_lp).abs()
+    assert (d < 1e-3).float().mean().item() > 0.98 and d.max().item() < 0.07
+    assert (ent - ref_ent).abs().max().item() < 5e-3
+    (lp * 0.01).sum().backward()
+    gw = model.lm_head.weight.grad.float()
+    ge = model.model.embed_tokens.weight.grad.float()
+    assert ((gw - ref_gw).norm() / ref_gw.norm()).item() < 1e-2
+    assert ((ge - ref_ge).norm() / ref_ge.norm()).item() < 2e-2  # through the whole (bf16) transformer body
+    with pytest.raises(RuntimeError):
+        model(input_ids=ids, position_ids=pos)  # context must be set before every forward
+
+
+def test_next_rows_sft_cross_entropy_and_logprob_recompute(P):
+    """SURVEY §8f N3 (SFT cross-entropy on the fused LM head) and N2 (forward-only old-logprob recompute)."""
+    d = load("sft.npz")
+    hidden, weight = cu(d["sft_bf16/hidden"], torch.bfloat16), cu(d["sft_bf16/weight"], torch.bfloat16)
+    targets, mask = cu(d["sft_bf16/targets"]), cu(d["sft_bf16/mask"])
+    hidden.requires_grad_(True)
+    weight.requires_grad_(True)
+    loss = P.fused_linear_cross_entropy(hidden, weight, targets, mask)
+    loss.backward()
+    want, wdh, wdw = oracle.sft_cross_entropy(d["sft_bf16/hidden"][0], d["sft_bf16/weight"], d["sft_bf16/targets"], d["sft_bf16/mask"], True)
+    np.testing.assert_allclose(loss.item(), want, rtol=2e-3)
+    np.testing.assert_allclose(loss.item(), d["sft_bf16/loss"], rtol=2e-2)  # reference call site computes in bf16
+    assert rel_l2(hidden.grad.float().cpu().numpy()[0], wdh) < 1e-2 and rel_l2(weight.grad.float().cpu().numpy(), wdw) < 1e-2
+    assert rel_l2(hidden.grad.float().cpu().numpy(), d["sft_bf16/d_hidden"]) < 3e-2
+
+    T, H, V, tau = 333, 256, 5000, 0.6
+    h, w, ids = _mk(T, H, V, 5)
+    logits = oracle.lm_head_logits(h.float().numpy(), w.float().numpy(), True)
+    wl, _, _ = oracle.logprobs_entropy(oracle.shift_rows(logits), ids.numpy(), tau)
+    old = torch.from_numpy(wl).float().cuda() + 0.1
+    lp, err = P.recompute_logprobs(h.cuda().unsqueeze(0), w.cuda(), ids.cuda().unsqueeze(0), tau, old.unsqueeze(0))
+    dl = np.abs(lp[0].cpu().numpy() - wl)
+    assert np.mean(dl < 1e-3) >= 0.99 and dl.max() < 0.07
+    np.testing.assert_allclose(err[0].cpu().numpy(), np.exp(lp[0].cpu().numpy() - old.cpu().numpy()), rtol=1e-5)
+
+
+def test_next_row_on_device_logging_stats(P):
+    """masked mean/std/min/max per logged key, accumulated across micro-batches on the device."""
+    rng = np.random.default_rng(8)
+    st = P.TensorStats()
+    vals, probs = [], []
+    for T in (1000, 16384, 77):
+        x = rng.standard_normal(T).astype(np.float32) - 1.0
+        m = rng.random(T) < 0.6
+        st.add("entropy", cu(x), cu(m))
+        st.add("probs", cu(x), cu(m), exp=True)
+        st.add("all", cu(x))
+        vals.append(x[m])
+        probs.append(np.exp(x[m].astype(np.float64)))
+    got = st.compute_stats()
+    v, p = np.concatenate(vals).astype(np.float64), np.concatenate(probs)
+    for key, ref in (("entropy", v), ("probs", p)):
+        np.testing.assert_allclose(got[f"{key}/mean"], ref.mean(), rtol=1e-6)
+        np.testing.assert_allclose(got[f"{key}/std"], ref.std(ddof=1), rtol=1e-5)
+        np.testing.assert_allclose(got[f"{key}/min"], ref.min(), rtol=1e-6)
+        np.testing.assert_allclose(got[f"{key}/max"], ref.max(), rtol=1e-6)
+        assert got[f"{key}/count"] == len(ref)
+    assert got["all/count"] == 1000 + 16384 + 77 and st.compute_stats() == {}

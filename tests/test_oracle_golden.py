@@ -158,3 +158,13 @@ def test_bf16_round_matches_torch():
     x = np.random.default_rng(0).standard_normal(10000).astype(np.float32) * 37
     ref = torch.from_numpy(x).to(torch.bfloat16).float().numpy()
     np.testing.assert_array_equal(oracle.bf16_round(x), ref)
+
+
+def test_sft_cross_entropy_vs_reference_call_site():
+    d = load("sft.npz")
+    for name in d["names"]:
+        bf = bool(d[f"{name}/is_bf16"])
+        loss, dh, dw = oracle.sft_cross_entropy(d[f"{name}/hidden"][0], d[f"{name}/weight"], d[f"{name}/targets"], d[f"{name}/mask"], bf)
+        np.testing.assert_allclose(loss, d[f"{name}/loss"], rtol=2e-2 if bf else 1e-5)  # the bf16 reference loss has 8 mantissa bits
+        assert rel_l2(dh, d[f"{name}/d_hidden"][0]) < (2e-2 if bf else 1e-5)
+        assert rel_l2(dw, d[f"{name}/d_weight"]) < (2e-2 if bf else 1e-5)
