@@ -44,10 +44,11 @@ def rl_micro_step(
 
     # train.py:292-299
     loss, loss_tensors = compute_loss(
-        logprobs=logprobs.squeeze().split(response_lengths),
-        old_logprobs=old_logprobs.squeeze().split(response_lengths),
-        advantages=advantages.squeeze().split(response_lengths),
-        loss_mask=loss_mask.squeeze().split(response_lengths),
+        # `.reshape(-1)` == the reference's `.squeeze()` for a [1, T] row, and also works for T == 1
+        logprobs=logprobs.reshape(-1).split(response_lengths),
+        old_logprobs=old_logprobs.reshape(-1).split(response_lengths),
+        advantages=advantages.reshape(-1).split(response_lengths),
+        loss_mask=loss_mask.reshape(-1).split(response_lengths),
         loss_config=loss_config,
         loss_scale=loss_scale,
     )

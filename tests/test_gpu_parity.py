@@ -428,3 +428,45 @@ def test_next_row_on_device_logging_stats(P):
         np.testing.assert_allclose(got[f"{key}/max"], ref.max(), rtol=1e-6)
         assert got[f"{key}/count"] == len(ref)
     assert got["all/count"] == 1000 + 16384 + 77 and st.compute_stats() == {}
+
+
+@pytest.mark.parametrize("T,H,V", [(1, 64, 512), (2, 8, 8), (3, 64, 255), (127, 72, 1000), (129, 200, 257), (513, 136, 4104)])
+def test_micro_step_edge_shapes(P, T, H, V):
+    """Ragged / tiny shapes: T = 1 (only shift_logits' zero row), V and H that are not multiples of the tile sizes
+    (H % 8 == 0 is the only requirement: 16-byte TMA row pitch), single-token segments."""
+    hidden, weight, ids = _mk(T, H, V, 1000 + T)
+    rng = np.random.default_rng(T)
+    lens = [T] if T < 3 else [1, T - 2, 1]
+    pos = np.concatenate([np.arange(n) for n in lens])
+    adv = rng.standard_normal(T).astype(np.float32)
+    mask = np.ones(T, dtype=bool)
+    tau = 0.9
+    logits = oracle.lm_head_logits(hidden.float().numpy(), weight.float().numpy(), True)
+    lp_true, _, _ = oracle.logprobs_entropy(oracle.shift_rows(logits), ids.numpy(), tau)
+    old = (lp_true + 0.2 * rng.standard_normal(T)).astype(np.float32)
+    want = oracle.micro_step(hidden.float().numpy(), weight.float().numpy(), ids.numpy(), pos, old, adv, mask, tau, LossCfg(), T)
+    h = hidden.cuda().requires_grad_(True)
+    w = weight.cuda().requires_grad_(True)
+    mb = dict(input_ids=ids.cuda().unsqueeze(0), position_ids=cu(pos).unsqueeze(0), advantages=cu(adv).unsqueeze(0),
+              logprobs=cu(old).unsqueeze(0), loss_mask=cu(mask).unsqueeze(0), temperature=tau)
+    out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), T, response_lengths=want["lengths"])
+    dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
+    assert dl.max() < 0.07 and np.mean(dl < 1e-3) >= 0.97
+    np.testing.assert_allclose(out["loss"].item(), want["loss"], rtol=2e-2, atol=1e-5)
+    if T > 1:
+        assert rel_l2(h.grad.float().cpu().numpy(), want["d_hidden"]) < 1.5e-2
+        assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1.5e-2
+    else:
+        assert float(h.grad.abs().max()) == 0.0 and float(w.grad.abs().max()) == 0.0  # row 0 is a constant
+
+
+def test_unsupported_shapes_raise(P):
+    h = torch.zeros(1, 4, 12, dtype=torch.bfloat16, device="cuda")  # H % 8 != 0
+    w = torch.zeros(16, 12, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(ValueError):
+        P.fused_lm_head_logprobs_entropy(h, w, torch.zeros(1, 4, dtype=torch.long, device="cuda"), 1.0)
+    with pytest.raises(ValueError):
+        P.fused_lm_head_logprobs_entropy(h.float(), w.float(), torch.zeros(1, 4, dtype=torch.long, device="cuda"), 1.0)
+    with pytest.raises(ValueError):
+        P.compute_loss([torch.zeros(4, device="cuda")], [torch.zeros(3, device="cuda")], [torch.zeros(4, device="cuda")],
+                       [torch.ones(4, dtype=torch.bool, device="cuda")], P.LossConfig(), 1)
