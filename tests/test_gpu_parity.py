@@ -470,3 +470,33 @@ def test_unsupported_shapes_raise(P):
     with pytest.raises(ValueError):
         P.compute_loss([torch.zeros(4, device="cuda")], [torch.zeros(3, device="cuda")], [torch.zeros(4, device="cuda")],
                        [torch.ones(4, dtype=torch.bool, device="cuda")], P.LossConfig(), 1)
+
+
+def test_backward_output_modes(P):
+    """d_weight in bf16 / fp32, stored or accumulated in the kernel; d_hidden in bf16 / fp32; W-only and hidden-only."""
+    from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_forward_raw
+
+    T, H, V, tau = 384, 256, 9000, 0.8
+    hidden, weight, ids = _mk(T, H, V, 21)
+    h, w, i = hidden.cuda(), weight.cuda(), ids.cuda()
+    g = torch.randn(T, device="cuda") / T
+    logp, ent, lse, _ = lm_head_forward_raw(h, w, i, 1 / tau)
+    dh_ref, dw_ref = lm_head_backward_raw(h, w, i, lse, g, 1 / tau, dweight=torch.zeros(V, H, device="cuda"), dweight_accumulate=False,
+                                          dhidden_f32=True, vchunk=4096)
+    assert dh_ref.dtype == torch.float32 and dw_ref.dtype == torch.float32
+
+    def rel(a, b):
+        return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+    for vchunk in (0, 4096):
+        dh, dw = lm_head_backward_raw(h, w, i, lse, g, 1 / tau, vchunk=vchunk)  # bf16 / bf16, stored
+        assert dh.dtype == torch.bfloat16 and dw.dtype == torch.bfloat16
+        assert rel(dh, dh_ref) < 5e-3 and rel(dw, dw_ref) < 5e-3
+    acc32 = dw_ref.clone()
+    lm_head_backward_raw(h, w, i, lse, g, 1 / tau, dweight=acc32, dweight_accumulate=True, want_dhidden=False)  # fp32 +=
+    assert rel(acc32, 2 * dw_ref) < 1e-5
+    acc16 = dw_ref.bfloat16()
+    lm_head_backward_raw(h, w, i, lse, g, 1 / tau, dweight=acc16, dweight_accumulate=True, want_dhidden=False)  # bf16 +=
+    assert rel(acc16, 2 * dw_ref) < 5e-3
+    dh_only, none_w = lm_head_backward_raw(h, w, i, lse, g, 1 / tau, want_dweight=False)
+    assert none_w is None and rel(dh_only, dh_ref) < 5e-3
