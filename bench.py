@@ -361,6 +361,8 @@ def run_b200(args):
                               "frac_of_burst": achieved / peaks["burst"]}
         result["kernel_breakdown_ms_per_micro_batch"] = {k: v["ms_per_launch"] * v["launches_per_mb"] for k, v in fam.items()}
         result["kernel_tflops"] = {k: v["flops_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e12 for k, v in fam.items()}
+    if rank == 0 and not args.no_torch_baseline:
+        result["torch_gpu_reference"] = torch_gpu_reference(wl, dev)
     if rank == 0:
         if not args.no_cpu_baseline and world >= 1:
             result["cpu_baseline"] = cpu_baseline(args.workload, steps=3, warmup=0)
@@ -368,6 +370,48 @@ def run_b200(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def torch_gpu_reference(wl, dev, T_s=4096, reps=3):
+    """The reference's own GPU path for the same micro-step (bf16 lm_head GEMM via cuBLAS -> fp32 logits -> shift -> /tau ->
+    log-softmax gather -> loss -> entropy -> autograd backward; oracle/torch_port.py restating rl/train.py:285-310) on this
+    B200, on a 4096-token slice of the workload (materialised [T,V] fp32 logits: ~2.5 GB per temporary).  Context only."""
+    from oracle import torch_port
+
+    mb = wl["mbs"][0]
+    T_s = min(T_s, wl["T"])
+    nseg = 4
+    seg = [T_s // nseg] * nseg
+    hidden0 = mb["hidden"][0, :T_s].to(dev)
+    weight0 = wl["weight"].to(dev)
+    ids = mb["input_ids"][0, :T_s].to(dev)
+    pos = torch.cat([torch.arange(n) for n in seg]).to(dev)
+    adv = mb["advantages"][0, :T_s].to(dev)
+    mask = torch.ones(T_s, dtype=torch.bool, device=dev)
+    old = mb["logprobs"][0, :T_s].to(dev)
+
+    def one():
+        h = hidden0.clone().requires_grad_(True)
+        w = weight0.detach().clone().requires_grad_(True)
+        torch_port.micro_step_cpu(h, w, ids, pos, old, adv, mask, 1.0, wl["ratio_type"], False, 8.0, T_s)
+
+    try:
+        one()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            one()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        peak = torch.cuda.max_memory_allocated(dev) / 2**30
+        return {"value": T_s / ms * 1e3, "unit": UNIT, "sample": f"{T_s}-token packed row of the same shape, torch ops on this GPU "
+                f"(cuBLAS bf16 lm_head + ATen, materialised fp32 logits), mean of {reps}", "ms_per_sample": ms, "peak_mem_gib": peak}
+    except Exception as e:  # noqa: BLE001  (e.g. out of memory on a shared box): context only, never fatal
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    finally:
+        torch.cuda.empty_cache()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -452,6 +496,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=3, help="distinct micro-batches kept resident and rotated")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-on-GPU reference-chain timing")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -21,7 +21,7 @@ def segment_lengths(position_ids: torch.Tensor) -> list[int]:
     T = p.numel()
     if T < 3:
         return [T]
-    i = torch.arange(1, T - 1)
+    i = torch.arange(1, T - 1, device=p.device)
     is_b = (p[1:-1] == 0) & (p[:-2] != 0) & (p[2:] == 1)
     b = [0] + i[is_b].tolist() + [T]
     return [b[k + 1] - b[k] for k in range(len(b) - 1)]

@@ -12,6 +12,13 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(1234)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(1234)
+
+
 @pytest.fixture(scope="module")
 def P():
     if not torch.cuda.is_available():
@@ -60,15 +67,18 @@ def test_forward_properties_full_size(P, T, H, V, tau):
     assert (lp_m - logp).abs().max().item() < 5e-4 and (ent_m - ent).abs().max().item() < 5e-4 and (lse_m - lse).abs().max().item() < 5e-4
 
     # sampled rows against torch fp32 on the same bf16-rounded logits
-    rows = torch.randint(1, T, (96,), device="cuda")
+    rows = torch.randint(1, T, (96,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
     z = (hidden[rows - 1].float() @ W.float().t()).bfloat16().float() / tau
     ref_lse = torch.logsumexp(z, -1)
     ref_lp = z.gather(1, ids[rows].unsqueeze(1)).squeeze(1) - ref_lse
     ref_ent = ref_lse - (torch.softmax(z, -1) * z).sum(-1)
+    # tcgen05 and cuBLAS/ATen accumulate in different orders, so a logit that sits on a bf16 rounding boundary can round the
+    # other way: at most ONE bf16 ulp of that logit (2^-7 relative), everything else is within 1e-3
+    bound = 1.05 * z.abs().max().item() * 2.0**-7 + 1e-3
     d = (logp[rows] - ref_lp).abs()
-    assert (d < 1e-3).float().mean().item() >= 0.97 and d.max().item() < 0.07, d.max().item()
-    de = (ent[rows] - ref_ent).abs()  # same bf16-boundary caveat as logp (a flipped high-probability logit moves H)
-    assert (de < 1e-3).float().mean().item() >= 0.97 and de.max().item() < 0.07, de.max().item()
+    assert (d < 1e-3).float().mean().item() >= 0.97 and d.max().item() < bound, (d.max().item(), bound)
+    de = (ent[rows] - ref_ent).abs()  # same caveat: a flipped high-probability logit moves H
+    assert (de < 1e-3).float().mean().item() >= 0.97 and de.max().item() < bound, (de.max().item(), bound)
 
 
 @pytest.mark.parametrize("T,H,V,tau", SHAPES[1:])
@@ -78,14 +88,16 @@ def test_backward_sampled_slices_full_size(P, T, H, V, tau):
     hidden, W, ids = make(T, H, V, seed=7 * T + H)
     inv = 1.0 / tau
     logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, inv)
-    g = (torch.randn(T, device="cuda") / T)
-    g[torch.rand(T, device="cuda") < 0.25] = 0.0  # masked tokens
+    gg = torch.Generator(device="cuda").manual_seed(7)
+    g = (torch.randn(T, device="cuda", generator=gg) / T)
+    g[torch.rand(T, device="cuda", generator=gg) < 0.25] = 0.0  # masked tokens
     dW = torch.zeros(V, H, device="cuda")
     dh, _ = lm_head_backward_raw(hidden, W, ids, lse, g, inv, dweight=dW, dweight_accumulate=True)
     assert float(dh[-1].abs().max()) == 0.0  # dropped last position (loss.py:54)
 
     # d_hidden rows: dlogits[r] = g[r+1]/tau * (onehot - softmax(z[r+1])) in bf16, then @ W
-    rows = torch.randint(0, T - 1, (64,), device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    rows = torch.randint(0, T - 1, (64,), device="cuda", generator=gen)
     z = (hidden[rows].float() @ W.float().t()).bfloat16().float() * inv
     p = torch.exp(z - lse[rows + 1].unsqueeze(1))
     dz = -p * g[rows + 1].unsqueeze(1)
@@ -96,7 +108,7 @@ def test_backward_sampled_slices_full_size(P, T, H, V, tau):
     assert num / max(ref_dh.norm().item(), 1e-30) < 1e-2
 
     # d_W rows for a few vocab ids (including ids that occur as targets)
-    vs = torch.cat([ids[1:9], torch.randint(0, V, (24,), device="cuda")]).unique()
+    vs = torch.cat([ids[1:9], torch.randint(0, V, (24,), device="cuda", generator=gen)]).unique()
     zc = (hidden[:-1].float() @ W[vs].float().t()).bfloat16().float() * inv  # [T-1, nv]: logits of source rows
     pc = torch.exp(zc - lse[1:].unsqueeze(1))
     dzc = -pc * g[1:].unsqueeze(1)
@@ -168,3 +180,39 @@ def test_vocab_sharded_two_gpus_nccl():
            "--master-port", "29531", os.path.join(root, "tools", "vocab_parallel_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_micro_step_vs_torch_reference_chain_on_gpu(P):
+    """Qwen3-8B shape, 2048 tokens: the fused path against the reference's own GPU op sequence (cuBLAS bf16 lm_head ->
+    fp32 logits -> shift -> /tau -> log-softmax gather -> loss -> entropy -> autograd), restated in oracle/torch_port.py."""
+    from oracle import torch_port
+
+    T, H, V, tau = 2048, 4096, 151936, 0.6
+    hidden, W, ids = make(T, H, V, seed=99)
+    lens = [700, 900, 448]
+    pos = torch.cat([torch.arange(n) for n in lens]).cuda()
+    adv = torch.cat([torch.full((n,), float(a)) for n, a in zip(lens, (0.5, -0.25, 1.0))]).cuda()
+    mask = torch.rand(T, device="cuda") < 0.8
+    with torch.no_grad():
+        lp0, _ = P.fused_lm_head_logprobs_entropy(hidden.unsqueeze(0), W, ids.unsqueeze(0), tau)
+    old = lp0[0] + 0.2 * torch.randn(T, device="cuda")
+    scale = int(mask.sum())
+
+    h_ref = hidden.clone().requires_grad_(True)
+    w_ref = W.clone().requires_grad_(True)
+    loss_ref, lp_ref, ent_ref = torch_port.micro_step_cpu(h_ref, w_ref, ids, pos, old, adv, mask, tau, "token", False, 8.0, scale)
+
+    h = hidden.clone().requires_grad_(True)
+    w = W.clone().requires_grad_(True)
+    mb = dict(input_ids=ids.unsqueeze(0), position_ids=pos.unsqueeze(0), advantages=adv.unsqueeze(0), logprobs=old.unsqueeze(0),
+              loss_mask=mask.unsqueeze(0), temperature=tau)
+    out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), scale)
+    # |logit| reaches ~16 here: one bf16 ulp (2^-7 relative) of a boundary logit, divided by tau, is ~0.2
+    bound = 16.0 * 2.0**-7 / tau
+    d = (out["logprobs"][0] - lp_ref).abs()
+    assert (d < 1e-3).float().mean().item() >= 0.98 and d.max().item() < bound, (d.max().item(), (d < 1e-3).float().mean().item())
+    de = (out["entropy"][0] - ent_ref).abs()
+    assert (de < 1e-3).float().mean().item() >= 0.98 and de.max().item() < bound
+    assert abs(out["loss"].item() - loss_ref.item()) <= 5e-3 * abs(loss_ref.item()) + 1e-6
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()  # noqa: E731
+    assert rel(h.grad, h_ref.grad) < 1e-2 and rel(w.grad, w_ref.grad) < 1e-2

@@ -18,6 +18,13 @@ G = os.path.join(os.path.dirname(__file__), "golden")
 KINDS = ["drgrpo", "drgrpo-negclipped", "rloo", "opo"]
 
 
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(4321)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(4321)
+
+
 @pytest.fixture(scope="module")
 def P():
     if not torch.cuda.is_available():
