@@ -41,6 +41,7 @@ SHAPES = {
     "qwen3-1.7b-wordle": (2048, 151936, 16384, 8, 8, 16, "token"),
     "qwen3-0.6b-reverse": (1024, 151936, 4096, 32, 1, 8, "token"),
     "qwen3-8b-deepscaler": (4096, 151936, 32768, 1, 8, 32, "sequence"),
+    "tiny": (128, 2048, 512, 4, 2, 4, "token"),  # CI smoke of this script only, not a benchmark
 }
 
 
