@@ -32,6 +32,17 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+# stdout carries exactly ONE JSON line: everything else that libraries print to fd 1 (e.g. NCCL's version banner) is sent to
+# stderr by pointing fd 1 at fd 2 for the duration of the run; emit() writes the result to the saved, real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 METRIC = "loss_fwd_bwd_tokens_per_sec"
 UNIT = "tokens/s"
 
@@ -367,7 +378,7 @@ def run_b200(args):
     if rank == 0:
         if not args.no_cpu_baseline and world >= 1:
             result["cpu_baseline"] = cpu_baseline(args.workload, steps=3, warmup=0)
-        print(json.dumps(result), flush=True)
+        emit(result)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -475,7 +486,7 @@ def run_reference(args):
     sample = (f"each step = one packed row of {T_s} tokens (4 segments) of the same workload shape, fp32, all host threads "
               f"(torch CPU ops, oracle/torch_port.py restating the reference's rl/train.py:285-310; the reference is pure Python "
               f"and /root/reference does not travel to the GPU box)")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -483,7 +494,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 def main():
@@ -507,7 +518,7 @@ def main():
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     run_b200(args)
 
 
