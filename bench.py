@@ -315,15 +315,22 @@ def run_b200(args):
         dlogp = torch.randn(T, device=dev) / T
 
         def ev_time(fn, reps):
-            fn()
+            """average launch-sequence time over ~1 s of back-to-back repetitions (so the SM clock has settled under the
+            power cap, like inside the timed step), CUDA events on the launching stream"""
+            for _ in range(2):
+                fn()
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n, t0 = 0, time.perf_counter()
             a.record()
-            for _ in range(reps):
+            while n < reps or time.perf_counter() - t0 < 1.0:
                 fn()
+                n += 1
+                if n % 8 == 0:
+                    torch.cuda.synchronize()
             b.record()
             torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
+            return a.elapsed_time(b) / n
 
         vc = 16384  # default vocab chunk of prl_lmhead_bwd
         nchunks = (V + vc - 1) // vc

@@ -25,7 +25,7 @@ FL = 2.0 * T * H * V
 def fam_fn(fam):
     if fam == "FWD":
         return lambda: lm_head_forward_raw(hidden, W, ids, 1.0, workspace=ws_f)
-    mask = {"DZ": 1, "DH": 2, "DW": 4}[fam]
+    mask = {"DZ": 1, "DH": 2, "DW": 4, "BWD": 7, "DZDH": 3, "DZDW": 5, "DHDW": 6}[fam]
     return lambda: lm_head_backward_raw(hidden, W, ids, lse, g, 1.0, dweight=dW, dweight_accumulate=True, workspace=ws_b, phase_mask=mask)
 
 
