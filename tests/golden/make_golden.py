@@ -5,7 +5,7 @@ Run in the build container only (the reference is not on the GPU box):
 
     PYTHONPATH=/root/reference/src python tests/golden/make_golden.py
 
-Writes advantages.npz, segments.npz, loss.npz, lmhead.npz next to this file.
+Writes advantages.npz, segments.npz, loss.npz, lmhead.npz, sft.npz, packed_layout.npz next to this file.
 The reference entry points exercised (paths relative to /root/reference):
   src/prime_rl/orchestrator/advantage.py:71   compute_advantages
   src/prime_rl/trainer/utils.py:36            get_response_lengths
@@ -234,18 +234,6 @@ def gen_lmhead():
     np.savez_compressed(os.path.join(HERE, "lmhead.npz"), **out)
 
 
-if __name__ == "__main__":
-    torch.manual_seed(0)
-    torch.set_num_threads(1)  # fixed reduction order for reproducible fixtures
-    gen_advantages()
-    gen_segments()
-    gen_loss()
-    gen_lmhead()
-    for f in sorted(os.listdir(HERE)):
-        if f.endswith(".npz"):
-            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
-
-
 def gen_sft():
     """SFT cross-entropy call site (src/prime_rl/trainer/sft/train.py:209-216), restated with the same torch call."""
     from torch.nn.functional import cross_entropy
@@ -271,6 +259,55 @@ def gen_sft():
     np.savez_compressed(os.path.join(HERE, "sft.npz"), **out)
 
 
+def gen_packed_layout():
+    """KAT-5: the packed MicroBatch layout exactly as the reference's orchestrator produces it
+    (prepare_batch, src/prime_rl/orchestrator/batch.py:123-175) from toy rollouts whose advantages come from the
+    reference's compute_advantages: prompt tokens masked, multi-turn holes in the completion mask, per-rollout advantage
+    broadcast over prompt + completion, first-fit-decreasing packing, all-masked padding micro-batches for rank balance."""
+    from prime_rl.orchestrator.batch import prepare_batch
+    from prime_rl.orchestrator.buffer import Rollout
+
+    rng = np.random.default_rng(2024)
+    V, G, n_problems = 1000, 4, 3
+    rewards, lens, protos = [], [], []
+    for p in range(n_problems):
+        prompt = rng.integers(0, V, rng.integers(3, 9)).tolist()
+        for _ in range(G):
+            n = int(rng.integers(4, 40))
+            comp = rng.integers(0, V, n).tolist()
+            cmask = (rng.random(n) < 0.8).astype(int).tolist()  # environment turns masked out
+            clogp = (-rng.random(n) * 3).astype(np.float32).tolist()
+            r = float(rng.integers(0, 2))
+            rewards.append(r)
+            lens.append(n)
+            protos.append((p, prompt, comp, cmask, clogp, r))
+    adv = compute_advantages(rewards, lens, G, "drgrpo")
+    rollouts = [Rollout(problem_id=p, prompt_tokens=pr, prompt_mask=[0] * len(pr), completion_tokens=c, completion_mask=cm,
+                        completion_logprobs=cl, is_truncated=False, reward=r, advantage=a)
+                for (p, pr, c, cm, cl, r), a in zip(protos, adv)]
+    per_rank = prepare_batch(rollouts, temperature=0.6, tokenizer=None, batch_size=len(rollouts), micro_batch_size=2, seq_len=48,
+                             num_train_workers=2)
+    out = {"n_ranks": np.asarray(len(per_rank)), "rewards": np.asarray(rewards, dtype=np.float32), "lens": np.asarray(lens),
+           "advantages": np.asarray(adv, dtype=np.float32)}
+    for r, mbs in enumerate(per_rank):
+        out[f"rank{r}/n"] = np.asarray(len(mbs))
+        for i, mb in enumerate(mbs):
+            for k in ("input_ids", "position_ids", "advantages", "logprobs", "loss_mask"):
+                out[f"rank{r}/mb{i}/{k}"] = mb[k].numpy()
+            out[f"rank{r}/mb{i}/temperature"] = np.asarray(mb["temperature"])
+            out[f"rank{r}/mb{i}/lengths"] = np.asarray(get_response_lengths(mb["position_ids"]), dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "packed_layout.npz"), **out)
+
+
 if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(1)  # fixed reduction order for reproducible fixtures
+    gen_advantages()
+    gen_segments()
+    gen_loss()
+    gen_lmhead()
     gen_sft()
-    print("sft.npz", os.path.getsize(os.path.join(HERE, "sft.npz")), "bytes")
+    gen_packed_layout()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -507,3 +507,37 @@ def test_backward_output_modes(P):
     assert rel(acc16, 2 * dw_ref) < 5e-3
     dh_only, none_w = lm_head_backward_raw(h, w, i, lse, g, 1 / tau, want_dweight=False)
     assert none_w is None and rel(dh_only, dh_ref) < 5e-3
+
+
+def test_micro_step_on_reference_packed_batches(P):
+    """The packed micro-batches the reference orchestrator writes (prepare_batch, 2 train workers, incl. the all-masked padding
+    batch) through the fused micro-step, each rank with its rank-local loss scale (train.py:263-267)."""
+    d = load("packed_layout.npz")
+    H, V = 64, 1000
+    hidden_rng = torch.Generator().manual_seed(3)
+    weight = (torch.randn(V, H, generator=hidden_rng) * 0.4).bfloat16()
+    for r in range(int(d["n_ranks"])):
+        mbs = []
+        for i in range(int(d[f"rank{r}/n"])):
+            pre = f"rank{r}/mb{i}"
+            mbs.append({k: torch.from_numpy(d[f"{pre}/{k}"]) for k in ("input_ids", "position_ids", "advantages", "logprobs", "loss_mask")}
+                       | {"temperature": float(d[f"{pre}/temperature"])})
+        scale = P.local_loss_scale(mbs, "token")
+        for mb in mbs:
+            T = mb["input_ids"].shape[1]
+            hidden = torch.randn(T, H, generator=hidden_rng).bfloat16()
+            want = oracle.micro_step(hidden.float().numpy(), weight.float().numpy(), mb["input_ids"][0].numpy(), mb["position_ids"][0].numpy(),
+                                     mb["logprobs"][0].numpy(), mb["advantages"][0].numpy(), mb["loss_mask"][0].numpy(), mb["temperature"],
+                                     LossCfg(), scale)
+            h = hidden.cuda().requires_grad_(True)
+            w = weight.cuda().requires_grad_(True)
+            out = P.rl_micro_step(h.unsqueeze(0), w, P.to_device(mb, "cuda"), P.LossConfig(), scale)
+            assert P.get_response_lengths(mb["position_ids"].cuda()) == want["lengths"]
+            dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
+            assert np.mean(dl < 1e-3) >= 0.97 and dl.max() < 0.07
+            np.testing.assert_allclose(out["loss"].item(), want["loss"], rtol=1e-2, atol=1e-6)
+            if mb["loss_mask"].any():
+                assert rel_l2(h.grad.float().cpu().numpy(), want["d_hidden"]) < 1.5e-2
+                assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1.5e-2
+            else:  # padding batch: exactly zero loss and gradients
+                assert out["loss"].item() == 0.0 and float(h.grad.abs().max()) == 0.0 and float(w.grad.abs().max()) == 0.0

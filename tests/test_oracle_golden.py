@@ -168,3 +168,26 @@ def test_sft_cross_entropy_vs_reference_call_site():
         np.testing.assert_allclose(loss, d[f"{name}/loss"], rtol=2e-2 if bf else 1e-5)  # the bf16 reference loss has 8 mantissa bits
         assert rel_l2(dh, d[f"{name}/d_hidden"][0]) < (2e-2 if bf else 1e-5)
         assert rel_l2(dw, d[f"{name}/d_weight"]) < (2e-2 if bf else 1e-5)
+
+
+def test_packed_layout_from_reference_prepare_batch():
+    """KAT-5: micro-batches produced by the reference orchestrator (prepare_batch) — layout facts the path relies on."""
+    d = load("packed_layout.npz")
+    assert int(d["n_ranks"]) == 2
+    np.testing.assert_array_equal(oracle.advantages(d["rewards"], d["lens"], 4, "drgrpo"), d["advantages"])
+    n_pad = 0
+    for r in range(2):
+        for i in range(int(d[f"rank{r}/n"])):
+            pre = f"rank{r}/mb{i}"
+            pos, mask, adv = d[f"{pre}/position_ids"][0], d[f"{pre}/loss_mask"][0], d[f"{pre}/advantages"][0]
+            lens = oracle.response_lengths(pos)
+            assert lens == d[f"{pre}/lengths"].tolist() and sum(lens) == pos.shape[0]
+            assert lens == sorted(lens, reverse=True)  # first-fit-decreasing keeps each bin longest-first
+            o = 0
+            for n in lens:  # one advantage per rollout, broadcast over prompt AND completion (batch.py:44)
+                assert np.all(adv[o : o + n] == adv[o]) and not mask[o]  # the first (prompt) token is never trained on
+                o += n
+            if not mask.any():
+                n_pad += 1
+                assert not adv.any()  # padding micro-batch: zero advantages, all-False mask (batch.py:153-161)
+    assert n_pad == 1
