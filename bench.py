@@ -142,7 +142,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # synthetic workload
 # ------------------------------------------------------------------------------------------------
-def make_workload(shape: str, rank: int, n_distinct: int, pin: bool, device="cpu"):
+def make_workload(shape: str, rank: int, n_distinct: int, pin: bool, device="cpu", prompt_frac: float = 0.0):
     """Micro-batches of the named shape (SURVEY §8d "D-uniform": W ~ N(0, 0.02^2), hidden ~ N(0,1)), generated on
     `device` (the GPU for the B200 arm: seconds instead of a single-threaded CPU randn under torchrun) and returned as
     HOST tensors (pinned when `pin`), exactly what a data loader hands the trainer; `weight` stays on `device`."""
@@ -163,6 +163,12 @@ def make_workload(shape: str, rank: int, n_distinct: int, pin: bool, device="cpu
         pos = torch.cat([torch.arange(n) for n in seg])
         mask = torch.ones(T, dtype=torch.bool)  # headline: all ones, as FakeDataLoader (rl/data.py:53)
         old = (-11.9 + 0.15 * torch.randn(T, generator=g, device=device)).cpu()  # near ln(1/V): ratios ~ 1 (near-uniform softmax)
+        if prompt_frac > 0:  # --prompt-frac: the first part of every rollout is a prompt (mask 0, old log-prob 0, batch.py:41-42)
+            o = 0
+            for n in seg:
+                mask[o : o + int(n * prompt_frac)] = False
+                o += n
+            old[~mask] = 0.0
         mb = dict(hidden=hidden.unsqueeze(0), input_ids=ids.unsqueeze(0), position_ids=pos.unsqueeze(0),
                   advantages=torch.cat([adv_r[(i * nseg + j) % n_rollouts].repeat(n) for j, n in enumerate(seg)]).unsqueeze(0),
                   logprobs=old.unsqueeze(0), loss_mask=mask.unsqueeze(0), temperature=1.0)
@@ -196,7 +202,7 @@ def run_b200(args):
         dist.init_process_group(backend="nccl", device_id=dev)
     _lib.load()
 
-    wl = make_workload(args.workload, rank, n_distinct=args.distinct, pin=True, device=dev)
+    wl = make_workload(args.workload, rank, n_distinct=args.distinct, pin=True, device=dev, prompt_frac=args.prompt_frac)
     H, V, T, n_mb = wl["H"], wl["V"], wl["T"], wl["n_mb"] if args.micro_batches <= 0 else args.micro_batches
     cfg = P.LossConfig(ratio_type=wl["ratio_type"], ratio_length_norm=False, clip_ratio=8.0)
     mode = 0 if cfg.ratio_type == "token" else 1
@@ -210,7 +216,8 @@ def run_b200(args):
         bounds.append(bounds[-1] + n)
     cu = torch.tensor(bounds, dtype=torch.int32, device=dev)
     nseg = len(wl["seg"])
-    loss_scale = n_mb * T if mode == 0 else n_mb  # rl/train.py:263-267 (all-ones mask)
+    n_unmasked = int(wl["mbs"][0]["loss_mask"].sum())
+    loss_scale = n_mb * n_unmasked if mode == 0 else n_mb  # rl/train.py:263-267
     lib = _lib.load()
     ws_f = torch.empty(lib.prl_lmhead_fwd_workspace_bytes(T, H, V), dtype=torch.uint8, device=dev)
     ws_b = torch.empty(lib.prl_lmhead_bwd_workspace_bytes(T, H, V, 0), dtype=torch.uint8, device=dev)
@@ -352,7 +359,9 @@ def run_b200(args):
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: H={H} V={V}, {n_mb} packed micro-batches x [1,{T}] tokens per GPU per step "
-                               f"({len(wl['seg'])} x {wl['seg'][0]}-token rollouts each), ratio_type={cfg.ratio_type}, all-ones mask, tau=1",
+                               f"({len(wl['seg'])} x {wl['seg'][0]}-token rollouts each), ratio_type={cfg.ratio_type}, "
+                               + ("all-ones mask" if args.prompt_frac == 0 else f"first {args.prompt_frac:.0%} of every rollout masked (prompt); the e2e arm's "
+                                  "backward skips masked positions, the resident arm visits all T like the reference") + ", tau=1",
                    "tokens_per_gpu_per_step": tokens_per_step, "parallelism": f"token-sharded dp{world} (no data-path collective; "
                    + ("d_W_lm fp32 reduce-scatter once per step)" if world > 1 else "single GPU)"),
                    "l2_policy": "inputs larger than L2 (W_lm 1.24 GB + 134 MB hidden per micro-batch, rotating micro-batches)",
@@ -515,6 +524,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=3, help="distinct micro-batches kept resident and rotated")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--prompt-frac", type=float, default=0.0, help="mask the first fraction of every rollout (default 0 = all-ones mask)")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-on-GPU reference-chain timing")
     args = ap.parse_args()
     if args.impl == "reference":

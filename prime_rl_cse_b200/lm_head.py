@@ -69,7 +69,7 @@ def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, 
 
 class _FusedLMHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, hidden, weight, ids, inv_temp, shift, round_bf16, main_grad):
+    def forward(ctx, hidden, weight, ids, inv_temp, shift, round_bf16, main_grad, active_positions=None):
         lead = hidden.shape[:-1]
         h2 = hidden.detach().reshape(-1, hidden.shape[-1]).contiguous()
         w2 = weight.detach().contiguous()
@@ -77,6 +77,7 @@ class _FusedLMHead(torch.autograd.Function):
         logp, ent, lse, _ = lm_head_forward_raw(h2, w2, i2, inv_temp, shift, round_bf16)
         ctx.save_for_backward(h2, w2, i2, lse)
         ctx.cfg = (inv_temp, shift, round_bf16, hidden.shape, main_grad)
+        ctx.active = active_positions
         logp, ent = logp.reshape(lead), ent.reshape(lead)
         ctx.mark_non_differentiable(ent)
         return logp, ent
@@ -87,6 +88,27 @@ class _FusedLMHead(torch.autograd.Function):
         inv_temp, shift, round_bf16, hshape, main_grad = ctx.cfg
         g = g_logp.detach().reshape(-1).contiguous().float()
         need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if ctx.active is not None:
+            # Only positions with a non-zero d loss / d logp contribute to d_hidden and d_W: run the recompute backward on
+            # the compacted rows (exactly the same sums, minus the all-zero terms) and scatter d_hidden back.
+            pos = ctx.active.reshape(-1).to(torch.int64)
+            pos = pos[pos >= int(shift)]          # position 0 of a shifted row is a constant: no gradient
+            rows = pos - int(shift)               # source row of `hidden` feeding each position
+            dw_target = main_grad if (main_grad is not None and need_w) else None
+            dh = torch.zeros(h2.shape, dtype=torch.bfloat16, device=h2.device) if need_h else None
+            dw = None
+            if pos.numel() > 0:
+                dh_c, dw = lm_head_backward_raw(h2.index_select(0, rows), w2, i2.index_select(0, pos), lse.index_select(0, pos),
+                                                g.index_select(0, pos), inv_temp, False, round_bf16, want_dhidden=need_h,
+                                                dweight=dw_target, dweight_accumulate=dw_target is not None,
+                                                want_dweight=need_w)
+                if need_h:
+                    dh.index_copy_(0, rows, dh_c)
+            elif need_w and dw_target is None:
+                dw = torch.zeros_like(w2)
+            if dw_target is not None:
+                dw = None
+            return (dh.reshape(hshape) if dh is not None else None), dw, None, None, None, None, None, None
         if main_grad is not None and need_w:
             dh, _ = lm_head_backward_raw(h2, w2, i2, lse, g, inv_temp, shift, round_bf16, want_dhidden=need_h,
                                          dweight=main_grad, dweight_accumulate=True)
@@ -94,7 +116,7 @@ class _FusedLMHead(torch.autograd.Function):
         else:
             dh, dw = lm_head_backward_raw(h2, w2, i2, lse, g, inv_temp, shift, round_bf16, want_dhidden=need_h,
                                           want_dweight=need_w)
-        return (dh.reshape(hshape) if dh is not None else None), dw, None, None, None, None, None
+        return (dh.reshape(hshape) if dh is not None else None), dw, None, None, None, None, None, None
 
 
 def fused_lm_head_logprobs_entropy(
@@ -106,6 +128,7 @@ def fused_lm_head_logprobs_entropy(
     shift: bool = True,
     round_bf16: bool = True,
     main_grad: torch.Tensor | None = None,
+    active_positions: torch.Tensor | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """hidden [..., T, H] bf16 (final-norm output), weight [V, H] bf16 (`lm_head.weight`), input_ids
     [..., T] -> (logprobs [..., T] fp32, differentiable w.r.t. hidden and weight; entropy [..., T] fp32,
@@ -115,7 +138,10 @@ def fused_lm_head_logprobs_entropy(
     (rl/train.py:285-288,302-303) for one packed row.  `shift` applies to the whole flattened row as the
     reference's `shift_logits` does for batch size 1 (packed micro-batches, rl/data.py:13-23).
     `main_grad`: optional fp32/bf16 [V,H] buffer; the weight gradient is then ACCUMULATED into it by the
-    kernel and `weight.grad` is left untouched (fused gradient accumulation across micro-batches)."""
+    kernel and `weight.grad` is left untouched (fused gradient accumulation across micro-batches).
+    `active_positions`: optional int64 index tensor of the positions that can receive a non-zero gradient (e.g.
+    `loss_mask.nonzero()`): the backward then skips every other row (prompt / environment tokens) — identical gradients,
+    proportionally less recompute.  The forward always covers all T positions, as the reference does."""
     _lib.require_cuda(hidden, weight, input_ids)
     if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise ValueError("fused_lm_head_logprobs_entropy needs bf16 hidden and weight (FSDP param_dtype=bf16, model.py:103)")
@@ -123,7 +149,8 @@ def fused_lm_head_logprobs_entropy(
         raise ValueError("hidden [..., T, H] and input_ids [..., T] disagree")
     if hidden.dim() > 2 and hidden.shape[:-2].numel() != 1:
         raise ValueError("only one packed row per call (micro_batch_size == 1 for packed batches)")
-    return _FusedLMHead.apply(hidden, weight, input_ids, 1.0 / float(temperature), bool(shift), bool(round_bf16), main_grad)
+    return _FusedLMHead.apply(hidden, weight, input_ids, 1.0 / float(temperature), bool(shift), bool(round_bf16), main_grad,
+                              active_positions)
 
 
 class FusedLMHead(nn.Module):

@@ -23,11 +23,14 @@ def rl_micro_step(
     backward: bool = True,
     main_grad: torch.Tensor | None = None,
     response_lengths: list[int] | None = None,
+    skip_masked: bool = True,
 ) -> dict[str, torch.Tensor]:
     """`hidden` [1,T,H] bf16 is what the transformer body hands to `lm_head` (requires_grad as the
     caller wishes); `micro_batch` is a `MicroBatch` (rl/data.py:13-23) whose tensors are already on the
     device (train.py:275-279).  Returns loss, logprobs, entropy and the three logging tensors of
-    `compute_loss`; with `backward=True` also runs `loss.backward()` (train.py:310)."""
+    `compute_loss`; with `backward=True` also runs `loss.backward()` (train.py:310).  `skip_masked`: tokens with
+    `loss_mask == False` get a zero gradient (loss.py:104), so the recompute backward only visits the unmasked positions;
+    skipped automatically when every token is unmasked."""
     input_ids = micro_batch["input_ids"]
     position_ids = micro_batch["position_ids"]
     advantages = micro_batch["advantages"]
@@ -39,8 +42,15 @@ def rl_micro_step(
     if response_lengths is None:
         response_lengths = get_response_lengths(position_ids)
 
+    active = None
+    if skip_masked and backward:
+        nz = loss_mask.reshape(-1).nonzero().reshape(-1)  # sizes it on the host: same sync point as the segment lengths
+        if nz.numel() < loss_mask.numel():
+            active = nz
+
     # train.py:285-288 + 302-303
-    logprobs, entropy = fused_lm_head_logprobs_entropy(hidden, lm_head_weight, input_ids, temperature, main_grad=main_grad)
+    logprobs, entropy = fused_lm_head_logprobs_entropy(hidden, lm_head_weight, input_ids, temperature, main_grad=main_grad,
+                                                       active_positions=active)
 
     # train.py:292-299
     loss, loss_tensors = compute_loss(

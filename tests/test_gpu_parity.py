@@ -541,3 +541,23 @@ def test_micro_step_on_reference_packed_batches(P):
                 assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1.5e-2
             else:  # padding batch: exactly zero loss and gradients
                 assert out["loss"].item() == 0.0 and float(h.grad.abs().max()) == 0.0 and float(w.grad.abs().max()) == 0.0
+
+
+def test_backward_skips_masked_positions_exactly(P):
+    """`active_positions`: the compacted backward gives the same gradients as the full one (masked rows contribute zeros)."""
+    T, H, V, tau = 900, 256, 6000, 0.7
+    hidden, weight, ids = _mk(T, H, V, 31)
+    mask = torch.rand(T) < 0.6
+    mask[0] = True  # position 0 is active but has no source row: must be ignored
+    g = (torch.randn(T) / T) * mask
+    outs = []
+    for active in (None, mask.nonzero().reshape(-1).cuda()):
+        h = hidden.cuda().requires_grad_(True)
+        w = weight.cuda().requires_grad_(True)
+        lp, _ = P.fused_lm_head_logprobs_entropy(h.unsqueeze(0), w, ids.cuda().unsqueeze(0), tau, active_positions=active)
+        (lp[0] * g.cuda()).sum().backward()
+        outs.append((h.grad.float(), w.grad.float()))
+    (dh0, dw0), (dh1, dw1) = outs
+    assert ((dh1 - dh0).norm() / dh0.norm()).item() < 2e-3 and ((dw1 - dw0).norm() / dw0.norm()).item() < 2e-3
+    inactive_rows = (~mask[1:]).nonzero().reshape(-1).cuda()
+    assert float(dh1[inactive_rows].abs().max()) == 0.0
