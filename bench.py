@@ -273,7 +273,8 @@ def run_b200(args):
                 if torch.is_tensor(v):
                     v.record_stream(cur)
             hid = mb["hidden"].requires_grad_(True)
-            out = P.rl_micro_step(hid, W, mb, cfg, loss_scale, main_grad=main_grad, response_lengths=None)
+            out = P.rl_micro_step(hid, W, mb, cfg, loss_scale, main_grad=main_grad, response_lengths=None,
+                                  forward_skips_masked=args.forward_skips_masked)
             loss_host[i].copy_(out["loss"], non_blocking=True)
         if dist is not None and rs_out is not None:
             dist.reduce_scatter_tensor(rs_out, main_grad.view(-1))
@@ -524,6 +525,7 @@ def main():
     ap.add_argument("--distinct", type=int, default=3, help="distinct micro-batches kept resident and rotated")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--forward-skips-masked", action="store_true", help="e2e arm: also restrict the forward to unmasked positions")
     ap.add_argument("--prompt-frac", type=float, default=0.0, help="mask the first fraction of every rollout (default 0 = all-ones mask)")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-on-GPU reference-chain timing")
     args = ap.parse_args()

@@ -40,7 +40,7 @@ def fused_linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, targe
     if hidden.shape[:-1] != target_ids.shape or target_ids.shape != loss_mask.shape:
         raise ValueError("hidden [..., T, H], target_ids [..., T] and loss_mask [..., T] disagree")
     h2 = hidden.reshape(1, -1, hidden.shape[-1])
-    logp, _ = _FusedLMHead.apply(h2, weight, target_ids.reshape(1, -1), 1.0, False, bool(round_bf16), None, None)
+    logp, _ = _FusedLMHead.apply(h2, weight, target_ids.reshape(1, -1), 1.0, False, bool(round_bf16), None, None, False)
     mask = loss_mask.reshape(1, -1)
     n = mask.sum()
     return -(logp * mask).sum() / n  # mean over unmasked tokens (nan for an all-False mask, like the reference)

@@ -69,15 +69,41 @@ def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, 
 
 class _FusedLMHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, hidden, weight, ids, inv_temp, shift, round_bf16, main_grad, active_positions=None):
+    def forward(ctx, hidden, weight, ids, inv_temp, shift, round_bf16, main_grad, active_positions=None, forward_active_only=False):
         lead = hidden.shape[:-1]
         h2 = hidden.detach().reshape(-1, hidden.shape[-1]).contiguous()
         w2 = weight.detach().contiguous()
         i2 = ids.detach().reshape(-1).contiguous().to(torch.int64)
-        logp, ent, lse, _ = lm_head_forward_raw(h2, w2, i2, inv_temp, shift, round_bf16)
+        ctx.compact = None
+        if active_positions is not None:
+            # positions that can receive a gradient; position 0 of a shifted row is a constant (no source row)
+            pos = active_positions.reshape(-1).to(torch.int64)
+            pos = pos[pos >= int(shift)]
+            rows = pos - int(shift)
+            ctx.compact = (pos, rows)
+        if forward_active_only and ctx.compact is not None:
+            # forward on the compacted rows only: outputs at the other positions are 0 (nothing downstream reads them: the
+            # loss multiplies by the mask and the trainer logs `[loss_mask]` slices only, rl/train.py:313-333)
+            pos, rows = ctx.compact
+            T = h2.shape[0]
+            logp = torch.zeros(T, dtype=torch.float32, device=h2.device)
+            ent = torch.zeros(T, dtype=torch.float32, device=h2.device)
+            lse = torch.zeros(T, dtype=torch.float32, device=h2.device)
+            if pos.numel() > 0:
+                h_c, i_c = h2.index_select(0, rows), i2.index_select(0, pos)
+                lp_c, ent_c, lse_c, _ = lm_head_forward_raw(h_c, w2, i_c, inv_temp, False, round_bf16)
+                logp.index_copy_(0, pos, lp_c)
+                ent.index_copy_(0, pos, ent_c)
+                lse.index_copy_(0, pos, lse_c)
+            if shift and T > 0:  # shift_logits' all-zero row: closed form (rl/loss.py:55-56)
+                import math
+
+                ln_v = math.log(float(w2.shape[0]))
+                logp[0], ent[0], lse[0] = -ln_v, ln_v, ln_v
+        else:
+            logp, ent, lse, _ = lm_head_forward_raw(h2, w2, i2, inv_temp, shift, round_bf16)
         ctx.save_for_backward(h2, w2, i2, lse)
         ctx.cfg = (inv_temp, shift, round_bf16, hidden.shape, main_grad)
-        ctx.active = active_positions
         logp, ent = logp.reshape(lead), ent.reshape(lead)
         ctx.mark_non_differentiable(ent)
         return logp, ent
@@ -88,12 +114,11 @@ class _FusedLMHead(torch.autograd.Function):
         inv_temp, shift, round_bf16, hshape, main_grad = ctx.cfg
         g = g_logp.detach().reshape(-1).contiguous().float()
         need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if ctx.active is not None:
+        none_tail = (None,) * 7
+        if ctx.compact is not None:
             # Only positions with a non-zero d loss / d logp contribute to d_hidden and d_W: run the recompute backward on
             # the compacted rows (exactly the same sums, minus the all-zero terms) and scatter d_hidden back.
-            pos = ctx.active.reshape(-1).to(torch.int64)
-            pos = pos[pos >= int(shift)]          # position 0 of a shifted row is a constant: no gradient
-            rows = pos - int(shift)               # source row of `hidden` feeding each position
+            pos, rows = ctx.compact
             dw_target = main_grad if (main_grad is not None and need_w) else None
             dh = torch.zeros(h2.shape, dtype=torch.bfloat16, device=h2.device) if need_h else None
             dw = None
@@ -108,7 +133,7 @@ class _FusedLMHead(torch.autograd.Function):
                 dw = torch.zeros_like(w2)
             if dw_target is not None:
                 dw = None
-            return (dh.reshape(hshape) if dh is not None else None), dw, None, None, None, None, None, None
+            return ((dh.reshape(hshape) if dh is not None else None), dw) + none_tail
         if main_grad is not None and need_w:
             dh, _ = lm_head_backward_raw(h2, w2, i2, lse, g, inv_temp, shift, round_bf16, want_dhidden=need_h,
                                          dweight=main_grad, dweight_accumulate=True)
@@ -116,7 +141,7 @@ class _FusedLMHead(torch.autograd.Function):
         else:
             dh, dw = lm_head_backward_raw(h2, w2, i2, lse, g, inv_temp, shift, round_bf16, want_dhidden=need_h,
                                           want_dweight=need_w)
-        return (dh.reshape(hshape) if dh is not None else None), dw, None, None, None, None, None, None
+        return ((dh.reshape(hshape) if dh is not None else None), dw) + none_tail
 
 
 def fused_lm_head_logprobs_entropy(
@@ -129,6 +154,7 @@ def fused_lm_head_logprobs_entropy(
     round_bf16: bool = True,
     main_grad: torch.Tensor | None = None,
     active_positions: torch.Tensor | None = None,
+    forward_active_only: bool = False,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """hidden [..., T, H] bf16 (final-norm output), weight [V, H] bf16 (`lm_head.weight`), input_ids
     [..., T] -> (logprobs [..., T] fp32, differentiable w.r.t. hidden and weight; entropy [..., T] fp32,
@@ -141,7 +167,8 @@ def fused_lm_head_logprobs_entropy(
     kernel and `weight.grad` is left untouched (fused gradient accumulation across micro-batches).
     `active_positions`: optional int64 index tensor of the positions that can receive a non-zero gradient (e.g.
     `loss_mask.nonzero()`): the backward then skips every other row (prompt / environment tokens) — identical gradients,
-    proportionally less recompute.  The forward always covers all T positions, as the reference does."""
+    proportionally less recompute.  By default the forward still covers all T positions, as the reference does; with
+    `forward_active_only=True` it visits the active positions only and returns 0 for log-prob and entropy elsewhere."""
     _lib.require_cuda(hidden, weight, input_ids)
     if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise ValueError("fused_lm_head_logprobs_entropy needs bf16 hidden and weight (FSDP param_dtype=bf16, model.py:103)")
@@ -150,7 +177,7 @@ def fused_lm_head_logprobs_entropy(
     if hidden.dim() > 2 and hidden.shape[:-2].numel() != 1:
         raise ValueError("only one packed row per call (micro_batch_size == 1 for packed batches)")
     return _FusedLMHead.apply(hidden, weight, input_ids, 1.0 / float(temperature), bool(shift), bool(round_bf16), main_grad,
-                              active_positions)
+                              active_positions, bool(forward_active_only))
 
 
 class FusedLMHead(nn.Module):

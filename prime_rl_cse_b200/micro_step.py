@@ -24,13 +24,16 @@ def rl_micro_step(
     main_grad: torch.Tensor | None = None,
     response_lengths: list[int] | None = None,
     skip_masked: bool = True,
+    forward_skips_masked: bool = False,
 ) -> dict[str, torch.Tensor]:
     """`hidden` [1,T,H] bf16 is what the transformer body hands to `lm_head` (requires_grad as the
     caller wishes); `micro_batch` is a `MicroBatch` (rl/data.py:13-23) whose tensors are already on the
     device (train.py:275-279).  Returns loss, logprobs, entropy and the three logging tensors of
     `compute_loss`; with `backward=True` also runs `loss.backward()` (train.py:310).  `skip_masked`: tokens with
     `loss_mask == False` get a zero gradient (loss.py:104), so the recompute backward only visits the unmasked positions;
-    skipped automatically when every token is unmasked."""
+    skipped automatically when every token is unmasked.  `forward_skips_masked` (opt-in) also restricts the FORWARD to the
+    unmasked positions: log-probs / entropy come back as 0 at masked positions (the reference computes values there that
+    nothing reads: the loss multiplies by the mask and the trainer logs `[loss_mask]` slices, train.py:313-333)."""
     input_ids = micro_batch["input_ids"]
     position_ids = micro_batch["position_ids"]
     advantages = micro_batch["advantages"]
@@ -50,7 +53,7 @@ def rl_micro_step(
 
     # train.py:285-288 + 302-303
     logprobs, entropy = fused_lm_head_logprobs_entropy(hidden, lm_head_weight, input_ids, temperature, main_grad=main_grad,
-                                                       active_positions=active)
+                                                       active_positions=active, forward_active_only=forward_skips_masked)
 
     # train.py:292-299
     loss, loss_tensors = compute_loss(

@@ -561,3 +561,31 @@ def test_backward_skips_masked_positions_exactly(P):
     assert ((dh1 - dh0).norm() / dh0.norm()).item() < 2e-3 and ((dw1 - dw0).norm() / dw0.norm()).item() < 2e-3
     inactive_rows = (~mask[1:]).nonzero().reshape(-1).cuda()
     assert float(dh1[inactive_rows].abs().max()) == 0.0
+
+
+def test_forward_active_only(P):
+    """Opt-in: forward restricted to the unmasked positions gives the same values there (and the same loss / gradients)."""
+    T, H, V, tau = 700, 256, 6000, 0.7
+    hidden, weight, ids = _mk(T, H, V, 41)
+    rng = np.random.default_rng(4)
+    mask = rng.random(T) < 0.55
+    mask[0] = True
+    lens = [300, 400]
+    pos = np.concatenate([np.arange(n) for n in lens])
+    adv = rng.standard_normal(T).astype(np.float32)
+    old = -rng.random(T).astype(np.float32) * 3
+    mb = dict(input_ids=ids.cuda().unsqueeze(0), position_ids=cu(pos).unsqueeze(0), advantages=cu(adv).unsqueeze(0),
+              logprobs=cu(old).unsqueeze(0), loss_mask=cu(mask).unsqueeze(0), temperature=tau)
+    res = []
+    for skip_fwd in (False, True):
+        h = hidden.cuda().requires_grad_(True)
+        w = weight.cuda().requires_grad_(True)
+        out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), int(mask.sum()), forward_skips_masked=skip_fwd)
+        res.append((out, h.grad.float(), w.grad.float()))
+    (o0, dh0, dw0), (o1, dh1, dw1) = res
+    m = torch.from_numpy(mask).cuda()
+    assert (o0["logprobs"][0][m] - o1["logprobs"][0][m]).abs().max().item() < 2e-4
+    assert (o0["entropy"][0][m] - o1["entropy"][0][m]).abs().max().item() < 2e-4
+    assert float(o1["logprobs"][0][~m].abs().max()) == 0.0
+    assert abs(o0["loss"].item() - o1["loss"].item()) <= 1e-4 * abs(o0["loss"].item()) + 1e-7
+    assert ((dh1 - dh0).norm() / dh0.norm()).item() < 2e-3 and ((dw1 - dw0).norm() / dw0.norm()).item() < 2e-3
