@@ -36,6 +36,7 @@ constexpr int ST_STORE_F32 = 2;   // write fp32 to c_f32
 constexpr int ST_STORE_BF16 = 4;  // write bf16 to c_bf16
 constexpr int ST_LOAD_BF16 = 8;   // C += existing bf16 at c_bf16
 constexpr int ST_TMA = 16;         // epilogue writes through smem staging + TMA store / reduce-add (tma_c)
+constexpr int ST_WAIT_BACKOFF = 1 << 18;  // epilogue warps sleep between mbarrier probes (PRL_WAIT_BACKOFF=1)
 constexpr int ST_DEBUG_SKIPB = 1 << 17;
 constexpr int ST_DEBUG_SKIP = 1 << 16;  // profiling aid (PRL_DEBUG_NOSTORE=1): run the GEMM but skip the epilogue's global memory traffic
 
@@ -541,7 +542,10 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
         }
       }
       for (int nt = it.n_begin; nt < it.n_begin + it.n_count; ++nt) {
-        ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+        if (p.epi.flags & ST_WAIT_BACKOFF)
+          ptx::mbar_wait_backoff(&tfull_bar[acc], acc_phase, 256);
+        else
+          ptx::mbar_wait(&tfull_bar[acc], acc_phase);
         ptx::tc_fence_after();
         const int64_t n0 = (int64_t)nt * BLOCK_N;
         const int64_t n_left = e.n_cols - n0;  // > 0

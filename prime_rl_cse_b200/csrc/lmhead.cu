@@ -171,6 +171,7 @@ static int launch_gemm_cg(const GemmParams& p, cudaStream_t st, const char* name
   if (p.num_items < 1) return PRL_OK;
   if (env_long("PRL_DEBUG_NOSTORE", 0)) const_cast<GemmParams&>(p).epi.flags |= ST_DEBUG_SKIP;
   if (env_long("PRL_DEBUG_SKIPB", 0)) const_cast<GemmParams&>(p).epi.flags |= ST_DEBUG_SKIPB;
+  if (env_long("PRL_WAIT_BACKOFF", 0)) const_cast<GemmParams&>(p).epi.flags |= ST_WAIT_BACKOFF;
   int nw = resident_workers<CG>();
   if (nw > p.num_items) nw = p.num_items;
   cudaLaunchConfig_t cfg;
