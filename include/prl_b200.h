@@ -168,6 +168,19 @@ int prl_masked_moments_f32(const float* x, const uint8_t* mask, int64_t n, int32
                            size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Packed micro-batch rows from rollouts ("next" row N4).  Replaces the per-token tensor building of prepare_sample
+ * (src/prime_rl/orchestrator/batch.py:21-62: cat(prompt, completion), arange position ids, advantage.repeat(len),
+ * cat(zeros(len(prompt)), completion_logprobs)) and the concatenation of prepare_micro_batch_packing (:105-120) for ALL
+ * rollouts of a step in one launch.  Rollout i (source order) has tokens[src_tok_off[i] .. src_tok_off[i+1]) =
+ * prompt + completion (int64), mask[...] (uint8, same indexing), completion log-probs lp[src_lp_off[i] ..), prompt_len[i],
+ * advantage[i]; it is written at dst_off[i] of the packed stream (the bin order decided by the host's first-fit-decreasing
+ * pass, batch.py:76-102).  Outputs are flat [total] arrays; a micro-batch is a contiguous slice of them.
+ * ---------------------------------------------------------------------------------------- */
+int prl_pack_rollouts(const int64_t* tokens, const uint8_t* mask, const float* completion_logprobs, const int64_t* src_tok_off,
+                      const int64_t* src_lp_off, const int32_t* prompt_len, const float* advantage, const int64_t* dst_off, int64_t n,
+                      int64_t* input_ids, int64_t* position_ids, float* advantages, float* logprobs, uint8_t* loss_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Plain bf16 GEMM on the same tcgen05 engine, exposed for tests and bring-up:
  *   C[M,N] (fp32) = A x B with per-operand major-ness:
  *   a_mn_major == 0: A is [M,K] row-major (K contiguous); != 0: A is stored [K,M] (M contiguous)

@@ -12,6 +12,7 @@ Everything runs on CUDA through the C-ABI library `libprl_b200.so`; there is no 
 """
 
 from .advantage import compute_advantages, compute_advantages_tensor
+from .batch import first_fit_decreasing, prepare_batch
 from .config import LossConfig
 from .data import MicroBatch, fake_micro_batch, synthetic_micro_batch, to_device
 from .lm_head import FusedLMHead, fused_lm_head_logprobs_entropy, lm_head_backward_raw, lm_head_forward_raw
@@ -28,6 +29,6 @@ __all__ = [
     "synthetic_micro_batch", "to_device", "FusedLMHead", "fused_lm_head_logprobs_entropy", "lm_head_backward_raw",
     "lm_head_forward_raw", "compute_entropy", "compute_loss", "selective_log_softmax", "shift_logits",
     "shifted_logprobs_entropy", "rl_micro_step", "get_response_lengths", "segments_from_position_ids",
-    "fused_linear_cross_entropy", "recompute_logprobs", "TensorStats",
+    "fused_linear_cross_entropy", "recompute_logprobs", "TensorStats", "prepare_batch", "first_fit_decreasing",
     "exchange_partials", "local_loss_scale", "shard_micro_batches", "vocab_parallel_lm_head_logprobs_entropy", "vocab_shard_bounds",
 ]

@@ -36,6 +36,7 @@ _SIGNATURES = {
          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p],
     ),
     "prl_scale_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "prl_pack_rollouts": (c_int32, [c_void_p] * 8 + [c_int64] + [c_void_p] * 6),
     "prl_masked_moments_workspace_bytes": (c_size_t, []),
     "prl_masked_moments_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "prl_logits_stats_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_int32, c_void_p, c_void_p, c_void_p]),

@@ -520,6 +520,30 @@ __global__ void masked_moments_finalize_kernel(const double* __restrict__ partia
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// rollouts -> packed rows (orchestrator/batch.py:21-62,105-120): one CTA per rollout, 13 B read + 25 B written per token
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_rollouts_kernel(const int64_t* __restrict__ tokens, const uint8_t* __restrict__ mask,
+                                                            const float* __restrict__ lp, const int64_t* __restrict__ src_tok_off,
+                                                            const int64_t* __restrict__ src_lp_off, const int32_t* __restrict__ prompt_len,
+                                                            const float* __restrict__ advantage, const int64_t* __restrict__ dst_off,
+                                                            int64_t n, int64_t* __restrict__ input_ids, int64_t* __restrict__ position_ids,
+                                                            float* __restrict__ advantages, float* __restrict__ logprobs,
+                                                            uint8_t* __restrict__ loss_mask) {
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const int64_t s0 = src_tok_off[i], len = src_tok_off[i + 1] - s0, d0 = dst_off[i], l0 = src_lp_off[i];
+    const int64_t pl = prompt_len[i];
+    const float a = advantage[i];
+    for (int64_t j = threadIdx.x; j < len; j += blockDim.x) {
+      input_ids[d0 + j] = tokens[s0 + j];
+      position_ids[d0 + j] = j;
+      advantages[d0 + j] = a;
+      logprobs[d0 + j] = (j < pl) ? 0.f : lp[l0 + j - pl];
+      loss_mask[d0 + j] = mask[s0 + j] != 0 ? 1 : 0;
+    }
+  }
+}
+
 }  // namespace prl
 
 // ================================================================================================
@@ -636,6 +660,21 @@ int prl_scale_f32(const float* a, const float* scale, float* out, int64_t n, voi
   const int64_t need = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
   scale_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(a, scale, out, n);
   return check_launch("scale_kernel");
+}
+
+int prl_pack_rollouts(const int64_t* tokens, const uint8_t* mask, const float* completion_logprobs, const int64_t* src_tok_off,
+                      const int64_t* src_lp_off, const int32_t* prompt_len, const float* advantage, const int64_t* dst_off, int64_t n,
+                      int64_t* input_ids, int64_t* position_ids, float* advantages, float* logprobs, uint8_t* loss_mask, void* stream) {
+  PRL_REQUIRE(n >= 0, PRL_ERR_BAD_ARG, "pack_rollouts: negative size");
+  if (n == 0) return PRL_OK;
+  PRL_REQUIRE(tokens && mask && completion_logprobs && src_tok_off && src_lp_off && prompt_len && advantage && dst_off && input_ids &&
+                  position_ids && advantages && logprobs && loss_mask,
+              PRL_ERR_BAD_ARG, "pack_rollouts: null pointer");
+  const int64_t cap = (int64_t)sm_count() * 8;
+  pack_rollouts_kernel<<<(int)(n < cap ? n : cap), 256, 0, (cudaStream_t)stream>>>(tokens, mask, completion_logprobs, src_tok_off, src_lp_off,
+                                                                                    prompt_len, advantage, dst_off, n, input_ids, position_ids,
+                                                                                    advantages, logprobs, loss_mask);
+  return check_launch("pack_rollouts_kernel");
 }
 
 size_t prl_masked_moments_workspace_bytes(void) { return sizeof(double) * 5 * MOM_BLOCKS; }

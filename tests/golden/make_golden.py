@@ -289,6 +289,16 @@ def gen_packed_layout():
                              num_train_workers=2)
     out = {"n_ranks": np.asarray(len(per_rank)), "rewards": np.asarray(rewards, dtype=np.float32), "lens": np.asarray(lens),
            "advantages": np.asarray(adv, dtype=np.float32)}
+    # the rollouts themselves (inputs of prepare_batch), flattened
+    out["ro/prompt_len"] = np.asarray([len(r.prompt_tokens) for r in rollouts], dtype=np.int64)
+    out["ro/completion_len"] = np.asarray([len(r.completion_tokens) for r in rollouts], dtype=np.int64)
+    out["ro/prompt_tokens"] = np.concatenate([np.asarray(r.prompt_tokens, dtype=np.int64) for r in rollouts])
+    out["ro/prompt_mask"] = np.concatenate([np.asarray(r.prompt_mask, dtype=np.int64) for r in rollouts])
+    out["ro/completion_tokens"] = np.concatenate([np.asarray(r.completion_tokens, dtype=np.int64) for r in rollouts])
+    out["ro/completion_mask"] = np.concatenate([np.asarray(r.completion_mask, dtype=np.int64) for r in rollouts])
+    out["ro/completion_logprobs"] = np.concatenate([np.asarray(r.completion_logprobs, dtype=np.float32) for r in rollouts])
+    out["ro/advantage"] = np.asarray([r.advantage for r in rollouts], dtype=np.float32)
+    out["ro/args"] = np.asarray([0.6, len(rollouts), 2, 48, 2])  # temperature, batch_size, micro_batch_size, seq_len, num_train_workers
     for r, mbs in enumerate(per_rank):
         out[f"rank{r}/n"] = np.asarray(len(mbs))
         for i, mb in enumerate(mbs):

@@ -589,3 +589,34 @@ def test_forward_active_only(P):
     assert float(o1["logprobs"][0][~m].abs().max()) == 0.0
     assert abs(o0["loss"].item() - o1["loss"].item()) <= 1e-4 * abs(o0["loss"].item()) + 1e-7
     assert ((dh1 - dh0).norm() / dh0.norm()).item() < 2e-3 and ((dw1 - dw0).norm() / dw0.norm()).item() < 2e-3
+
+
+def test_next_row_prepare_batch_on_device(P):
+    """`prepare_batch` drop-in (host first-fit-decreasing + one packing kernel) reproduces the reference
+    orchestrator's micro-batches bit for bit, including the padding micro-batch and the per-worker split."""
+    from types import SimpleNamespace
+
+    d = load("packed_layout.npz")
+    pl, cl = d["ro/prompt_len"], d["ro/completion_len"]
+    po, co = np.concatenate([[0], np.cumsum(pl)]), np.concatenate([[0], np.cumsum(cl)])
+    rollouts = []
+    for i in range(len(pl)):
+        rollouts.append(SimpleNamespace(
+            prompt_tokens=d["ro/prompt_tokens"][po[i]:po[i + 1]].tolist(), prompt_mask=d["ro/prompt_mask"][po[i]:po[i + 1]].tolist(),
+            completion_tokens=d["ro/completion_tokens"][co[i]:co[i + 1]].tolist(),
+            completion_mask=d["ro/completion_mask"][co[i]:co[i + 1]].tolist(),
+            completion_logprobs=d["ro/completion_logprobs"][co[i]:co[i + 1]].tolist(), advantage=float(d["ro/advantage"][i])))
+    temperature, batch_size, mbs, seq_len, nw = d["ro/args"]
+    out = P.prepare_batch(rollouts, float(temperature), None, int(batch_size), int(mbs), int(seq_len), int(nw))
+    assert len(out) == int(d["n_ranks"])
+    for r, per_rank in enumerate(out):
+        assert len(per_rank) == int(d[f"rank{r}/n"])
+        for i, mb in enumerate(per_rank):
+            assert mb["temperature"] == float(d[f"rank{r}/mb{i}/temperature"])
+            for k in ("input_ids", "position_ids", "advantages", "logprobs", "loss_mask"):
+                ref = d[f"rank{r}/mb{i}/{k}"]
+                got = mb[k].numpy()
+                assert got.dtype == ref.dtype and got.shape == ref.shape, (k, got.dtype, ref.dtype, got.shape, ref.shape)
+                np.testing.assert_array_equal(got, ref, err_msg=f"rank{r}/mb{i}/{k}")
+    with pytest.raises(ValueError):
+        P.prepare_batch(rollouts, 1.0, None, 12, 1, 8, 2)  # a rollout longer than seq_len * micro_batch_size

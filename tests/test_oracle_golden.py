@@ -191,3 +191,16 @@ def test_packed_layout_from_reference_prepare_batch():
                 n_pad += 1
                 assert not adv.any()  # padding micro-batch: zero advantages, all-False mask (batch.py:153-161)
     assert n_pad == 1
+
+
+def test_first_fit_decreasing_matches_reference_bins():
+    """Host half of N4: the bin assignment reproduces the reference's packed micro-batches (segment lengths per bin)."""
+    from prime_rl_cse_b200.batch import first_fit_decreasing
+
+    d = load("packed_layout.npz")
+    lens = (d["ro/prompt_len"] + d["ro/completion_len"]).tolist()
+    temperature, batch_size, mbs, seq_len, nw = d["ro/args"]
+    bins = first_fit_decreasing(lens, int(seq_len) * int(mbs))
+    got = [[lens[i] for i in b] for b in bins]
+    want = [d["rank0/mb0/lengths"].tolist(), d["rank0/mb1/lengths"].tolist(), d["rank1/mb0/lengths"].tolist()]
+    assert got == want
