@@ -307,6 +307,7 @@ int prl_lmhead_fwd(const void* hidden, const void* weight, const int64_t* ids, i
                    float* partials, void* workspace, size_t workspace_bytes, void* stream) {
   PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_fwd: bad sizes");
   PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_fwd: shift must be 0 or 1");
+  PRL_REQUIRE(inv_temp > 0.f && inv_temp < INFINITY, PRL_ERR_BAD_ARG, "lmhead_fwd: temperature must be positive and finite");
   PRL_REQUIRE(v_offset >= 0 && v_offset + V <= V_total, PRL_ERR_BAD_ARG, "lmhead_fwd: vocab shard outside [0, V_total)");
   if (T == 0) return PRL_OK;
   PRL_REQUIRE(hidden && weight && ids && workspace, PRL_ERR_BAD_ARG, "lmhead_fwd: null pointer");
@@ -373,6 +374,7 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
                    size_t workspace_bytes, void* stream) {
   PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_bwd: bad sizes");
   PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_bwd: shift must be 0 or 1");
+  PRL_REQUIRE(inv_temp > 0.f && inv_temp < INFINITY, PRL_ERR_BAD_ARG, "lmhead_bwd: temperature must be positive and finite");
   PRL_REQUIRE(d_weight_dtype == PRL_DT_BF16 || d_weight_dtype == PRL_DT_F32, PRL_ERR_BAD_ARG, "lmhead_bwd: bad d_weight dtype");
   if (T == 0) return PRL_OK;
   PRL_REQUIRE(hidden && weight && ids && lse && dlogp && workspace, PRL_ERR_BAD_ARG, "lmhead_bwd: null pointer");

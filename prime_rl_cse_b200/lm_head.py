@@ -174,6 +174,8 @@ def fused_lm_head_logprobs_entropy(
         raise ValueError("fused_lm_head_logprobs_entropy needs bf16 hidden and weight (FSDP param_dtype=bf16, model.py:103)")
     if hidden.shape[:-1] != input_ids.shape:
         raise ValueError("hidden [..., T, H] and input_ids [..., T] disagree")
+    if not float(temperature) > 0.0:
+        raise ValueError("temperature must be positive (the online softmax tracks the maximum logit)")
     if hidden.dim() > 2 and hidden.shape[:-2].numel() != 1:
         raise ValueError("only one packed row per call (micro_batch_size == 1 for packed batches)")
     return _FusedLMHead.apply(hidden, weight, input_ids, 1.0 / float(temperature), bool(shift), bool(round_bf16), main_grad,

@@ -52,6 +52,7 @@ def test_argument_validation_needs_no_gpu(lib):
     assert L.prl_advantages_f32(None, None, 0, 2, 0, None, None, None, None) == 0
     assert L.prl_lmhead_fwd(None, None, None, 8, 12, 100, 0, 100, 1.0, 1, 1, None, None, None, None, None, 0, None) == -1
     assert L.prl_loss_packed_fwd(None, None, None, None, None, 1, 8, 7, 0, 8.0, 1.0, None, None, None, None, None, None, 0, None) == -1
+    assert L.prl_lmhead_fwd(None, None, None, 8, 16, 100, 0, 100, -1.0, 1, 1, None, None, None, None, None, 0, None) == -1  # temperature <= 0
     assert L.prl_lmhead_fwd_workspace_bytes(16384, 4096, 151936) >= 64 * 16384 * 16
     assert L.prl_lmhead_bwd_workspace_bytes(16384, 4096, 151936, 8192) >= 16384 * 8192 * 2
 
