@@ -69,6 +69,7 @@ struct GemmParams {
   CUtensorMap tma_c;  // output map for the TMA-store epilogues (fp32 {32 x 32} or bf16 {64 x 32} boxes, 128B swizzle)
   int32_t m_tiles, n_tiles, k_blocks;
   int32_t tiles_per_split, n_splits, group_m, num_items;
+  int32_t split_group;  // 0: m-tile fastest inside a band; S > 0: splits fastest in groups of S (neighbouring workers share an m-tile)
   uint64_t a_desc_hi, b_desc_hi;  // smem descriptor templates (everything but the start address)
   uint32_t a_kstep, b_kstep;      // byte advance of the start address per UMMA_K step
   uint64_t hint_a, hint_b, hint_c;  // L2 eviction priority of the A / B loads and of the epilogue's stores
@@ -86,8 +87,18 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
   const int rows = min(p.group_m, p.m_tiles - m0);
   const int idx = item - band * per_band;
   Item it;
-  it.split = idx / rows;
-  it.m_tile = m0 + idx % rows;
+  if (p.split_group > 0) {
+    // the workers that sweep the same vocab range are spread over the whole chip (both dies), neighbours share the A panel
+    const int per_grp = rows * p.split_group;
+    const int g = idx / per_grp;
+    const int s_here = min(p.split_group, p.n_splits - g * p.split_group);
+    const int r = idx - g * per_grp;
+    it.split = g * p.split_group + r % s_here;
+    it.m_tile = m0 + r / s_here;
+  } else {
+    it.split = idx / rows;
+    it.m_tile = m0 + idx % rows;
+  }
   it.n_begin = it.split * p.tiles_per_split;
   it.n_count = min(p.tiles_per_split, p.n_tiles - it.n_begin);
   return it;

@@ -226,6 +226,7 @@ static void schedule_sweeps(GemmParams& p, int max_splits, int epi) {
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.group_m = (int)env_long("PRL_SWEEP_GROUP_M", 32) / (cta_group() * msub(epi));
   if (p.group_m < 1) p.group_m = 1;
+  p.split_group = (int)env_long("PRL_SPLIT_GROUP", 0);
   p.num_items = p.m_tiles * p.n_splits;
 }
 
