@@ -159,7 +159,7 @@ static void set_hints(GemmParams& p, const char* family, int a, int b, int c) {
 }
 
 template <int CG, int MS, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm_cg(const GemmParams& p, cudaStream_t st, const char* name) {
+static int launch_gemm_cg(GemmParams p /* by value: the profiling knobs below edit the copy */, cudaStream_t st, const char* name) {
   using C = Cfg<CG, MS, EPI>;
   static bool attr_set = false;
   auto kern = gemm_kernel<CG, MS, A_MN, B_MN, EPI>;
@@ -169,9 +169,9 @@ static int launch_gemm_cg(const GemmParams& p, cudaStream_t st, const char* name
     attr_set = true;
   }
   if (p.num_items < 1) return PRL_OK;
-  if (env_long("PRL_DEBUG_NOSTORE", 0)) const_cast<GemmParams&>(p).epi.flags |= ST_DEBUG_SKIP;
-  if (env_long("PRL_DEBUG_SKIPB", 0)) const_cast<GemmParams&>(p).epi.flags |= ST_DEBUG_SKIPB;
-  if (env_long("PRL_WAIT_BACKOFF", 0)) const_cast<GemmParams&>(p).epi.flags |= ST_WAIT_BACKOFF;
+  if (env_long("PRL_DEBUG_NOSTORE", 0)) p.epi.flags |= ST_DEBUG_SKIP;
+  if (env_long("PRL_DEBUG_SKIPB", 0)) p.epi.flags |= ST_DEBUG_SKIPB;
+  if (env_long("PRL_WAIT_BACKOFF", 0)) p.epi.flags |= ST_WAIT_BACKOFF;
   int nw = resident_workers<CG>();
   if (nw > p.num_items) nw = p.num_items;
   cudaLaunchConfig_t cfg;
