@@ -139,6 +139,8 @@ static int resident_workers() {
       if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
       cudaGetLastError();
     }
+    const long cap = env_long("PRL_MAX_WORKERS", 0);  // diagnostic: use only the first `cap` clusters
+    if (cap > 0 && cap < n) n = (int)cap;
     cached = n > 0 ? n : 1;
   }
   return cached;
