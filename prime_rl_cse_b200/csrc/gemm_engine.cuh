@@ -69,6 +69,7 @@ struct GemmParams {
   CUtensorMap tma_c;  // output map for the TMA-store epilogues (fp32 {32 x 32} or bf16 {64 x 32} boxes, 128B swizzle)
   int32_t m_tiles, n_tiles, k_blocks;
   int32_t tiles_per_split, n_splits, group_m, num_items;
+  int32_t max_stages;   // > 0: use at most this many of the smem ring's stages (prefetch-depth experiments)
   int32_t split_group;  // 0: m-tile fastest inside a band; S > 0: splits fastest in groups of S (neighbouring workers share an m-tile)
   uint64_t a_desc_hi, b_desc_hi;  // smem descriptor templates (everything but the start address)
   uint32_t a_kstep, b_kstep;      // byte advance of the start address per UMMA_K step
@@ -329,6 +330,7 @@ template <int CG, int MS, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<CG, MS, EPI>;
   constexpr int NS = C::kStages;
+  const int ns_run = (p.max_stages > 0 && p.max_stages < NS) ? p.max_stages : NS;  // stages actually cycled through
   static_assert(MS == 1 || CG == 2, "M sub-tiling is implemented for CTA pairs only");
   static_assert(NS >= 2, "pipeline needs at least two stages");
   extern __shared__ uint8_t smem_raw[];
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
                 load_b(sb + slab * (BLOCK_K * 128), n0 + slab * 64, kb * BLOCK_K);
               }
             }
-            if (++stage == NS) {
+            if (++stage == ns_run) {
               stage = 0;
               phase ^= 1;
             }
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
               ptx::umma_commit_cg2(&empty_bar[stage], mask_all);
             else
               ptx::umma_commit(&empty_bar[stage]);
-            if (++stage == NS) {
+            if (++stage == ns_run) {
               stage = 0;
               phase ^= 1;
             }
