@@ -428,7 +428,7 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
         p.epi.flags = ST_TMA;
       }
       set_hints(p, "DZ", 2, 1, 1);  // hidden band reused across the sweep, W tiles and the dlogits block stream through
-      p.max_stages = (int)env_long("PRL_DZ_STAGES", 0);  // all 6 stages: 4 measured 6 % slower, 5 the same
+      p.max_stages = (int)env_long("PRL_DZ_STAGES", 5);  // 5 of 6 stages: +1 % over 6, 4 is 6 % slower
       rc = launch_gemm<false, false, EPI_DZ>(p, st, "lmhead_bwd_dz_kernel");
       if (rc) return rc;
     }
