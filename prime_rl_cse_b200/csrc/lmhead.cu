@@ -205,6 +205,7 @@ static void schedule_tiles(GemmParams& p) {
   p.n_splits = p.n_tiles;
   p.group_m = (int)env_long("PRL_GROUP_M", 8) / (cta_group() * msub(EPI_STORE));
   if (p.group_m < 1) p.group_m = 1;
+  p.max_stages = (int)env_long("PRL_TILE_STAGES", 0);
   p.num_items = p.m_tiles * p.n_splits;
 }
 
