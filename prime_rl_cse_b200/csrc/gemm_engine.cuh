@@ -1,12 +1,16 @@
 // Persistent, warp-specialised tcgen05 GEMM engine for sm_100a with pluggable epilogues.
 //
-//   C[M,N] = A x B, bf16 inputs, fp32 accumulation in TMEM, 128 x 256 output tiles per CTA (256 x 256 per CTA
-//   pair with cta_group::2), BLOCK_K = 64.
-//   warp 0 (one lane): TMA producer  -> 4-stage (6-stage for CTA pairs) smem ring (128B-swizzled tiles)
-//   warp 1 (one lane): tcgen05.mma issuer -> 2 accumulator buffers of 256 TMEM columns
+//   C[M,N] = A x B, bf16 inputs, fp32 accumulation in TMEM, BLOCK_K = 64.  Tile shapes (template parameters CG, MS):
+//     CG = 1         128 x 256 per CTA
+//     CG = 2, MS = 1 256 x 256 per CTA pair (tcgen05.mma.cta_group::2), double-buffered accumulators   [forward, dlogits]
+//     CG = 2, MS = 2 512 x 256 per CTA pair: two M sub-tiles share every B k-block                     [d_hidden, d_weight]
+//     CG = 4         two pairs per cluster sharing B by TMA multicast (kept for comparison)
+//   warp 0 (one lane): TMA producer  -> smem ring of 128B-swizzled stages (as many as fit: 3..7; the host may cap the depth)
+//   warp 1 (one lane): tcgen05.mma issuer -> two 256-column TMEM accumulators
 //   warp 2           : TMEM allocator
-//   warps 4..7       : epilogue; thread i owns accumulator row (lane) i of the tile, so row-wise
-//                      softmax statistics are thread-local (tcgen05.ld 32x32b).
+//   warps 4..        : epilogue (4 warps per M sub-tile); thread i owns accumulator row (lane) i of the tile, so row-wise
+//                      softmax statistics are thread-local (tcgen05.ld 32x32b); outputs leave through smem staging + TMA
+//                      store / reduce-add.
 // Each operand is either K-major (rows of K contiguous) or MN-major (K rows of contiguous M/N), both in
 // the canonical SWIZZLE_128B layouts written directly by TMA.
 //
