@@ -25,6 +25,13 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// L2 promotion of TMA requests (PRL_L2_PROMO = 0 none | 64 | 128 | 256; default 256)
+static CUtensorMapL2promotion l2_promotion() {
+  const long v = env_long_fwd("PRL_L2_PROMO", 256);
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+}
+
 // matrix with `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements; 128B-swizzled boxes.
 static int make_tmap_t(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer,
                        bool f32) {
@@ -39,7 +46,7 @@ static int make_tmap_t(CUtensorMap* map, const void* base, int64_t inner, int64_
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PRL_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %s%lld)", "", (long long)r);
   return PRL_OK;
 }
