@@ -156,6 +156,31 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Saved-logits variant of the same forward / backward pair: trades T x saved_ld x 2 bytes of HBM for the
+ * backward's logits recompute (one of the four [T,H]x[H,V]-sized GEMMs of a micro-step).  Still replaces
+ * rl/train.py:285-288,302-303,310; the reference itself keeps the fp32 [T,V] logits (and their gradient)
+ * alive between forward and backward, this keeps ONE bf16 copy and overwrites it in place.
+ *   prl_lmhead_saved_logits_ld(V): row pitch (elements) the library recommends for the saved block.
+ *   prl_lmhead_fwd_save: prl_lmhead_fwd with round_bf16 = 1 that also writes the bf16 logits (before the
+ *     1/temperature scaling) of source row r to saved_logits[r * saved_ld + v], r < T - shift, v < V.
+ *   prl_lmhead_bwd_saved: converts saved_logits in place to dlogits (bit-identical to what the recompute
+ *     backward produces; the block is CONSUMED), then runs the d_hidden / d_weight GEMMs over the whole
+ *     vocabulary in one launch each (no vocab chunks, no fp32 d_hidden accumulator, no workspace).
+ *     phase_mask: bit 0 = logits -> dlogits pass, bit 1 = d_hidden GEMM, bit 2 = d_weight GEMM; 0 = all.
+ * saved_logits: 16-byte aligned, saved_ld >= V, saved_ld % 8 == 0, at least T * saved_ld bf16 elements.
+ * ---------------------------------------------------------------------------------------- */
+int64_t prl_lmhead_saved_logits_ld(int64_t V);
+int prl_lmhead_fwd_save(const void* hidden, const void* weight, const int64_t* ids, int64_t T, int32_t H, int64_t V,
+                        int64_t v_offset, int64_t V_total, float inv_temp, int32_t shift, float* logp,
+                        float* entropy, float* lse, float* partials, void* saved_logits, int64_t saved_ld,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int prl_lmhead_bwd_saved(const void* hidden, const void* weight, const int64_t* ids, const float* lse,
+                         const float* dlogp, int64_t T, int32_t H, int64_t V, int64_t v_offset, float inv_temp,
+                         int32_t shift, void* saved_logits, int64_t saved_ld, void* d_hidden,
+                         int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw,
+                         int32_t phase_mask, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * On-device logging statistics ("next" row N1).  Replaces the per-micro-batch boolean-index + blocking .to("cpu")
  * of src/prime_rl/trainer/rl/train.py:313-333 and the padded all-gather of every masked token in
  * Tensors.compute_stats (src/prime_rl/trainer/utils.py:228-256) by five running moments per logged key:

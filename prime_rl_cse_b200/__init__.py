@@ -15,7 +15,8 @@ from .advantage import compute_advantages, compute_advantages_tensor
 from .batch import first_fit_decreasing, prepare_batch
 from .config import LossConfig
 from .data import MicroBatch, fake_micro_batch, synthetic_micro_batch, to_device
-from .lm_head import FusedLMHead, fused_lm_head_logprobs_entropy, lm_head_backward_raw, lm_head_forward_raw
+from .lm_head import (FusedLMHead, fused_lm_head_logprobs_entropy, lm_head_backward_raw, lm_head_backward_saved_raw,
+                      lm_head_forward_raw, lm_head_forward_save_raw, saved_logits_policy)
 from .loss import compute_entropy, compute_loss, selective_log_softmax, shift_logits, shifted_logprobs_entropy
 from .extras import fused_linear_cross_entropy, recompute_logprobs
 from .micro_step import rl_micro_step
@@ -27,7 +28,7 @@ from .parallel import (exchange_partials, local_loss_scale, shard_micro_batches,
 __all__ = [
     "compute_advantages", "compute_advantages_tensor", "LossConfig", "MicroBatch", "fake_micro_batch",
     "synthetic_micro_batch", "to_device", "FusedLMHead", "fused_lm_head_logprobs_entropy", "lm_head_backward_raw",
-    "lm_head_forward_raw", "compute_entropy", "compute_loss", "selective_log_softmax", "shift_logits",
+    "lm_head_forward_raw", "lm_head_forward_save_raw", "lm_head_backward_saved_raw", "saved_logits_policy", "compute_entropy", "compute_loss", "selective_log_softmax", "shift_logits",
     "shifted_logprobs_entropy", "rl_micro_step", "get_response_lengths", "segments_from_position_ids",
     "fused_linear_cross_entropy", "recompute_logprobs", "TensorStats", "prepare_batch", "first_fit_decreasing",
     "exchange_partials", "local_loss_scale", "shard_micro_batches", "vocab_parallel_lm_head_logprobs_entropy", "vocab_shard_bounds",

@@ -32,7 +32,8 @@ constexpr int UMMA_K = 16;
 constexpr int TMEM_COLS = 512;
 constexpr float LOG2E = 1.4426950408889634f;
 
-enum EpiKind { EPI_STATS = 0, EPI_DZ = 1, EPI_STORE = 2 };
+// EPI_STATS_STORE = the forward statistics plus a bf16 copy of the (rounded) logits, kept for the saved-logits backward
+enum EpiKind { EPI_STATS = 0, EPI_DZ = 1, EPI_STORE = 2, EPI_STATS_STORE = 3 };
 
 // flags of the STORE epilogue
 constexpr int ST_LOAD_F32 = 1;    // C += existing fp32 at c_f32
@@ -58,7 +59,7 @@ struct EpiParams {
   int64_t part_stride;
   const float* lse;        // DZ: [T]
   const float* dlogp;      // DZ: [T]
-  __nv_bfloat16* dz;       // DZ: [rows][ldz] bf16
+  __nv_bfloat16* dz;       // DZ: [rows][ldz] bf16 dlogits; STATS_STORE: [rows][ldz] bf16 logits
   int64_t ldz;
   // --- STORE ---
   float* c_f32;
@@ -132,11 +133,22 @@ __device__ __forceinline__ void round_pair(uint32_t v0, uint32_t v1, bool round,
 }
 
 // 32 columns of one row: packed fp32x2 math (FFMA2 / FADD2), four independent accumulation chains, ~5 issue slots per logit
-template <bool PARTIAL>
-__device__ __forceinline__ void stats_chunk(const uint32_t (&v)[32], RowStats& st, float c1, bool round, int n_valid_in_chunk, int tj) {
+// STORE: also returns the 32 logits as 16 packed bf16x2 words (the rounding the statistics use anyway)
+template <bool PARTIAL, bool STORE = false>
+__device__ __forceinline__ void stats_chunk(const uint32_t (&v)[32], RowStats& st, float c1, bool round, int n_valid_in_chunk, int tj,
+                                            uint32_t* w = nullptr) {
   float a[32];
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) round_pair(v[j], v[j + 1], round, a[j], a[j + 1]);
+  for (int j = 0; j < 32; j += 2) {
+    if (STORE) {
+      const uint32_t pk = ptx::cvt_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+      w[j >> 1] = pk;
+      a[j] = __uint_as_float(pk << 16);
+      a[j + 1] = __uint_as_float(pk & 0xFFFF0000u);
+    } else {
+      round_pair(v[j], v[j + 1], round, a[j], a[j + 1]);
+    }
+  }
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
@@ -233,6 +245,20 @@ __device__ __forceinline__ void dz_pack(const uint32_t (&v)[32], float c1, bool 
   dz_values(v, c1, round, coef, nlse2, tj, d);
 #pragma unroll
   for (int j = 0; j < 16; ++j) w[j] = ptx::cvt_bf16x2(d[2 * j], d[2 * j + 1]);
+}
+
+// register-path store of 32 bf16 values held as 16 packed words (PRL_EPI_TMA=0)
+__device__ __forceinline__ void store_words(const uint32_t (&w)[16], __nv_bfloat16* dst, int n_valid_in_chunk) {
+  if (n_valid_in_chunk >= 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    uint4* o = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_uint4(w[4 * q + 0], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  } else {
+    uint16_t* o = reinterpret_cast<uint16_t*>(dst);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < n_valid_in_chunk) o[j] = (uint16_t)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xFFFFu));
+  }
 }
 
 __device__ __forceinline__ void store_chunk(const uint32_t (&v)[32], const EpiParams& e, int64_t row, int64_t col0, int n_valid_in_chunk) {
@@ -547,8 +573,9 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
       // per-item row state
       RowStats st = {-INFINITY, 0.f, 0.f, 0.f};
       int64_t tcol = -1;  // target column of this row, local to this GEMM's column space
-      float coef = 0.f, nlse2 = 0.f;
-      if (EPI == EPI_STATS || EPI == EPI_DZ) {
+      // rows without a target (t >= T) keep coef = 0 and exp2(.. - inf) = 0, so their dlogits are exactly 0
+      float coef = 0.f, nlse2 = -INFINITY;
+      if (EPI == EPI_STATS || EPI == EPI_STATS_STORE || EPI == EPI_DZ) {
         const int64_t t = row + e.shift;
         if (row_ok && t < e.T) {
           tcol = e.ids[t] - e.col_base;
@@ -567,7 +594,7 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
         const int64_t n0 = (int64_t)nt * BLOCK_N;
         const int64_t n_left = e.n_cols - n0;  // > 0
         const bool use_tma = (EPI != EPI_STATS) && (e.flags & ST_TMA) && !(e.flags & ST_DEBUG_SKIP);
-        const bool out_bf16 = (EPI == EPI_DZ) || (e.flags & ST_STORE_BF16);
+        const bool out_bf16 = (EPI == EPI_DZ) || (EPI == EPI_STATS_STORE) || (e.flags & ST_STORE_BF16);
         const int row0_warp = (int)row_base + quarter * 32;
 #pragma unroll 1
         for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
@@ -587,6 +614,13 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
               stats_chunk<false>(v, st, c1, e.round_bf16 != 0, 32, tj);
             else
               stats_chunk<true>(v, st, c1, e.round_bf16 != 0, n_valid, tj);
+          } else if (EPI == EPI_STATS_STORE && !use_tma) {
+            uint32_t w[16];
+            if (n_valid == 32)
+              stats_chunk<false, true>(v, st, c1, true, 32, tj, w);
+            else
+              stats_chunk<true, true>(v, st, c1, true, n_valid, tj, w);
+            if (row_ok) store_words(w, e.dz + row * e.ldz + c0, n_valid);
           } else if (!use_tma) {
             if (EPI == EPI_DZ) {
               if (row < e.T && !(e.flags & ST_DEBUG_SKIP))
@@ -613,6 +647,11 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
               uint32_t w[16];
               if (EPI == EPI_DZ) {
                 dz_pack(v, c1, e.round_bf16 != 0, coef, nlse2, tj, w);
+              } else if (EPI == EPI_STATS_STORE) {
+                if (n_valid == 32)
+                  stats_chunk<false, true>(v, st, c1, true, 32, tj, w);
+                else
+                  stats_chunk<true, true>(v, st, c1, true, n_valid, tj, w);
               } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
@@ -662,7 +701,7 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
           acc_phase ^= 1;
         }
       }
-      if (EPI == EPI_STATS) {
+      if (EPI == EPI_STATS || EPI == EPI_STATS_STORE) {
         if (row_ok)
           e.partials[(int64_t)it.split * e.part_stride + row] = make_float4(st.m * e.inv_temp, st.s, st.u * e.inv_temp, st.zt * e.inv_temp);
       }

@@ -291,6 +291,56 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
   for (int64_t i = n8 * 8 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// Saved-logits backward, step 1: turn the bf16 logits the forward kept into dlogits IN PLACE (HBM-bound: one read and one
+// write of [T, V] bf16).  Same per-element operations as the recompute epilogue (dz_values in gemm_engine.cuh), so both
+// modes produce the same dlogits bit for bit.  One work item = 2048 consecutive columns of one row.
+constexpr int DZS_THREADS = 256;
+constexpr int DZS_SEG = DZS_THREADS * 8;
+
+__device__ __forceinline__ uint4 dz_vec8(const uint4 in, float c1, float coef, float nlse2, int tj) {
+  const uint64_t C1 = ptx::pack2(c1, c1), NL = ptx::pack2(nlse2, nlse2), NC = ptx::pack2(-coef, -coef);
+  const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a0 = __uint_as_float(w[k] << 16), a1 = __uint_as_float(w[k] & 0xFFFF0000u);
+    float x0, x1, d0, d1;
+    ptx::unpack2(ptx::fma2(ptx::pack2(a0, a1), C1, NL), x0, x1);
+    ptx::unpack2(ptx::mul2(ptx::pack2(ptx::ex2(x0), ptx::ex2(x1)), NC), d0, d1);
+    if (tj == 2 * k) d0 += coef;
+    if (tj == 2 * k + 1) d1 += coef;
+    o[k] = ptx::cvt_bf16x2(d0, d1);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(DZS_THREADS) dz_from_saved_logits_kernel(__nv_bfloat16* __restrict__ z, int64_t ld, int64_t T, int64_t V,
+                                                                           int shift, const int64_t* __restrict__ ids,
+                                                                           const float* __restrict__ lse, const float* __restrict__ dlogp,
+                                                                           int64_t col_base, float inv_temp) {
+  const int64_t n_seg = (V + DZS_SEG - 1) / DZS_SEG;
+  const int64_t items = T * n_seg;
+  const float c1 = inv_temp * LOG2E;
+  const int64_t v8 = (V + 7) / 8 * 8;  // whole 16-byte vectors; columns in [V, v8) are padding of the caller's row pitch
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t row = item / n_seg;
+    const int64_t col = (item - row * n_seg) * DZS_SEG + (int64_t)threadIdx.x * 8;
+    if (col >= v8) continue;
+    uint4* ptr = reinterpret_cast<uint4*>(z + row * ld + col);
+    const int64_t t = row + shift;
+    if (t >= T) {  // no target for this source row (the last row of a shifted packed row): zero gradient
+      __stcs(ptr, make_uint4(0u, 0u, 0u, 0u));
+      continue;
+    }
+    const uint4 in = __ldcs(ptr);
+    const float coef = dlogp[t] * inv_temp;
+    const float nlse2 = -lse[t] * LOG2E;
+    const int64_t tj64 = ids[t] - col_base - col;
+    const int tj = (tj64 >= 0 && tj64 < 8) ? (int)tj64 : -1;
+    __stcs(ptr, dz_vec8(in, c1, coef, nlse2, tj));
+  }
+}
+
 static int launch_merge(const float4* parts, int nparts, int64_t stride, int64_t T, int shift, float v_shard, float* logp, float* entropy,
                         float* lse, float4* merged, cudaStream_t st) {
   if (T <= 0) return PRL_OK;
@@ -313,9 +363,12 @@ size_t prl_lmhead_fwd_workspace_bytes(int64_t T, int32_t H, int64_t V) {
   return (size_t)MAX_SPLITS * (size_t)round_up(T > 0 ? T : 1, BLOCK_M) * sizeof(float4) + 256;
 }
 
-int prl_lmhead_fwd(const void* hidden, const void* weight, const int64_t* ids, int64_t T, int32_t H, int64_t V, int64_t v_offset,
-                   int64_t V_total, float inv_temp, int32_t shift, int32_t round_bf16, float* logp, float* entropy, float* lse,
-                   float* partials, void* workspace, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+// forward; `saved` != nullptr additionally keeps the bf16 logits ([T - shift rows][saved_ld]) for prl_lmhead_bwd_saved
+static int lmhead_fwd_impl(const void* hidden, const void* weight, const int64_t* ids, int64_t T, int32_t H, int64_t V, int64_t v_offset,
+                           int64_t V_total, float inv_temp, int32_t shift, int32_t round_bf16, float* logp, float* entropy, float* lse,
+                           float* partials, void* saved, int64_t saved_ld, void* workspace, size_t workspace_bytes, void* stream) {
   PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_fwd: bad sizes");
   PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_fwd: shift must be 0 or 1");
   PRL_REQUIRE(inv_temp > 0.f && inv_temp < INFINITY, PRL_ERR_BAD_ARG, "lmhead_fwd: temperature must be positive and finite");
@@ -353,12 +406,45 @@ int prl_lmhead_fwd(const void* hidden, const void* weight, const int64_t* ids, i
     // reads, 5 stages 11.6 GB, 4 stages 6.7 GB (3 stages starve the MMAs); sustained under the power cap 5 stages is fastest
     // (+4..6 % over 7).  The hidden band is marked evict-last.
     p.max_stages = (int)env_long("PRL_FWD_STAGES", 5);
-    set_hints(p, "FWD", 2, 0, 0);
-    rc = launch_gemm<false, false, EPI_STATS>(p, st, "lmhead_fwd_kernel");
+    if (saved) {
+      p.epi.dz = reinterpret_cast<__nv_bfloat16*>(saved);
+      p.epi.ldz = saved_ld;
+      if (epi_tma_enabled()) {
+        rc = make_output_map(&p.tma_c, saved, rows, V, saved_ld, false);
+        if (rc) return rc;
+        p.epi.flags = ST_TMA;
+      }
+      set_hints(p, "FWDS", 2, 0, 1);  // the kept logits are not read again before the backward: evict first
+      rc = launch_gemm<false, false, EPI_STATS_STORE>(p, st, "lmhead_fwd_save_kernel");
+    } else {
+      set_hints(p, "FWD", 2, 0, 0);
+      rc = launch_gemm<false, false, EPI_STATS>(p, st, "lmhead_fwd_kernel");
+    }
     if (rc) return rc;
     nparts = p.n_splits;
   }
   return launch_merge(parts, nparts, stride, T, shift, (float)V, logp, entropy, lse, reinterpret_cast<float4*>(partials), st);
+}
+
+extern "C" {
+
+int prl_lmhead_fwd(const void* hidden, const void* weight, const int64_t* ids, int64_t T, int32_t H, int64_t V, int64_t v_offset,
+                   int64_t V_total, float inv_temp, int32_t shift, int32_t round_bf16, float* logp, float* entropy, float* lse,
+                   float* partials, void* workspace, size_t workspace_bytes, void* stream) {
+  return lmhead_fwd_impl(hidden, weight, ids, T, H, V, v_offset, V_total, inv_temp, shift, round_bf16, logp, entropy, lse, partials,
+                         nullptr, 0, workspace, workspace_bytes, stream);
+}
+
+int64_t prl_lmhead_saved_logits_ld(int64_t V) { return round_up(V > 0 ? V : 1, 64); }
+
+int prl_lmhead_fwd_save(const void* hidden, const void* weight, const int64_t* ids, int64_t T, int32_t H, int64_t V, int64_t v_offset,
+                        int64_t V_total, float inv_temp, int32_t shift, float* logp, float* entropy, float* lse, float* partials,
+                        void* saved_logits, int64_t saved_ld, void* workspace, size_t workspace_bytes, void* stream) {
+  PRL_REQUIRE(T == 0 || saved_logits, PRL_ERR_BAD_ARG, "lmhead_fwd_save: null saved_logits");
+  PRL_REQUIRE(saved_ld >= V && saved_ld % 8 == 0, PRL_ERR_BAD_ARG, "lmhead_fwd_save: saved_ld must be >= V and a multiple of 8");
+  PRL_REQUIRE((reinterpret_cast<uintptr_t>(saved_logits) & 15) == 0, PRL_ERR_BAD_ARG, "lmhead_fwd_save: saved_logits must be 16-byte aligned");
+  return lmhead_fwd_impl(hidden, weight, ids, T, H, V, v_offset, V_total, inv_temp, shift, 1, logp, entropy, lse, partials, saved_logits,
+                         saved_ld, workspace, workspace_bytes, stream);
 }
 
 int prl_lmhead_merge_partials(const float* partials, int32_t nparts, int64_t T, float* logp, float* entropy, float* lse, void* stream) {
@@ -368,6 +454,102 @@ int prl_lmhead_merge_partials(const float* partials, int32_t nparts, int64_t T, 
   PRL_REQUIRE((reinterpret_cast<uintptr_t>(partials) & 15) == 0, PRL_ERR_BAD_ARG, "merge_partials: partials must be 16-byte aligned");
   return launch_merge(reinterpret_cast<const float4*>(partials), nparts, T, T, 0, 0.f, logp, entropy, lse, nullptr, (cudaStream_t)stream);
 }
+
+}  // extern "C"
+
+// d_hidden and d_weight GEMMs over one block of dlogits: dz[T][ldz] holds vocab columns [c0, c0 + vce) of this shard
+static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __nv_bfloat16* dz, int64_t vc, int64_t c0, int64_t vce,
+                            int64_t T, int32_t H, void* d_hidden, int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype,
+                            int32_t accumulate_dw, int32_t phase_mask, bool first, bool last, int64_t nchunks, float* dh_acc,
+                            cudaStream_t st) {
+  // ---- K2: d_hidden[T,H] += dz[T,vce] x W[c0:c0+vce, :]   (A K-major, B MN-major) ----
+  if (d_hidden && (phase_mask & 2)) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = make_operand_map(&p.tma_a, dz, false, T, vce, vc, BLOCK_M);
+    if (rc) return rc;
+    rc = make_operand_map(&p.tma_b, W + c0 * H, true, H, vce, H, BLOCK_N);
+    if (rc) return rc;
+    set_tiling(p, T, H, vce, EPI_STORE);
+    schedule_tiles(p);
+    make_desc_defaults(p, false, true);
+    p.epi.m_rows = T;
+    p.epi.n_cols = H;
+    p.epi.ldc = H;
+    const bool tma = epi_tma_enabled();
+    if (d_hidden_f32) {
+      p.epi.c_f32 = reinterpret_cast<float*>(d_hidden);
+      p.epi.flags = ST_STORE_F32 | (first ? 0 : ST_LOAD_F32);
+      if (tma) {
+        rc = make_output_map(&p.tma_c, d_hidden, T, H, H, true);
+        p.epi.flags |= ST_TMA;
+      }
+    } else if (tma && nchunks == 1) {
+      p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_hidden);
+      p.epi.flags = ST_STORE_BF16 | ST_TMA;
+      rc = make_output_map(&p.tma_c, d_hidden, T, H, H, false);
+    } else if (tma) {
+      // fp32 accumulator in the workspace: TMA store for the first vocab chunk, TMA reduce-add (performed in L2, no
+      // SM-side read) for the others; one conversion pass to bf16 after the last chunk
+      p.epi.c_f32 = dh_acc;
+      p.epi.flags = ST_STORE_F32 | (first ? 0 : ST_LOAD_F32) | ST_TMA;
+      rc = make_output_map(&p.tma_c, dh_acc, T, H, H, true);
+    } else {
+      p.epi.c_f32 = dh_acc;
+      p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_hidden);
+      p.epi.flags = (first ? 0 : ST_LOAD_F32) | (last ? ST_STORE_BF16 : ST_STORE_F32);
+    }
+    if (rc) return rc;
+    set_hints(p, "DH", 0, 0, 0);
+    rc = launch_gemm<false, true, EPI_STORE>(p, st, "lmhead_bwd_dhidden_kernel");
+    if (rc) return rc;
+    if (last && tma && !d_hidden_f32 && nchunks > 1) {
+      const int64_t n = T * (int64_t)H;
+      const int64_t need = (n / 8 + 255) / 256 + 1, cap = (int64_t)sm_count() * 8;
+      f32_to_bf16_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(dh_acc, reinterpret_cast<__nv_bfloat16*>(d_hidden), n);
+      rc = check_launch("f32_to_bf16_kernel");
+      if (rc) return rc;
+    }
+  }
+  // ---- K3: d_weight[c0:c0+vce, H] (+)= dz^T x hidden   (both MN-major) ----
+  if (d_weight && (phase_mask & 4)) {
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = make_operand_map(&p.tma_a, dz, true, vce, T, vc, BLOCK_M);
+    if (rc) return rc;
+    rc = make_operand_map(&p.tma_b, hidden, true, H, T, H, BLOCK_N);
+    if (rc) return rc;
+    set_tiling(p, vce, H, T, EPI_STORE);
+    schedule_tiles(p);
+    make_desc_defaults(p, true, true);
+    p.epi.m_rows = vce;
+    p.epi.n_cols = H;
+    p.epi.ldc = H;
+    if (d_weight_dtype == PRL_DT_F32) {
+      p.epi.c_f32 = reinterpret_cast<float*>(d_weight) + c0 * H;
+      p.epi.flags = ST_STORE_F32 | (accumulate_dw ? ST_LOAD_F32 : 0);
+      if (epi_tma_enabled()) {
+        rc = make_output_map(&p.tma_c, p.epi.c_f32, vce, H, H, true);
+        if (rc) return rc;
+        p.epi.flags |= ST_TMA;
+      }
+    } else {
+      p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_weight) + c0 * H;
+      p.epi.flags = ST_STORE_BF16 | (accumulate_dw ? ST_LOAD_BF16 : 0);
+      if (epi_tma_enabled() && !accumulate_dw) {
+        rc = make_output_map(&p.tma_c, p.epi.c_bf16, vce, H, H, false);
+        if (rc) return rc;
+        p.epi.flags |= ST_TMA;
+      }
+    }
+    set_hints(p, "DW", 0, 0, 0);
+    rc = launch_gemm<true, true, EPI_STORE>(p, st, "lmhead_bwd_dweight_kernel");
+    if (rc) return rc;
+  }
+  return PRL_OK;
+}
+
+extern "C" {
 
 static int64_t pick_vchunk(int64_t V, int64_t vchunk) {
   if (vchunk <= 0) vchunk = env_long("PRL_VCHUNK", 16384);
@@ -440,93 +622,40 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
       rc = launch_gemm<false, false, EPI_DZ>(p, st, "lmhead_bwd_dz_kernel");
       if (rc) return rc;
     }
-    // ---- K2: d_hidden[T,H] += dz[T,vce] x W[c0:c0+vce, :]   (A K-major, B MN-major) ----
-    if (d_hidden && (phase_mask & 2)) {
-      GemmParams p;
-      memset(&p, 0, sizeof(p));
-      int rc = make_operand_map(&p.tma_a, dz, false, T, vce, vc, BLOCK_M);
-      if (rc) return rc;
-      rc = make_operand_map(&p.tma_b, W + c0 * H, true, H, vce, H, BLOCK_N);
-      if (rc) return rc;
-      set_tiling(p, T, H, vce, EPI_STORE);
-      schedule_tiles(p);
-      make_desc_defaults(p, false, true);
-      p.epi.m_rows = T;
-      p.epi.n_cols = H;
-      p.epi.ldc = H;
-      const bool first = (c == 0), last = (c == nchunks - 1);
-      const bool tma = epi_tma_enabled();
-      if (d_hidden_f32) {
-        p.epi.c_f32 = reinterpret_cast<float*>(d_hidden);
-        p.epi.flags = ST_STORE_F32 | (first ? 0 : ST_LOAD_F32);
-        if (tma) {
-          rc = make_output_map(&p.tma_c, d_hidden, T, H, H, true);
-          p.epi.flags |= ST_TMA;
-        }
-      } else if (tma && nchunks == 1) {
-        p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_hidden);
-        p.epi.flags = ST_STORE_BF16 | ST_TMA;
-        rc = make_output_map(&p.tma_c, d_hidden, T, H, H, false);
-      } else if (tma) {
-        // fp32 accumulator in the workspace: TMA store for the first vocab chunk, TMA reduce-add (performed in L2, no
-        // SM-side read) for the others; one conversion pass to bf16 after the last chunk
-        p.epi.c_f32 = dh_acc;
-        p.epi.flags = ST_STORE_F32 | (first ? 0 : ST_LOAD_F32) | ST_TMA;
-        rc = make_output_map(&p.tma_c, dh_acc, T, H, H, true);
-      } else {
-        p.epi.c_f32 = dh_acc;
-        p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_hidden);
-        p.epi.flags = (first ? 0 : ST_LOAD_F32) | (last ? ST_STORE_BF16 : ST_STORE_F32);
-      }
-      if (rc) return rc;
-      set_hints(p, "DH", 0, 0, 0);
-      rc = launch_gemm<false, true, EPI_STORE>(p, st, "lmhead_bwd_dhidden_kernel");
-      if (rc) return rc;
-      if (last && tma && !d_hidden_f32 && nchunks > 1) {
-        const int64_t n = T * (int64_t)H;
-        const int64_t need = (n / 8 + 255) / 256 + 1, cap = (int64_t)sm_count() * 8;
-        f32_to_bf16_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(dh_acc, reinterpret_cast<__nv_bfloat16*>(d_hidden), n);
-        rc = check_launch("f32_to_bf16_kernel");
-        if (rc) return rc;
-      }
-    }
-    // ---- K3: d_weight[c0:c0+vce, H] (+)= dz^T x hidden   (both MN-major) ----
-    if (d_weight && (phase_mask & 4)) {
-      GemmParams p;
-      memset(&p, 0, sizeof(p));
-      int rc = make_operand_map(&p.tma_a, dz, true, vce, T, vc, BLOCK_M);
-      if (rc) return rc;
-      rc = make_operand_map(&p.tma_b, hidden, true, H, T, H, BLOCK_N);
-      if (rc) return rc;
-      set_tiling(p, vce, H, T, EPI_STORE);
-      schedule_tiles(p);
-      make_desc_defaults(p, true, true);
-      p.epi.m_rows = vce;
-      p.epi.n_cols = H;
-      p.epi.ldc = H;
-      if (d_weight_dtype == PRL_DT_F32) {
-        p.epi.c_f32 = reinterpret_cast<float*>(d_weight) + c0 * H;
-        p.epi.flags = ST_STORE_F32 | (accumulate_dw ? ST_LOAD_F32 : 0);
-        if (epi_tma_enabled()) {
-          rc = make_output_map(&p.tma_c, p.epi.c_f32, vce, H, H, true);
-          if (rc) return rc;
-          p.epi.flags |= ST_TMA;
-        }
-      } else {
-        p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_weight) + c0 * H;
-        p.epi.flags = ST_STORE_BF16 | (accumulate_dw ? ST_LOAD_BF16 : 0);
-        if (epi_tma_enabled() && !accumulate_dw) {
-          rc = make_output_map(&p.tma_c, p.epi.c_bf16, vce, H, H, false);
-          if (rc) return rc;
-          p.epi.flags |= ST_TMA;
-        }
-      }
-      set_hints(p, "DW", 0, 0, 0);
-      rc = launch_gemm<true, true, EPI_STORE>(p, st, "lmhead_bwd_dweight_kernel");
+    {
+      const int rc = lmhead_bwd_gemms(hidden, W, dz, vc, c0, vce, T, H, d_hidden, d_hidden_f32, d_weight, d_weight_dtype, accumulate_dw,
+                                      phase_mask, c == 0, c == nchunks - 1, nchunks, dh_acc, st);
       if (rc) return rc;
     }
   }
   return PRL_OK;
+}
+
+int prl_lmhead_bwd_saved(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T,
+                         int32_t H, int64_t V, int64_t v_offset, float inv_temp, int32_t shift, void* saved_logits, int64_t saved_ld,
+                         void* d_hidden, int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw,
+                         int32_t phase_mask, void* stream) {
+  PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: bad sizes");
+  PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: shift must be 0 or 1");
+  PRL_REQUIRE(inv_temp > 0.f && inv_temp < INFINITY, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: temperature must be positive and finite");
+  PRL_REQUIRE(d_weight_dtype == PRL_DT_BF16 || d_weight_dtype == PRL_DT_F32, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: bad d_weight dtype");
+  PRL_REQUIRE(saved_ld >= V && saved_ld % 8 == 0, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: saved_ld must be >= V and a multiple of 8");
+  if (T == 0) return PRL_OK;
+  PRL_REQUIRE(hidden && weight && ids && lse && dlogp && saved_logits, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: null pointer");
+  PRL_REQUIRE((reinterpret_cast<uintptr_t>(saved_logits) & 15) == 0, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: saved_logits must be 16-byte aligned");
+  PRL_REQUIRE(H % 8 == 0, PRL_ERR_UNSUPPORTED, "lmhead_bwd_saved: H must be a multiple of 8 (16-byte TMA row pitch)");
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(saved_logits);
+  if ((phase_mask & 7) == 0) phase_mask = 7;
+  if (phase_mask & 1) {
+    const int64_t items = T * ((V + DZS_SEG - 1) / DZS_SEG), cap = (int64_t)sm_count() * 16;
+    dz_from_saved_logits_kernel<<<(int)(items < cap ? items : cap), DZS_THREADS, 0, st>>>(dz, saved_ld, T, V, shift, ids, lse, dlogp, v_offset,
+                                                                                         inv_temp);
+    const int rc = check_launch("dz_from_saved_logits_kernel");
+    if (rc) return rc;
+  }
+  return lmhead_bwd_gemms(hidden, reinterpret_cast<const __nv_bfloat16*>(weight), dz, saved_ld, 0, V, T, H, d_hidden, d_hidden_f32, d_weight,
+                          d_weight_dtype, accumulate_dw, phase_mask, true, true, 1, nullptr, st);
 }
 
 int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn_major, int32_t b_mn_major,

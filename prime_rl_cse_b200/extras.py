@@ -33,7 +33,7 @@ def fused_linear_cross_entropy(hidden: torch.Tensor, weight: torch.Tensor, targe
     """SFT loss of the reference (sft/train.py:209-216): `cross_entropy(lm_head(hidden), target_ids,
     reduction="none")[loss_mask].mean()` — targets are already shifted there, there is no temperature and no
     `shift_logits`.  hidden [..., T, H] bf16, weight [V, H] bf16, target_ids / loss_mask [..., T].  Differentiable w.r.t.
-    hidden and weight through the recompute-based backward; the [T, V] logits are never materialised."""
+    hidden and weight; the fp32 [T, V] logits are never materialised (one bf16 copy is kept for the backward when it fits)."""
     _lib.require_cuda(hidden, weight, target_ids, loss_mask)
     if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise ValueError("fused_linear_cross_entropy needs bf16 hidden and weight")

@@ -1,8 +1,16 @@
 """Fused LM head: hidden x W_lm^T -> (log-prob of the sampled token, entropy) without materialising
-the [T, V] logits, with a recompute-based backward.  Replaces rl/train.py:285-288,302-303 of the
-reference (src/prime_rl/trainer/rl/train.py) and the autograd chain behind `loss.backward()` (:310)."""
+the fp32 [T, V] logits.  Replaces rl/train.py:285-288,302-303 of the reference
+(src/prime_rl/trainer/rl/train.py) and the autograd chain behind `loss.backward()` (:310).
+
+Two backward modes, same results:
+  * saved logits (default when the block fits, see `saved_logits_policy`): the forward keeps ONE bf16 copy of
+    the logits (T x V x 2 bytes, 5 GB for a 16384-token micro-batch of Qwen3; the reference keeps the fp32
+    logits plus their gradient), the backward rewrites it in place into dlogits and runs two GEMMs;
+  * recompute: nothing but lse[T] is kept, the backward recomputes the logits per vocab chunk (one more GEMM)."""
 
 from __future__ import annotations
+
+import os
 
 import torch
 from torch import nn
@@ -35,6 +43,90 @@ def lm_head_forward_raw(hidden, weight, ids, inv_temp, shift=True, round_bf16=Tr
     return logp, ent, lse, parts
 
 
+def saved_logits_policy(T: int, V: int, override: bool | None = None) -> bool:
+    """Whether the forward keeps the bf16 logits for the backward.  `override` wins; else the environment variable
+    PRL_SAVE_LOGITS = 0 | 1 | auto (default); `auto` keeps them when the block is at most PRL_SAVE_LOGITS_MAX_GIB
+    (default 12 GiB: a 32768-token packed row at V = 151936 is 9.3 GiB)."""
+    if override is not None:
+        return bool(override)
+    env = os.environ.get("PRL_SAVE_LOGITS", "auto").strip().lower()
+    if env in ("0", "off", "false", "no"):
+        return False
+    if env in ("1", "on", "true", "yes"):
+        return True
+    limit = float(os.environ.get("PRL_SAVE_LOGITS_MAX_GIB", "12")) * 2**30
+    return 0 < T * saved_logits_ld(V) * 2 <= limit
+
+
+def saved_logits_ld(V: int) -> int:
+    """Row pitch (elements) of the saved-logits block (prl_lmhead_saved_logits_ld)."""
+    return int(_lib.load().prl_lmhead_saved_logits_ld(int(V)))
+
+
+def lm_head_forward_save_raw(hidden, weight, ids, inv_temp, shift=True, v_offset=0, v_total=None, want_partials=False,
+                             workspace=None, saved=None):
+    """`lm_head_forward_raw` (bf16-rounded logits) that also keeps the logits: returns (logp, entropy, lse,
+    partials|None, saved [T, ld] bf16).  `saved` may be a preallocated [T, ld] bf16 block, ld = saved_logits_ld(V)."""
+    lib = _lib.load()
+    T, H = hidden.shape
+    V = weight.shape[0]
+    v_total = V if v_total is None else v_total
+    dev = hidden.device
+    ld = saved_logits_ld(V)
+    if saved is None:
+        saved = torch.empty(T, ld, dtype=torch.bfloat16, device=dev)
+    elif saved.dtype != torch.bfloat16 or saved.dim() != 2 or saved.shape[0] < T or saved.shape[1] < V or not saved.is_contiguous():
+        raise ValueError("saved logits block must be a contiguous bf16 [>= T, >= V] tensor")
+    logp = torch.empty(T, dtype=torch.float32, device=dev)
+    ent = torch.empty(T, dtype=torch.float32, device=dev)
+    lse = torch.empty(T, dtype=torch.float32, device=dev)
+    parts = torch.empty(T, 4, dtype=torch.float32, device=dev) if want_partials else None
+    nb = lib.prl_lmhead_fwd_workspace_bytes(T, H, V)
+    ws = workspace if workspace is not None and workspace.numel() >= nb else _ws(nb, dev)
+    rc = lib.prl_lmhead_fwd_save(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), T, H, V, v_offset, v_total, float(inv_temp),
+                                 1 if shift else 0, _lib.ptr(logp), _lib.ptr(ent), _lib.ptr(lse), _lib.ptr(parts),
+                                 _lib.ptr(saved), saved.shape[1], _lib.ptr(ws), ws.numel(), _lib.stream())
+    _lib.check(rc, "prl_lmhead_fwd_save")
+    return logp, ent, lse, parts, saved
+
+
+def _dweight_arg(dweight, want_dweight, dweight_accumulate, V, H, dev):
+    if want_dweight and dweight is None:
+        dweight = torch.empty(V, H, dtype=torch.bfloat16, device=dev)
+        dweight_accumulate = False
+    dt = _lib.PRL_DT_BF16
+    if dweight is not None:
+        if dweight.dtype == torch.float32:
+            dt = _lib.PRL_DT_F32
+        elif dweight.dtype != torch.bfloat16:
+            raise ValueError("d_weight must be bf16 or fp32")
+        if tuple(dweight.shape) != (V, H) or not dweight.is_contiguous():
+            raise ValueError("d_weight must be a contiguous [V, H] tensor")
+    return dweight, dt, dweight_accumulate
+
+
+def lm_head_backward_saved_raw(hidden, weight, ids, lse, dlogp, inv_temp, saved, shift=True, v_offset=0, want_dhidden=True,
+                               dweight=None, dweight_accumulate=False, want_dweight=True, dhidden_f32=False, phase_mask=0):
+    """Backward from the logits kept by `lm_head_forward_save_raw`.  `saved` is overwritten (it holds the bf16 dlogits
+    afterwards).  Returns (d_hidden, d_weight) like `lm_head_backward_raw`."""
+    lib = _lib.load()
+    T, H = hidden.shape
+    V = weight.shape[0]
+    dev = hidden.device
+    if saved.dtype != torch.bfloat16 or saved.dim() != 2 or saved.shape[0] < T or saved.shape[1] < V or not saved.is_contiguous():
+        raise ValueError("saved logits block must be a contiguous bf16 [>= T, >= V] tensor")
+    dh = None
+    if want_dhidden:
+        dh = torch.empty(T, H, dtype=torch.float32 if dhidden_f32 else torch.bfloat16, device=dev)
+    dweight, dt, dweight_accumulate = _dweight_arg(dweight, want_dweight, dweight_accumulate, V, H, dev)
+    rc = lib.prl_lmhead_bwd_saved(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), _lib.ptr(lse), _lib.ptr(dlogp), T, H, V, v_offset,
+                                  float(inv_temp), 1 if shift else 0, _lib.ptr(saved), saved.shape[1], _lib.ptr(dh),
+                                  1 if dhidden_f32 else 0, _lib.ptr(dweight), dt, 1 if dweight_accumulate else 0, phase_mask,
+                                  _lib.stream())
+    _lib.check(rc, "prl_lmhead_bwd_saved")
+    return dh, dweight
+
+
 def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, round_bf16=True, v_offset=0,
                          want_dhidden=True, dweight=None, dweight_accumulate=False, want_dweight=True, vchunk=0,
                          dhidden_f32=False, phase_mask=0, workspace=None):
@@ -47,17 +139,7 @@ def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, 
     dh = None
     if want_dhidden:
         dh = torch.empty(T, H, dtype=torch.float32 if dhidden_f32 else torch.bfloat16, device=dev)
-    if want_dweight and dweight is None:
-        dweight = torch.empty(V, H, dtype=torch.bfloat16, device=dev)
-        dweight_accumulate = False
-    dt = _lib.PRL_DT_BF16
-    if dweight is not None:
-        if dweight.dtype == torch.float32:
-            dt = _lib.PRL_DT_F32
-        elif dweight.dtype != torch.bfloat16:
-            raise ValueError("d_weight must be bf16 or fp32")
-        if tuple(dweight.shape) != (V, H) or not dweight.is_contiguous():
-            raise ValueError("d_weight must be a contiguous [V, H] tensor")
+    dweight, dt, dweight_accumulate = _dweight_arg(dweight, want_dweight, dweight_accumulate, V, H, dev)
     nb = lib.prl_lmhead_bwd_workspace_bytes(T, H, V, vchunk)
     ws = workspace if workspace is not None and workspace.numel() >= nb else _ws(nb, dev)
     rc = lib.prl_lmhead_bwd(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), _lib.ptr(lse), _lib.ptr(dlogp), T, H, V, v_offset,
@@ -67,14 +149,30 @@ def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, 
     return dh, dweight
 
 
+def _forward_any(h, w, i, inv_temp, shift, round_bf16, save):
+    """(logp, ent, lse, saved|None): saved-logits forward when asked for and possible, else the plain one."""
+    if save and round_bf16 and h.shape[0] > 0:
+        try:
+            logp, ent, lse, _, saved = lm_head_forward_save_raw(h, w, i, inv_temp, shift)
+            return logp, ent, lse, saved
+        except torch.OutOfMemoryError:
+            pass  # no room for the block: recompute mode needs lse only
+    logp, ent, lse, _ = lm_head_forward_raw(h, w, i, inv_temp, shift, round_bf16)
+    return logp, ent, lse, None
+
+
 class _FusedLMHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, hidden, weight, ids, inv_temp, shift, round_bf16, main_grad, active_positions=None, forward_active_only=False):
+    def forward(ctx, hidden, weight, ids, inv_temp, shift, round_bf16, main_grad, active_positions=None, forward_active_only=False,
+                save_logits=None):
         lead = hidden.shape[:-1]
         h2 = hidden.detach().reshape(-1, hidden.shape[-1]).contiguous()
         w2 = weight.detach().contiguous()
         i2 = ids.detach().reshape(-1).contiguous().to(torch.int64)
         ctx.compact = None
+        ctx.saved_logits = None   # bf16 logits kept for the backward (consumed by it)
+        ctx.saved_rows = "all"    # which rows the block covers: "all" source rows or "compact" (the active rows only)
+        needs_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         if active_positions is not None:
             # positions that can receive a gradient; position 0 of a shifted row is a constant (no source row)
             pos = active_positions.reshape(-1).to(torch.int64)
@@ -91,7 +189,9 @@ class _FusedLMHead(torch.autograd.Function):
             lse = torch.zeros(T, dtype=torch.float32, device=h2.device)
             if pos.numel() > 0:
                 h_c, i_c = h2.index_select(0, rows), i2.index_select(0, pos)
-                lp_c, ent_c, lse_c, _ = lm_head_forward_raw(h_c, w2, i_c, inv_temp, False, round_bf16)
+                save = needs_grad and saved_logits_policy(h_c.shape[0], w2.shape[0], save_logits)
+                lp_c, ent_c, lse_c, ctx.saved_logits = _forward_any(h_c, w2, i_c, inv_temp, False, round_bf16, save)
+                ctx.saved_rows = "compact"
                 logp.index_copy_(0, pos, lp_c)
                 ent.index_copy_(0, pos, ent_c)
                 lse.index_copy_(0, pos, lse_c)
@@ -101,7 +201,8 @@ class _FusedLMHead(torch.autograd.Function):
                 ln_v = math.log(float(w2.shape[0]))
                 logp[0], ent[0], lse[0] = -ln_v, ln_v, ln_v
         else:
-            logp, ent, lse, _ = lm_head_forward_raw(h2, w2, i2, inv_temp, shift, round_bf16)
+            save = needs_grad and saved_logits_policy(h2.shape[0], w2.shape[0], save_logits)
+            logp, ent, lse, ctx.saved_logits = _forward_any(h2, w2, i2, inv_temp, shift, round_bf16, save)
         ctx.save_for_backward(h2, w2, i2, lse)
         ctx.cfg = (inv_temp, shift, round_bf16, hidden.shape, main_grad)
         logp, ent = logp.reshape(lead), ent.reshape(lead)
@@ -114,19 +215,31 @@ class _FusedLMHead(torch.autograd.Function):
         inv_temp, shift, round_bf16, hshape, main_grad = ctx.cfg
         g = g_logp.detach().reshape(-1).contiguous().float()
         need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        none_tail = (None,) * 7
+        none_tail = (None,) * 8
+        # the kept logits are consumed by the first backward; a second one (retain_graph) falls back to the recompute
+        saved, ctx.saved_logits = ctx.saved_logits, None
+        dw_target = main_grad if (main_grad is not None and need_w) else None
+
+        def run(h, i, l, gg, sh, block):
+            kw = dict(want_dhidden=need_h, dweight=dw_target, dweight_accumulate=dw_target is not None, want_dweight=need_w)
+            if block is not None:
+                return lm_head_backward_saved_raw(h, w2, i, l, gg, inv_temp, block, sh, **kw)
+            return lm_head_backward_raw(h, w2, i, l, gg, inv_temp, sh, round_bf16, **kw)
+
         if ctx.compact is not None:
-            # Only positions with a non-zero d loss / d logp contribute to d_hidden and d_W: run the recompute backward on
-            # the compacted rows (exactly the same sums, minus the all-zero terms) and scatter d_hidden back.
+            # Only positions with a non-zero d loss / d logp contribute to d_hidden and d_W: run the backward on the
+            # compacted rows (exactly the same sums, minus the all-zero terms) and scatter d_hidden back.
             pos, rows = ctx.compact
-            dw_target = main_grad if (main_grad is not None and need_w) else None
             dh = torch.zeros(h2.shape, dtype=torch.bfloat16, device=h2.device) if need_h else None
             dw = None
             if pos.numel() > 0:
-                dh_c, dw = lm_head_backward_raw(h2.index_select(0, rows), w2, i2.index_select(0, pos), lse.index_select(0, pos),
-                                                g.index_select(0, pos), inv_temp, False, round_bf16, want_dhidden=need_h,
-                                                dweight=dw_target, dweight_accumulate=dw_target is not None,
-                                                want_dweight=need_w)
+                if saved is not None and ctx.saved_rows == "all":
+                    block = saved[: h2.shape[0]].index_select(0, rows)  # logits of the active rows
+                    del saved
+                else:
+                    block = saved
+                dh_c, dw = run(h2.index_select(0, rows), i2.index_select(0, pos), lse.index_select(0, pos), g.index_select(0, pos),
+                               False, block)
                 if need_h:
                     dh.index_copy_(0, rows, dh_c)
             elif need_w and dw_target is None:
@@ -134,13 +247,9 @@ class _FusedLMHead(torch.autograd.Function):
             if dw_target is not None:
                 dw = None
             return ((dh.reshape(hshape) if dh is not None else None), dw) + none_tail
-        if main_grad is not None and need_w:
-            dh, _ = lm_head_backward_raw(h2, w2, i2, lse, g, inv_temp, shift, round_bf16, want_dhidden=need_h,
-                                         dweight=main_grad, dweight_accumulate=True)
+        dh, dw = run(h2, i2, lse, g, shift, saved)
+        if dw_target is not None:
             dw = None
-        else:
-            dh, dw = lm_head_backward_raw(h2, w2, i2, lse, g, inv_temp, shift, round_bf16, want_dhidden=need_h,
-                                          want_dweight=need_w)
         return ((dh.reshape(hshape) if dh is not None else None), dw) + none_tail
 
 
@@ -155,6 +264,7 @@ def fused_lm_head_logprobs_entropy(
     main_grad: torch.Tensor | None = None,
     active_positions: torch.Tensor | None = None,
     forward_active_only: bool = False,
+    save_logits: bool | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """hidden [..., T, H] bf16 (final-norm output), weight [V, H] bf16 (`lm_head.weight`), input_ids
     [..., T] -> (logprobs [..., T] fp32, differentiable w.r.t. hidden and weight; entropy [..., T] fp32,
@@ -168,7 +278,10 @@ def fused_lm_head_logprobs_entropy(
     `active_positions`: optional int64 index tensor of the positions that can receive a non-zero gradient (e.g.
     `loss_mask.nonzero()`): the backward then skips every other row (prompt / environment tokens) — identical gradients,
     proportionally less recompute.  By default the forward still covers all T positions, as the reference does; with
-    `forward_active_only=True` it visits the active positions only and returns 0 for log-prob and entropy elsewhere."""
+    `forward_active_only=True` it visits the active positions only and returns 0 for log-prob and entropy elsewhere.
+    `save_logits`: True keeps one bf16 copy of the logits (T x V x 2 bytes) between forward and backward so that the backward
+    needs two GEMMs instead of three; False recomputes; None (default) decides by size (`saved_logits_policy`).  Both give the
+    same gradients (same bf16 dlogits)."""
     _lib.require_cuda(hidden, weight, input_ids)
     if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise ValueError("fused_lm_head_logprobs_entropy needs bf16 hidden and weight (FSDP param_dtype=bf16, model.py:103)")
@@ -179,7 +292,7 @@ def fused_lm_head_logprobs_entropy(
     if hidden.dim() > 2 and hidden.shape[:-2].numel() != 1:
         raise ValueError("only one packed row per call (micro_batch_size == 1 for packed batches)")
     return _FusedLMHead.apply(hidden, weight, input_ids, 1.0 / float(temperature), bool(shift), bool(round_bf16), main_grad,
-                              active_positions, bool(forward_active_only))
+                              active_positions, bool(forward_active_only), save_logits)
 
 
 class FusedLMHead(nn.Module):
@@ -188,10 +301,11 @@ class FusedLMHead(nn.Module):
     `forward(hidden)` returns a `[..., T, 2]` tensor (logprob, entropy) where the reference returns
     logits.  Call `set_context(input_ids, temperature)` right before the model forward."""
 
-    def __init__(self, weight: nn.Parameter, main_grad: torch.Tensor | None = None):
+    def __init__(self, weight: nn.Parameter, main_grad: torch.Tensor | None = None, save_logits: bool | None = None):
         super().__init__()
         self.weight = weight
         self.main_grad = main_grad
+        self.save_logits = save_logits  # None: by size (saved_logits_policy)
         self._ctx: tuple[torch.Tensor, float] | None = None
 
     @classmethod
@@ -208,5 +322,6 @@ class FusedLMHead(nn.Module):
             raise RuntimeError("FusedLMHead.set_context(input_ids, temperature) must be called before forward")
         ids, temp = self._ctx
         self._ctx = None
-        logp, ent = fused_lm_head_logprobs_entropy(hidden, self.weight, ids, temp, main_grad=self.main_grad)
+        logp, ent = fused_lm_head_logprobs_entropy(hidden, self.weight, ids, temp, main_grad=self.main_grad,
+                                                   save_logits=self.save_logits)
         return torch.stack([logp, ent], dim=-1)

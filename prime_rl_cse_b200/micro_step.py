@@ -25,6 +25,7 @@ def rl_micro_step(
     response_lengths: list[int] | None = None,
     skip_masked: bool = True,
     forward_skips_masked: bool = False,
+    save_logits: bool | None = None,
 ) -> dict[str, torch.Tensor]:
     """`hidden` [1,T,H] bf16 is what the transformer body hands to `lm_head` (requires_grad as the
     caller wishes); `micro_batch` is a `MicroBatch` (rl/data.py:13-23) whose tensors are already on the
@@ -33,7 +34,8 @@ def rl_micro_step(
     `loss_mask == False` get a zero gradient (loss.py:104), so the recompute backward only visits the unmasked positions;
     skipped automatically when every token is unmasked.  `forward_skips_masked` (opt-in) also restricts the FORWARD to the
     unmasked positions: log-probs / entropy come back as 0 at masked positions (the reference computes values there that
-    nothing reads: the loss multiplies by the mask and the trainer logs `[loss_mask]` slices, train.py:313-333)."""
+    nothing reads: the loss multiplies by the mask and the trainer logs `[loss_mask]` slices, train.py:313-333).
+    `save_logits`: see `fused_lm_head_logprobs_entropy` (None = keep the bf16 logits for the backward when they fit)."""
     input_ids = micro_batch["input_ids"]
     position_ids = micro_batch["position_ids"]
     advantages = micro_batch["advantages"]
@@ -53,7 +55,8 @@ def rl_micro_step(
 
     # train.py:285-288 + 302-303
     logprobs, entropy = fused_lm_head_logprobs_entropy(hidden, lm_head_weight, input_ids, temperature, main_grad=main_grad,
-                                                       active_positions=active, forward_active_only=forward_skips_masked)
+                                                       active_positions=active, forward_active_only=forward_skips_masked,
+                                                       save_logits=save_logits)
 
     # train.py:292-299
     loss, loss_tensors = compute_loss(

@@ -295,13 +295,14 @@ def test_lmhead_fixtures_from_reference(P):
         assert rel_l2(weight.grad.float().cpu().numpy(), d[f"{key}/d_weight"]) < 1e-2, key
 
 
+@pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
 @pytest.mark.parametrize("T,H,V,tau,mode,vchunk", [
     (48, 32, 160, 1.0, "token", 0),
     (300, 256, 5000, 0.6, "token", 1024),
     (640, 512, 20000, 1.0, "sequence", 8192),
     (200, 1024, 151936, 0.6, "token", 0),
 ])
-def test_micro_step_vs_oracle(P, T, H, V, tau, mode, vchunk):
+def test_micro_step_vs_oracle(P, T, H, V, tau, mode, vchunk, save):
     os.environ["PRL_VCHUNK"] = str(vchunk) if vchunk else "8192"
     try:
         hidden, weight, ids = _mk(T, H, V, T + H, peaked=True)
@@ -321,7 +322,7 @@ def test_micro_step_vs_oracle(P, T, H, V, tau, mode, vchunk):
         w = weight.cuda().requires_grad_(True)
         mb = dict(input_ids=ids.cuda().unsqueeze(0), position_ids=cu(pos).unsqueeze(0), advantages=cu(adv).unsqueeze(0),
                   logprobs=cu(old).unsqueeze(0), loss_mask=cu(mask).unsqueeze(0), temperature=tau)
-        out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(mode, mode == "sequence", 8.0), scale)
+        out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(mode, mode == "sequence", 8.0), scale, save_logits=save)
         dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
         assert np.mean(dl < 1e-3) >= 0.99 and dl.max() < 0.07, (dl.max(), np.mean(dl < 1e-3))
         assert np.abs(out["entropy"][0].cpu().numpy() - want["entropy"]).max() < 2e-3
@@ -437,8 +438,9 @@ def test_next_row_on_device_logging_stats(P):
     assert got["all/count"] == 1000 + 16384 + 77 and st.compute_stats() == {}
 
 
+@pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
 @pytest.mark.parametrize("T,H,V", [(1, 64, 512), (2, 8, 8), (3, 64, 255), (127, 72, 1000), (129, 200, 257), (513, 136, 4104)])
-def test_micro_step_edge_shapes(P, T, H, V):
+def test_micro_step_edge_shapes(P, T, H, V, save):
     """Ragged / tiny shapes: T = 1 (only shift_logits' zero row), V and H that are not multiples of the tile sizes
     (H % 8 == 0 is the only requirement: 16-byte TMA row pitch), single-token segments."""
     hidden, weight, ids = _mk(T, H, V, 1000 + T)
@@ -456,7 +458,7 @@ def test_micro_step_edge_shapes(P, T, H, V):
     w = weight.cuda().requires_grad_(True)
     mb = dict(input_ids=ids.cuda().unsqueeze(0), position_ids=cu(pos).unsqueeze(0), advantages=cu(adv).unsqueeze(0),
               logprobs=cu(old).unsqueeze(0), loss_mask=cu(mask).unsqueeze(0), temperature=tau)
-    out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), T, response_lengths=want["lengths"])
+    out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), T, response_lengths=want["lengths"], save_logits=save)
     dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
     assert dl.max() < 0.07 and np.mean(dl < 1e-3) >= 0.97
     np.testing.assert_allclose(out["loss"].item(), want["loss"], rtol=2e-2, atol=1e-5)
@@ -509,6 +511,80 @@ def test_backward_output_modes(P):
     assert none_w is None and rel(dh_only, dh_ref) < 5e-3
 
 
+@pytest.mark.parametrize("T,H,V,shift", [(129, 64, 1003, True), (700, 256, 20000 + 64, True), (384, 128, 4096, False), (1, 64, 300, True)])
+def test_saved_logits_mode_is_the_recompute_mode_bit_for_bit(P, T, H, V, shift):
+    """Saved-logits pair (prl_lmhead_fwd_save / prl_lmhead_bwd_saved): the forward statistics are bit-identical to the plain
+    forward, the kept block holds the bf16 logits, the in-place logits -> dlogits pass reproduces the recompute epilogue's
+    dlogits bit for bit, and (single vocab chunk: same K order) so do d_hidden / d_weight."""
+    from prime_rl_cse_b200 import (lm_head_backward_raw, lm_head_backward_saved_raw, lm_head_forward_raw, lm_head_forward_save_raw)
+    from prime_rl_cse_b200 import _lib
+
+    tau = 0.8
+    hidden, weight, ids = _mk(T, H, V, 7 * T + V, peaked=True)
+    h, w, i = hidden.cuda(), weight.cuda(), ids.cuda()
+    g = torch.randn(T, device="cuda") / T
+    lp0, ent0, lse0, _ = lm_head_forward_raw(h, w, i, 1 / tau, shift=shift)
+    lp1, ent1, lse1, _, saved = lm_head_forward_save_raw(h, w, i, 1 / tau, shift=shift)
+    assert torch.equal(lp0, lp1) and torch.equal(ent0, ent1) and torch.equal(lse0, lse1)
+    rows = T - int(shift)
+    assert saved.shape[0] >= T and saved.shape[1] >= V and saved.shape[1] % 8 == 0
+    want_logits = (h[:rows].float() @ w.float().t())
+    got = saved[:rows, :V].float()
+    ulp = 2.0 ** -7 * want_logits.abs() + 1e-4  # one bf16 ulp is at most 2^-7 relative; + fp32 accumulation-order noise
+    assert bool(((got - want_logits).abs() <= ulp).all())  # = a correctly rounded bf16 of some fp32 accumulation order
+    # recompute mode, dlogits only (phase 1), single vocab chunk: its workspace starts with the [T_pad, vc] bf16 dlogits block
+    lib = _lib.load()
+    vc = (V + 255) // 256 * 256
+    ws = torch.zeros(lib.prl_lmhead_bwd_workspace_bytes(T, H, V, vc), dtype=torch.uint8, device="cuda")
+    lm_head_backward_raw(h, w, i, lse0, g, 1 / tau, shift=shift, vchunk=vc, phase_mask=1, workspace=ws)
+    dz_re = ws[: ((T + 127) // 128 * 128) * vc * 2].view(torch.bfloat16).view(-1, vc)[:T, :V]
+    blk = saved.clone()
+    lm_head_backward_saved_raw(h, w, i, lse0, g, 1 / tau, blk, shift=shift, phase_mask=1, want_dhidden=False, want_dweight=False)
+    assert torch.equal(blk[:T, :V].float(), dz_re.float())  # float compare: -0.0 == 0.0 for the target-less last row
+    if shift:
+        assert float(blk[T - 1, :V].abs().max()) == 0.0
+    # full backward, both modes
+    dh0, dw0 = lm_head_backward_raw(h, w, i, lse0, g, 1 / tau, shift=shift, vchunk=vc)
+    dh1, dw1 = lm_head_backward_saved_raw(h, w, i, lse0, g, 1 / tau, saved, shift=shift)
+    assert torch.equal(dh0, dh1) and torch.equal(dw0, dw1)
+    # many vocab chunks in the recompute mode: the fp32 partial sums are combined in another order, nothing else changes
+    if V > 512 and T > 1:
+        dh2, dw2 = lm_head_backward_raw(h, w, i, lse0, g, 1 / tau, shift=shift, vchunk=256)
+        assert rel_l2(dh2.float().cpu().numpy(), dh1.float().cpu().numpy()) < 3e-3
+        assert rel_l2(dw2.float().cpu().numpy(), dw1.float().cpu().numpy()) < 1e-3
+    # fp32 accumulation into main_grad and fp32 d_hidden
+    acc = torch.ones(V, H, device="cuda")
+    _, _, _, _, saved = lm_head_forward_save_raw(h, w, i, 1 / tau, shift=shift)
+    dh3, _ = lm_head_backward_saved_raw(h, w, i, lse0, g, 1 / tau, saved, shift=shift, dweight=acc, dweight_accumulate=True, dhidden_f32=True)
+    assert dh3.dtype == torch.float32
+    if T > 1:
+        assert rel_l2((acc - 1).cpu().numpy(), dw1.float().cpu().numpy()) < 5e-3
+        assert rel_l2(dh3.cpu().numpy(), dh1.float().cpu().numpy()) < 5e-3
+
+
+def test_saved_logits_policy_and_second_backward(P):
+    """Autograd integration: size policy, and a second backward through a retained graph (the kept block is consumed by the
+    first one) falls back to the recompute and gives the same gradients."""
+    from prime_rl_cse_b200 import saved_logits_policy
+
+    assert saved_logits_policy(16384, 151936) and not saved_logits_policy(10**6, 151936) and not saved_logits_policy(0, 1000)
+    assert saved_logits_policy(10**6, 151936, True) and not saved_logits_policy(16, 1000, False)
+    T, H, V = 300, 128, 3000
+    hidden, weight, ids = _mk(T, H, V, 5)
+    h = hidden.cuda().requires_grad_(True)
+    w = weight.cuda().requires_grad_(True)
+    lp, _ = P.fused_lm_head_logprobs_entropy(h.unsqueeze(0), w, ids.cuda().unsqueeze(0), 0.9, save_logits=True)
+    loss = (lp[0] * torch.linspace(-1, 1, T, device="cuda")).sum()
+    loss.backward(retain_graph=True)
+    g1 = (h.grad.clone(), w.grad.clone())
+    h.grad = w.grad = None
+    loss.backward()
+    assert torch.equal(g1[0], h.grad) and torch.equal(g1[1], w.grad)
+    with torch.no_grad():  # nothing is kept when no gradient can flow
+        lp2, _ = P.fused_lm_head_logprobs_entropy(hidden.cuda().unsqueeze(0), weight.cuda(), ids.cuda().unsqueeze(0), 0.9, save_logits=True)
+        assert torch.equal(lp2, lp.detach())
+
+
 def test_micro_step_on_reference_packed_batches(P):
     """The packed micro-batches the reference orchestrator writes (prepare_batch, 2 train workers, incl. the all-masked padding
     batch) through the fused micro-step, each rank with its rank-local loss scale (train.py:263-267)."""
@@ -543,7 +619,8 @@ def test_micro_step_on_reference_packed_batches(P):
                 assert out["loss"].item() == 0.0 and float(h.grad.abs().max()) == 0.0 and float(w.grad.abs().max()) == 0.0
 
 
-def test_backward_skips_masked_positions_exactly(P):
+@pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
+def test_backward_skips_masked_positions_exactly(P, save):
     """`active_positions`: the compacted backward gives the same gradients as the full one (masked rows contribute zeros)."""
     T, H, V, tau = 900, 256, 6000, 0.7
     hidden, weight, ids = _mk(T, H, V, 31)
@@ -554,7 +631,8 @@ def test_backward_skips_masked_positions_exactly(P):
     for active in (None, mask.nonzero().reshape(-1).cuda()):
         h = hidden.cuda().requires_grad_(True)
         w = weight.cuda().requires_grad_(True)
-        lp, _ = P.fused_lm_head_logprobs_entropy(h.unsqueeze(0), w, ids.cuda().unsqueeze(0), tau, active_positions=active)
+        lp, _ = P.fused_lm_head_logprobs_entropy(h.unsqueeze(0), w, ids.cuda().unsqueeze(0), tau, active_positions=active,
+                                                 save_logits=save)
         (lp[0] * g.cuda()).sum().backward()
         outs.append((h.grad.float(), w.grad.float()))
     (dh0, dw0), (dh1, dw1) = outs
@@ -563,7 +641,8 @@ def test_backward_skips_masked_positions_exactly(P):
     assert float(dh1[inactive_rows].abs().max()) == 0.0
 
 
-def test_forward_active_only(P):
+@pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
+def test_forward_active_only(P, save):
     """Opt-in: forward restricted to the unmasked positions gives the same values there (and the same loss / gradients)."""
     T, H, V, tau = 700, 256, 6000, 0.7
     hidden, weight, ids = _mk(T, H, V, 41)
@@ -580,7 +659,7 @@ def test_forward_active_only(P):
     for skip_fwd in (False, True):
         h = hidden.cuda().requires_grad_(True)
         w = weight.cuda().requires_grad_(True)
-        out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), int(mask.sum()), forward_skips_masked=skip_fwd)
+        out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), int(mask.sum()), forward_skips_masked=skip_fwd, save_logits=save)
         res.append((out, h.grad.float(), w.grad.float()))
     (o0, dh0, dw0), (o1, dh1, dw1) = res
     m = torch.from_numpy(mask).cuda()

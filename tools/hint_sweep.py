@@ -22,9 +22,39 @@ torch.cuda.synchronize()
 FL = 2.0 * T * H * V
 
 
+_saved = {}
+
+
+def saved_block():
+    """[T, ld] bf16 block of the saved-logits mode, holding REAL dlogits (forward, then the in-place conversion)"""
+    if "blk" not in _saved:
+        from prime_rl_cse_b200 import lm_head_backward_saved_raw, lm_head_forward_save_raw
+
+        _, _, _, _, blk = lm_head_forward_save_raw(hidden, W, ids, 1.0, workspace=ws_f)
+        lm_head_backward_saved_raw(hidden, W, ids, lse, g, 1.0, blk, want_dhidden=False, want_dweight=False, phase_mask=1)
+        torch.cuda.synchronize()
+        _saved["blk"] = blk
+    return _saved["blk"]
+
+
 def fam_fn(fam):
     if fam == "FWD":
         return lambda: lm_head_forward_raw(hidden, W, ids, 1.0, workspace=ws_f)
+    if fam in ("FWDS", "SDZ", "SDH", "SDW", "SBWD", "STEP_S"):
+        # saved-logits mode.  SDZ re-applies the in-place conversion to its own output (timing only)
+        from prime_rl_cse_b200 import lm_head_backward_saved_raw, lm_head_forward_save_raw
+
+        blk = saved_block()
+        fwd = lambda: lm_head_forward_save_raw(hidden, W, ids, 1.0, workspace=ws_f, saved=blk)
+        bwd = lambda m: lm_head_backward_saved_raw(hidden, W, ids, lse, g, 1.0, blk, dweight=dW, dweight_accumulate=True, phase_mask=m)
+        if fam == "FWDS":
+            return fwd
+        if fam == "STEP_S":
+            return lambda: (fwd(), bwd(7))
+        return lambda: bwd({"SDZ": 1, "SDH": 2, "SDW": 4, "SBWD": 7}[fam])
+    if fam == "STEP_R":
+        return lambda: (lm_head_forward_raw(hidden, W, ids, 1.0, workspace=ws_f),
+                        lm_head_backward_raw(hidden, W, ids, lse, g, 1.0, dweight=dW, dweight_accumulate=True, workspace=ws_b))
     mask = {"DZ": 1, "DH": 2, "DW": 4, "BWD": 7, "DZDH": 3, "DZDW": 5, "DHDW": 6}[fam]
     return lambda: lm_head_backward_raw(hidden, W, ids, lse, g, 1.0, dweight=dW, dweight_accumulate=True, workspace=ws_b, phase_mask=mask)
 

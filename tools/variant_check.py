@@ -40,6 +40,16 @@ dl = torch.zeros_like(dz); dl[:-1] = (dz[1:] / tau).bfloat16().float()
 ref_dh, ref_dw = dl @ W.float(), dl.t() @ hidden.float()
 r1 = ((dh.float() - ref_dh).norm() / ref_dh.norm()).item(); r2 = ((dw.float() - ref_dw).norm() / ref_dw.norm()).item()
 ok &= r1 < 1e-2 and r2 < 1e-2
+# saved-logits pair: same statistics, same gradients (one vocab chunk here: identical K order -> identical bits)
+from prime_rl_cse_b200 import lm_head_backward_saved_raw, lm_head_forward_save_raw
+logp_s, ent_s, lse_s, _, saved = lm_head_forward_save_raw(hidden, W, ids, 1 / tau)
+ok &= bool(torch.equal(logp_s, logp) and torch.equal(ent_s, ent) and torch.equal(lse_s, lse))
+dh_s, dw_s = lm_head_backward_saved_raw(hidden, W, ids, lse, g, 1 / tau, saved)
+dh_1, dw_1 = lm_head_backward_raw(hidden, W, ids, lse, g, 1 / tau, vchunk=V)
+s1 = ((dh_s.float() - ref_dh).norm() / ref_dh.norm()).item(); s2 = ((dw_s.float() - ref_dw).norm() / ref_dw.norm()).item()
+same = bool(torch.equal(dh_s, dh_1) and torch.equal(dw_s, dw_1))
+ok &= s1 < 1e-2 and s2 < 1e-2 and same
+print(f"saved-logits: dH rel {s1:.2e}, dW rel {s2:.2e}, bit-identical to single-chunk recompute: {same}")
 print(f"MSUB={os.environ.get('PRL_MSUB','1')} CTA_GROUP={os.environ.get('PRL_CTA_GROUP','2')} EPI_TMA={os.environ.get('PRL_EPI_TMA','1')}: logp max err {d.max().item():.2e}, "
       f"dH rel {r1:.2e}, dW rel {r2:.2e} -> {'OK' if ok else 'FAIL'}")
 sys.exit(0 if ok else 1)
