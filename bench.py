@@ -56,23 +56,40 @@ SHAPES = {
 }
 
 
-# DRAM bytes (read + write) per launch of each GEMM family at the Qwen3-8B shape (T=16384, H=4096, vocab chunk 16384), from
-# the `ncu --set full` capture summarised in profiles/r1_lmhead_final_ncu_summary.txt (dram__bytes_read.sum +
-# dram__bytes_write.sum).  The forward capture there covers a 32768-row vocabulary slice; it is scaled to V=151936.
+# DRAM bytes (read + write) per launch of each kernel family at the Qwen3-8B shape (T=16384, H=4096), from `ncu --set full`
+# captures (dram__bytes_read.sum + dram__bytes_write.sum).  "recompute": vocab chunk 16384, profiles/r1_lmhead_final_ncu_summary.txt
+# (the forward capture there covers a 32768-row vocabulary slice; it is scaled to V=151936).  "saved": whole-vocabulary
+# launches, profiles/r1_saved_logits_ncu_summary.txt.
 NCU_TRAFFIC_BYTES = {
-    "lmhead_bwd_dz_kernel": 2.81e9 + 0.508e9,
-    "lmhead_bwd_dhidden_kernel": 2.05e9 + 0.245e9,
-    "lmhead_bwd_dweight_kernel": 2.06e9 + 0.242e9,
-    "lmhead_fwd_kernel": (4.75e9 + 0.007e9) * 151936 / 32768,
+    "recompute": {
+        "lmhead_bwd_dz_kernel": 2.81e9 + 0.508e9,
+        "lmhead_bwd_dhidden_kernel": 2.05e9 + 0.245e9,
+        "lmhead_bwd_dweight_kernel": 2.06e9 + 0.242e9,
+        "lmhead_fwd_kernel": (4.75e9 + 0.007e9) * 151936 / 32768,
+    },
+    "saved": {
+        "lmhead_fwd_save_kernel": 7.834e9 + 4.972e9,
+        "dz_from_saved_logits_kernel": 4.979e9 + 4.921e9,
+        "lmhead_bwd_dhidden_kernel": 23.650e9 + 0.128e9,
+        "lmhead_bwd_dweight_kernel": 18.218e9 + 2.488e9,
+    },
 }
-# algorithmic bytes per launch (operands read once + outputs written once), for comparison with `traffic`
+NCU_TRAFFIC_SOURCE = {"recompute": "profiles/r1_lmhead_final_ncu_summary.txt", "saved": "profiles/r1_saved_logits_ncu_summary.txt"}
+
+
+# algorithmic bytes per launch (operands read once + outputs written once), for comparison with `traffic`; vc = vocab columns
+# one launch covers (the vocab chunk in recompute mode, V in saved-logits mode)
 def algorithmic_bytes(kernel, T, H, V, vc):
     if kernel == "lmhead_fwd_kernel":
         return 2.0 * (T * H + V * H) + 16.0 * T
+    if kernel == "lmhead_fwd_save_kernel":
+        return 2.0 * (T * H + V * H) + 16.0 * T + 2.0 * T * V
+    if kernel == "dz_from_saved_logits_kernel":
+        return 4.0 * T * V + 16.0 * T
     if kernel == "lmhead_bwd_dz_kernel":
         return 2.0 * (T * H + vc * H) + 2.0 * T * vc
     if kernel == "lmhead_bwd_dhidden_kernel":
-        return 2.0 * (T * vc + vc * H) + 8.0 * T * H
+        return 2.0 * (T * vc + vc * H) + (8.0 if vc < V else 2.0) * T * H
     return 2.0 * (T * vc + T * H) + 8.0 * vc * H
 
 
@@ -221,6 +238,13 @@ def run_b200(args):
     lib = _lib.load()
     ws_f = torch.empty(lib.prl_lmhead_fwd_workspace_bytes(T, H, V), dtype=torch.uint8, device=dev)
     ws_b = torch.empty(lib.prl_lmhead_bwd_workspace_bytes(T, H, V, 0), dtype=torch.uint8, device=dev)
+    # backward mode: "saved" keeps one bf16 copy of the logits per micro-batch (T x V x 2 bytes) between forward and backward,
+    # "recompute" keeps lse[T] only and recomputes the logits per vocab chunk; "auto" = the library's size policy
+    bwd_mode = args.lm_head_backward
+    if bwd_mode == "auto":
+        bwd_mode = "saved" if P.saved_logits_policy(T, V) else "recompute"
+    save_flag = bwd_mode == "saved"
+    saved_blk = torch.empty(T, int(lib.prl_lmhead_saved_logits_ld(V)), dtype=torch.bfloat16, device=dev) if save_flag else None
 
     Wd = W.detach()
 
@@ -232,12 +256,19 @@ def run_b200(args):
             mb = dev_mbs[i % len(dev_mbs)]
             hid = mb["hidden"][0]
             ids = mb["input_ids"][0]
-            logp, ent, lse, _ = P.lm_head_forward_raw(hid, Wd, ids, 1.0 / mb["temperature"], workspace=ws_f)
+            if save_flag:
+                logp, ent, lse, _, _ = P.lm_head_forward_save_raw(hid, Wd, ids, 1.0 / mb["temperature"], workspace=ws_f, saved=saved_blk)
+            else:
+                logp, ent, lse, _ = P.lm_head_forward_raw(hid, Wd, ids, 1.0 / mb["temperature"], workspace=ws_f)
             loss, ratio, clipped, is_clipped, dlogp = _loss_packed_raw(
                 logp, mb["logprobs"][0], mb["advantages"][0], mb["loss_mask"][0].view(torch.uint8), cu, nseg, mode,
                 cfg.ratio_length_norm, cfg.clip_ratio, loss_scale)
-            P.lm_head_backward_raw(hid, Wd, ids, lse, dlogp, 1.0 / mb["temperature"], dweight=main_grad, dweight_accumulate=True,
-                                   workspace=ws_b)
+            if save_flag:
+                P.lm_head_backward_saved_raw(hid, Wd, ids, lse, dlogp, 1.0 / mb["temperature"], saved_blk, dweight=main_grad,
+                                             dweight_accumulate=True)
+            else:
+                P.lm_head_backward_raw(hid, Wd, ids, lse, dlogp, 1.0 / mb["temperature"], dweight=main_grad, dweight_accumulate=True,
+                                       workspace=ws_b)
             last = loss
         if dist is not None and rs_out is not None:
             dist.reduce_scatter_tensor(rs_out, main_grad.view(-1))
@@ -274,7 +305,7 @@ def run_b200(args):
                     v.record_stream(cur)
             hid = mb["hidden"].requires_grad_(True)
             out = P.rl_micro_step(hid, W, mb, cfg, loss_scale, main_grad=main_grad, response_lengths=None,
-                                  forward_skips_masked=args.forward_skips_masked)
+                                  forward_skips_masked=args.forward_skips_masked, save_logits=save_flag)
             loss_host[i].copy_(out["loss"], non_blocking=True)
         if dist is not None and rs_out is not None:
             dist.reduce_scatter_tensor(rs_out, main_grad.view(-1))
@@ -340,14 +371,27 @@ def run_b200(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / n
 
-        vc = 16384  # default vocab chunk of prl_lmhead_bwd
-        nchunks = (V + vc - 1) // vc
-        fam["lmhead_fwd_kernel"] = dict(ms_per_launch=ev_time(lambda: P.lm_head_forward_raw(hid, Wd, ids, 1.0, workspace=ws_f), 8),
-                                        launches_per_mb=1, flops_per_launch=2.0 * T * H * V)
-        for name, mask in (("lmhead_bwd_dz_kernel", 1), ("lmhead_bwd_dhidden_kernel", 2), ("lmhead_bwd_dweight_kernel", 4)):
-            t_ms = ev_time(lambda: P.lm_head_backward_raw(hid, Wd, ids, lse, dlogp, 1.0, dweight=main_grad, dweight_accumulate=True,
-                                                          phase_mask=mask, workspace=ws_b), 4)
-            fam[name] = dict(ms_per_launch=t_ms / nchunks, launches_per_mb=nchunks, flops_per_launch=2.0 * T * H * V / nchunks)
+        if save_flag:
+            vc, nchunks = V, 1
+            fwd_s = lambda: P.lm_head_forward_save_raw(hid, Wd, ids, 1.0, workspace=ws_f, saved=saved_blk)
+            bwd_s = lambda m: P.lm_head_backward_saved_raw(hid, Wd, ids, lse, dlogp, 1.0, saved_blk, dweight=main_grad,
+                                                           dweight_accumulate=True, phase_mask=m)
+            fam["lmhead_fwd_save_kernel"] = dict(ms_per_launch=ev_time(fwd_s, 8), launches_per_mb=1, flops_per_launch=2.0 * T * H * V)
+            bwd_s(1)  # the block now holds real dlogits (tensor-core power is data dependent), as inside the step
+            for name, mask in (("lmhead_bwd_dhidden_kernel", 2), ("lmhead_bwd_dweight_kernel", 4)):
+                fam[name] = dict(ms_per_launch=ev_time(lambda: bwd_s(mask), 4), launches_per_mb=1, flops_per_launch=2.0 * T * H * V)
+            # HBM-bound in-place pass (re-applied to its own output here: timing only)
+            fam["dz_from_saved_logits_kernel"] = dict(ms_per_launch=ev_time(lambda: bwd_s(1), 8), launches_per_mb=1, flops_per_launch=0.0,
+                                                      bytes_per_launch=algorithmic_bytes("dz_from_saved_logits_kernel", T, H, V, V))
+        else:
+            vc = 16384  # default vocab chunk of prl_lmhead_bwd
+            nchunks = (V + vc - 1) // vc
+            fam["lmhead_fwd_kernel"] = dict(ms_per_launch=ev_time(lambda: P.lm_head_forward_raw(hid, Wd, ids, 1.0, workspace=ws_f), 8),
+                                            launches_per_mb=1, flops_per_launch=2.0 * T * H * V)
+            for name, mask in (("lmhead_bwd_dz_kernel", 1), ("lmhead_bwd_dhidden_kernel", 2), ("lmhead_bwd_dweight_kernel", 4)):
+                t_ms = ev_time(lambda: P.lm_head_backward_raw(hid, Wd, ids, lse, dlogp, 1.0, dweight=main_grad, dweight_accumulate=True,
+                                                              phase_mask=mask, workspace=ws_b), 4)
+                fam[name] = dict(ms_per_launch=t_ms / nchunks, launches_per_mb=nchunks, flops_per_launch=2.0 * T * H * V / nchunks)
 
     peaks = measured_peaks()
     tokens_per_step = n_mb * T
@@ -366,7 +410,11 @@ def run_b200(args):
                    "tokens_per_gpu_per_step": tokens_per_step, "parallelism": f"token-sharded dp{world} (no data-path collective; "
                    + ("d_W_lm fp32 reduce-scatter once per step)" if world > 1 else "single GPU)"),
                    "l2_policy": "inputs larger than L2 (W_lm 1.24 GB + 134 MB hidden per micro-batch, rotating micro-batches)",
-                   "flops_per_token_algorithmic": flops_per_token},
+                   "flops_per_token_algorithmic": flops_per_token,
+                   "lm_head_backward": (f"saved-logits: one bf16 [T, V] block ({T * V * 2 / 2**30:.2f} GiB) kept per micro-batch between "
+                                        "forward and backward, rewritten in place into dlogits; 3 GEMMs of T*H*V per micro-batch"
+                                        if save_flag else "recompute: lse[T] kept only, logits recomputed per 16384-column vocab "
+                                        "chunk; 4 GEMMs of T*H*V per micro-batch")},
         "per_gpu": value / world,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * n_mb + 8 * n_mb,
                 "ms_per_step": ms_e2e / args.steps, "api": "prime_rl_cse_b200.rl_micro_step + compute_advantages (host buffers)"},
@@ -374,7 +422,7 @@ def run_b200(args):
         "clocks": clocks,
         "tensor_tflops_algorithmic_per_gpu": alg_tflops,
         "frac_of_peak": {"measured_burst": alg_tflops / peaks["burst"], "measured_sustained": alg_tflops / peaks["sustained"],
-                         "nominal_2250": alg_tflops / 2250.0, "executed_over_algorithmic": 8.0 / 6.0},
+                         "nominal_2250": alg_tflops / 2250.0, "executed_over_algorithmic": (6.0 if save_flag else 8.0) / 6.0},
     }
     if fam:
         top = max(fam, key=lambda k: fam[k]["ms_per_launch"] * fam[k]["launches_per_mb"])
@@ -382,14 +430,19 @@ def run_b200(args):
         achieved = f["flops_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e12
         result["roofline"] = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
                               "frac": achieved / peaks["sustained"],
-                              "traffic": NCU_TRAFFIC_BYTES.get(top) if args.workload == "qwen3-8b-hendrycks" else None,
-                              "traffic_source": "profiles/r1_lmhead_final_ncu_summary.txt (dram read+write bytes per launch)",
+                              "traffic": NCU_TRAFFIC_BYTES[bwd_mode].get(top) if args.workload == "qwen3-8b-hendrycks" else None,
+                              "traffic_source": NCU_TRAFFIC_SOURCE[bwd_mode] + " (dram read+write bytes per launch)",
                               "algorithmic_bytes": algorithmic_bytes(top, T, H, V, vc),
                               "flops_per_launch": f["flops_per_launch"], "ms_per_launch": f["ms_per_launch"],
                               "peak_source": peaks["source"] + " sustained (kernel timed inside a long power-capped step)",
                               "frac_of_burst": achieved / peaks["burst"]}
         result["kernel_breakdown_ms_per_micro_batch"] = {k: v["ms_per_launch"] * v["launches_per_mb"] for k, v in fam.items()}
-        result["kernel_tflops"] = {k: v["flops_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e12 for k, v in fam.items()}
+        result["kernel_tflops"] = {k: v["flops_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e12 for k, v in fam.items() if v["flops_per_launch"]}
+        hbm = {k: v for k, v in fam.items() if v.get("bytes_per_launch")}
+        if hbm:  # the HBM-bound pass of the saved-logits backward against the measured copy bandwidth
+            result["hbm_kernels"] = {k: {"achieved_gbs": v["bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9, "peak_gbs": peaks["hbm"],
+                                         "frac": v["bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9 / peaks["hbm"],
+                                         "algorithmic_bytes": v["bytes_per_launch"]} for k, v in hbm.items()}
     if rank == 0 and not args.no_torch_baseline:
         result["torch_gpu_reference"] = torch_gpu_reference(wl, dev)
     if rank == 0:
@@ -528,6 +581,8 @@ def main():
     ap.add_argument("--forward-skips-masked", action="store_true", help="e2e arm: also restrict the forward to unmasked positions")
     ap.add_argument("--prompt-frac", type=float, default=0.0, help="mask the first fraction of every rollout (default 0 = all-ones mask)")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-on-GPU reference-chain timing")
+    ap.add_argument("--lm-head-backward", default="auto", choices=["auto", "saved", "recompute"],
+                    help="saved = keep the bf16 logits between forward and backward (T*V*2 bytes); recompute = keep lse only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

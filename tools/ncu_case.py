@@ -1,9 +1,10 @@
 """Short single-GPU case for ncu: one fused forward + one backward at the Qwen3-8B tile shape but a
-reduced vocabulary (2 vocab chunks), so every launch has the same per-launch work as in bench.py."""
+reduced vocabulary (2 vocab chunks), so every launch has the same per-launch work as in bench.py.
+NCU_SAVED=1: the saved-logits pair instead (whole-vocabulary launches: set NCU_V=151936 for the bench.py shape)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_forward_raw
+from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_backward_saved_raw, lm_head_forward_raw, lm_head_forward_save_raw
 
 T, H, V = 16384, 4096, int(os.environ.get("NCU_V", 16384))
 dev = "cuda"
@@ -12,7 +13,13 @@ hidden = torch.randn(T, H, device=dev).bfloat16()
 W = (torch.randn(V, H, device=dev) * 0.02).bfloat16()
 ids = torch.randint(0, V, (T,), device=dev)
 dW = torch.zeros(V, H, device=dev)
+saved = None
 for _ in range(int(os.environ.get("NCU_ITERS", 2))):
+    if os.environ.get("NCU_SAVED"):
+        logp, ent, lse, _, saved = lm_head_forward_save_raw(hidden, W, ids, 1.0, saved=saved)
+        g = torch.randn(T, device=dev) / T
+        lm_head_backward_saved_raw(hidden, W, ids, lse, g, 1.0, saved, dweight=dW, dweight_accumulate=True)
+        continue
     logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, 1.0)
     g = torch.randn(T, device=dev) / T
     if os.environ.get("NCU_FWD_ONLY"):
