@@ -206,11 +206,13 @@ static void set_tiling(GemmParams& p, int64_t M, int64_t N, int64_t K, int epi) 
   p.k_blocks = (int)((K + BLOCK_K - 1) / BLOCK_K);
 }
 
-// one item per output tile, m-tiles in bands of 8 for L2 reuse of the B operand
-static void schedule_tiles(GemmParams& p) {
+// one item per output tile, m-tiles in bands of `band` 128-row blocks (PRL_GROUP_M overrides) for L2 reuse of the B operand.
+// Measured: 8 for the per-vocab-chunk GEMMs of the recompute backward (within 1 % of its neighbours); 4 (= one 512-row
+// m-tile: neighbouring workers share the A panel) for the whole-vocabulary GEMMs of the saved-logits backward (+1..2 %).
+static void schedule_tiles(GemmParams& p, int band = 8) {
   p.tiles_per_split = 1;
   p.n_splits = p.n_tiles;
-  p.group_m = (int)env_long("PRL_GROUP_M", 8) / (cta_group() * msub(EPI_STORE));
+  p.group_m = (int)env_long("PRL_GROUP_M", band) / (cta_group() * msub(EPI_STORE));
   if (p.group_m < 1) p.group_m = 1;
   p.max_stages = (int)env_long("PRL_TILE_STAGES", 0);
   p.num_items = p.m_tiles * p.n_splits;
@@ -461,7 +463,7 @@ int prl_lmhead_merge_partials(const float* partials, int32_t nparts, int64_t T, 
 static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __nv_bfloat16* dz, int64_t vc, int64_t c0, int64_t vce,
                             int64_t T, int32_t H, void* d_hidden, int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype,
                             int32_t accumulate_dw, int32_t phase_mask, bool first, bool last, int64_t nchunks, float* dh_acc,
-                            cudaStream_t st) {
+                            int band, cudaStream_t st) {
   // ---- K2: d_hidden[T,H] += dz[T,vce] x W[c0:c0+vce, :]   (A K-major, B MN-major) ----
   if (d_hidden && (phase_mask & 2)) {
     GemmParams p;
@@ -471,7 +473,7 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
     rc = make_operand_map(&p.tma_b, W + c0 * H, true, H, vce, H, BLOCK_N);
     if (rc) return rc;
     set_tiling(p, T, H, vce, EPI_STORE);
-    schedule_tiles(p);
+    schedule_tiles(p, band);
     make_desc_defaults(p, false, true);
     p.epi.m_rows = T;
     p.epi.n_cols = H;
@@ -520,7 +522,7 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
     rc = make_operand_map(&p.tma_b, hidden, true, H, T, H, BLOCK_N);
     if (rc) return rc;
     set_tiling(p, vce, H, T, EPI_STORE);
-    schedule_tiles(p);
+    schedule_tiles(p, band);
     make_desc_defaults(p, true, true);
     p.epi.m_rows = vce;
     p.epi.n_cols = H;
@@ -624,7 +626,7 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
     }
     {
       const int rc = lmhead_bwd_gemms(hidden, W, dz, vc, c0, vce, T, H, d_hidden, d_hidden_f32, d_weight, d_weight_dtype, accumulate_dw,
-                                      phase_mask, c == 0, c == nchunks - 1, nchunks, dh_acc, st);
+                                      phase_mask, c == 0, c == nchunks - 1, nchunks, dh_acc, 8, st);
       if (rc) return rc;
     }
   }
@@ -655,7 +657,7 @@ int prl_lmhead_bwd_saved(const void* hidden, const void* weight, const int64_t* 
     if (rc) return rc;
   }
   return lmhead_bwd_gemms(hidden, reinterpret_cast<const __nv_bfloat16*>(weight), dz, saved_ld, 0, V, T, H, d_hidden, d_hidden_f32, d_weight,
-                          d_weight_dtype, accumulate_dw, phase_mask, true, true, 1, nullptr, st);
+                          d_weight_dtype, accumulate_dw, phase_mask, true, true, 1, nullptr, 4, st);
 }
 
 int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn_major, int32_t b_mn_major,
