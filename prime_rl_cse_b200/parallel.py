@@ -17,7 +17,8 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
-from .lm_head import lm_head_backward_raw, lm_head_forward_raw
+from .lm_head import (lm_head_backward_raw, lm_head_backward_saved_raw, lm_head_forward_raw, lm_head_forward_save_raw,
+                      saved_logits_policy)
 
 
 # --------------------------------------------------------------------------- token sharding (host logic)
@@ -61,17 +62,26 @@ def exchange_partials(partials: torch.Tensor, group: dist.ProcessGroup | None = 
 # --------------------------------------------------------------------------- vocab-sharded fused LM head
 class _VocabParallelLMHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, hidden, weight_shard, ids, inv_temp, v_offset, v_total, group, shift, round_bf16):
+    def forward(ctx, hidden, weight_shard, ids, inv_temp, v_offset, v_total, group, shift, round_bf16, save_logits=None):
         lib = _lib.load()
         h2 = hidden.detach().reshape(-1, hidden.shape[-1]).contiguous()
         w2 = weight_shard.detach().contiguous()
         i2 = ids.detach().reshape(-1).contiguous().to(torch.int64)
         T = h2.shape[0]
         dev = h2.device
-        if w2.shape[0] > 0:
+        ctx.saved_logits = None  # this shard's bf16 logits [T, V_local], consumed by the backward
+        save = (round_bf16 and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+                and saved_logits_policy(T, w2.shape[0], save_logits))
+        if w2.shape[0] > 0 and save:
+            try:
+                _, _, _, parts, ctx.saved_logits = lm_head_forward_save_raw(h2, w2, i2, inv_temp, shift, v_offset=v_offset,
+                                                                            v_total=v_total, want_partials=True)
+            except torch.OutOfMemoryError:
+                save = False
+        if w2.shape[0] > 0 and not save:
             _, _, _, parts = lm_head_forward_raw(h2, w2, i2, inv_temp, shift, round_bf16, v_offset=v_offset, v_total=v_total,
                                                  want_partials=True)
-        else:  # a trailing rank with an empty shard contributes the neutral element
+        elif w2.shape[0] == 0:  # a trailing rank with an empty shard contributes the neutral element
             parts = torch.zeros(T, 4, dtype=torch.float32, device=dev)
             parts[:, 0] = float("-inf")
         gathered = exchange_partials(parts, group)
@@ -95,7 +105,11 @@ class _VocabParallelLMHead(torch.autograd.Function):
         g = g_logp.detach().reshape(-1).contiguous().float()
         need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dh = dw = None
-        if w2.shape[0] > 0:
+        saved, ctx.saved_logits = ctx.saved_logits, None
+        if w2.shape[0] > 0 and saved is not None:
+            dh, dw = lm_head_backward_saved_raw(h2, w2, i2, lse, g, inv_temp, saved, shift, v_offset=v_offset, want_dhidden=need_h,
+                                                want_dweight=need_w, dhidden_f32=True)
+        elif w2.shape[0] > 0:
             dh, dw = lm_head_backward_raw(h2, w2, i2, lse, g, inv_temp, shift, round_bf16, v_offset=v_offset, want_dhidden=need_h,
                                           want_dweight=need_w, dhidden_f32=True)
         elif need_h:
@@ -105,7 +119,7 @@ class _VocabParallelLMHead(torch.autograd.Function):
             dh = dh.to(torch.bfloat16).reshape(hshape)
         if need_w and dw is None:
             dw = torch.zeros_like(w2)
-        return dh, dw, None, None, None, None, None, None, None
+        return dh, dw, None, None, None, None, None, None, None, None
 
 
 def vocab_parallel_lm_head_logprobs_entropy(
@@ -118,15 +132,17 @@ def vocab_parallel_lm_head_logprobs_entropy(
     *,
     shift: bool = True,
     round_bf16: bool = True,
+    save_logits: bool | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
     """Vocab-sharded variant of `fused_lm_head_logprobs_entropy`: `weight_shard` holds this rank's rows
     `vocab_shard_bounds(vocab_size, world, rank)` of W_lm; `hidden` / `input_ids` are the SAME on every rank
     of `group` (all-gathered by the caller).  Returns (logprobs, entropy) identical on every rank; backward
-    gives the full d_hidden (all-reduced) and the local shard of d_W_lm."""
+    gives the full d_hidden (all-reduced) and the local shard of d_W_lm.  `save_logits`: as in
+    `fused_lm_head_logprobs_entropy`, applied to this rank's `[T, V_local]` block."""
     _lib.require_cuda(hidden, weight_shard, input_ids)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     v0, v1 = vocab_shard_bounds(vocab_size, world, rank)
     if weight_shard.shape[0] != v1 - v0:
         raise ValueError(f"rank {rank} expects {v1 - v0} vocab rows, got {weight_shard.shape[0]}")
     return _VocabParallelLMHead.apply(hidden, weight_shard, input_ids, 1.0 / float(temperature), v0, vocab_size, group,
-                                      bool(shift), bool(round_bf16))
+                                      bool(shift), bool(round_bf16), save_logits)

@@ -81,13 +81,26 @@ def test_forward_properties_full_size(P, T, H, V, tau):
     assert (de < 1e-3).float().mean().item() >= 0.97 and de.max().item() < bound, (de.max().item(), bound)
 
 
+@pytest.mark.parametrize("mode", ["recompute", "saved-logits"])
 @pytest.mark.parametrize("T,H,V,tau", SHAPES[1:])
-def test_backward_sampled_slices_full_size(P, T, H, V, tau):
-    from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_forward_raw
+def test_backward_sampled_slices_full_size(P, T, H, V, tau, mode):
+    from prime_rl_cse_b200 import lm_head_backward_saved_raw, lm_head_forward_raw, lm_head_forward_save_raw
+    from prime_rl_cse_b200 import lm_head_backward_raw as backward_recompute
 
     hidden, W, ids = make(T, H, V, seed=7 * T + H)
     inv = 1.0 / tau
     logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, inv)
+    blk = None
+
+    def lm_head_backward_raw(hidden, W, ids, lse, g, inv, **kw):
+        """the backward under test: recompute, or (re)fill the kept-logits block and consume it"""
+        nonlocal blk
+        if mode == "recompute":
+            return backward_recompute(hidden, W, ids, lse, g, inv, **kw)
+        lp_s, _, lse_s, _, blk = lm_head_forward_save_raw(hidden, W, ids, inv, saved=blk)
+        assert torch.equal(lp_s, logp) and torch.equal(lse_s, lse)  # same statistics as the plain forward, bit for bit
+        return lm_head_backward_saved_raw(hidden, W, ids, lse, g, inv, blk, **kw)
+
     gg = torch.Generator(device="cuda").manual_seed(7)
     g = (torch.randn(T, device="cuda", generator=gg) / T)
     g[torch.rand(T, device="cuda", generator=gg) < 0.25] = 0.0  # masked tokens
@@ -127,10 +140,11 @@ def test_backward_sampled_slices_full_size(P, T, H, V, tau):
     assert ((dW2[vs] - 2 * sel).norm() / sel.norm()).item() < 1e-5
 
 
-def test_vocab_sharded_backward_emulated_on_one_gpu(P):
+@pytest.mark.parametrize("mode", ["recompute", "saved-logits"])
+def test_vocab_sharded_backward_emulated_on_one_gpu(P, mode):
     """config 4 semantics: per-shard d_hidden partial sums add up to the unsharded d_hidden and the d_W shards
     concatenate to the unsharded d_W (Qwen3-32B hidden size, reduced T)."""
-    from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_forward_raw
+    from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_backward_saved_raw, lm_head_forward_raw, lm_head_forward_save_raw
 
     T, H, V, tau, world = 1024, 5120, 151936, 1.0, 8
     hidden, W, ids = make(T, H, V, seed=3)
@@ -140,7 +154,11 @@ def test_vocab_sharded_backward_emulated_on_one_gpu(P):
     dh_sum = torch.zeros(T, H, device="cuda")
     for r in range(world):
         v0, v1 = P.vocab_shard_bounds(V, world, r)
-        dh_r, dw_r = lm_head_backward_raw(hidden, W[v0:v1], ids, lse, g, 1.0 / tau, v_offset=v0, dhidden_f32=True)
+        if mode == "recompute":
+            dh_r, dw_r = lm_head_backward_raw(hidden, W[v0:v1], ids, lse, g, 1.0 / tau, v_offset=v0, dhidden_f32=True)
+        else:  # the shard keeps its own [T, V_local] bf16 logits
+            blk = lm_head_forward_save_raw(hidden, W[v0:v1], ids, 1.0 / tau, v_offset=v0, v_total=V, want_partials=True)[4]
+            dh_r, dw_r = lm_head_backward_saved_raw(hidden, W[v0:v1], ids, lse, g, 1.0 / tau, blk, v_offset=v0, dhidden_f32=True)
         dh_sum += dh_r
         assert ((dw_r.float() - dw_full[v0:v1].float()).norm() / dw_full[v0:v1].float().norm()).item() < 1e-3
     assert ((dh_sum - dh_full).norm() / dh_full.norm()).item() < 1e-3
