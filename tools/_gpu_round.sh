@@ -1,10 +1,7 @@
-set -x
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -8
-for w in qwen3-1.7b-wordle qwen3-8b-deepscaler qwen3-0.6b-reverse; do
-  timeout 300 python bench.py --workload $w --no-cpu-baseline > gpurun_out/r1_bench_1gpu_$w.json 2> gpurun_out/bench_$w.err; echo rc=$?
-  python -c "
-import json,sys
-d=json.load(open('gpurun_out/r1_bench_1gpu_$w.json'))
-print('$w', round(d['value']), round(d['e2e']['value']), d['frac_of_peak'], d['config']['lm_head_backward'][:20], d.get('kernel_breakdown_ms_per_micro_batch'))
-"
-done
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533"
+timeout 200 $TR tools/vocab_parallel_check.py 2>&1 | grep -v "^W\|^\*\*\*\*" | tail -3
+timeout 200 $TR tools/vocab_parallel_check.py --perf 2>&1 | grep -v "^W\|^\*\*\*\*" | tail -3
+PRL_SAVE_LOGITS=0 timeout 200 $TR tools/vocab_parallel_check.py --perf 2>&1 | grep -v "^W\|^\*\*\*\*" | tail -1
+timeout 200 $TR tools/fsdp_check.py 2>&1 | grep -v "^W\|^\*\*\*\*" | tail -3
+timeout 300 $TR bench.py --gpus 2 --micro-batches 8 --no-cpu-baseline --no-breakdown --no-torch-baseline > gpurun_out/r1_bench_2gpu_8mb.json 2> gpurun_out/bench_2gpu.err; echo rc=$?
+head -c 600 gpurun_out/r1_bench_2gpu_8mb.json
