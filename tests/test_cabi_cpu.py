@@ -55,6 +55,15 @@ def test_argument_validation_needs_no_gpu(lib):
     assert L.prl_lmhead_fwd(None, None, None, 8, 16, 100, 0, 100, -1.0, 1, 1, None, None, None, None, None, 0, None) == -1  # temperature <= 0
     assert L.prl_lmhead_fwd_workspace_bytes(16384, 4096, 151936) >= 64 * 16384 * 16
     assert L.prl_lmhead_bwd_workspace_bytes(16384, 4096, 151936, 8192) >= 16384 * 8192 * 2
+    # saved-logits pair: the row pitch covers V and keeps rows 16-byte aligned; a pitch below V or off alignment is refused
+    for V in (1, 8, 1003, 151936):
+        ld = L.prl_lmhead_saved_logits_ld(V)
+        assert ld >= V and ld % 8 == 0
+    assert L.prl_lmhead_fwd_save(None, None, None, 8, 16, 100, 0, 100, 1.0, 1, None, None, None, None, None, 96, None, 0, None) == -1
+    assert L.prl_lmhead_fwd_save(None, None, None, 8, 16, 100, 0, 100, 1.0, 1, None, None, None, None, 16, 100, None, 0, None) == -1
+    assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 8, 16, 100, 0, 1.0, 1, None, 104, None, 0, None, 0, 0, 0, None) == -1
+    assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 8, 16, 100, 0, 0.0, 1, None, 104, None, 0, None, 0, 0, 0, None) == -1
+    assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 0, 16, 100, 0, 1.0, 1, None, 104, None, 0, None, 0, 0, 0, None) == 0  # T == 0
 
 
 def test_no_cpu_fallback():
