@@ -192,6 +192,21 @@ size_t prl_masked_moments_workspace_bytes(void);
 int prl_masked_moments_f32(const float* x, const uint8_t* mask, int64_t n, int32_t transform, double* acc, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* Exact median of the logged values without gathering them (N1, `torch.median` at trainer/utils.py:248 = the lower
+ * median, sorted[(n-1)/2]).  prl_masked_keys_u32 appends an order-preserving uint32 key of f(x[i]) for every unmasked
+ * element to keys[*counter ...] (device counter, advanced atomically; elements beyond `capacity` are dropped, so size
+ * the buffer for the number of elements offered).  A 3-pass radix select (bits 31..21, 20..10, 9..0) then finds the
+ * k-th smallest key: prl_radix_select_hist adds to hist[2048] (uint64, device) the histogram of bits
+ * [shift, shift + bits) over the keys that match state = {prefix, prefix_mask, k, -} (int64[4], device);
+ * ranks all-reduce(SUM) the histogram; prl_radix_select_pick locates the bin of the k-th element, extends
+ * prefix / prefix_mask, reduces k, and clears hist.  After the last pass state[0] is the key of the median
+ * (key -> float: key & 0x80000000 ? key ^ 0x80000000 : ~key).  No host synchronisation anywhere. */
+int prl_masked_keys_u32(const float* x, const uint8_t* mask, int64_t n, int32_t transform, uint32_t* keys,
+                        int64_t capacity, unsigned long long* counter, void* stream);
+int prl_radix_select_hist(const uint32_t* keys, const unsigned long long* counter, int64_t capacity,
+                          const int64_t* state, int32_t shift, int32_t bits, unsigned long long* hist, void* stream);
+int prl_radix_select_pick(unsigned long long* hist, int64_t* state, int32_t shift, int32_t bits, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Packed micro-batch rows from rollouts ("next" row N4).  Replaces the per-token tensor building of prepare_sample
  * (src/prime_rl/orchestrator/batch.py:21-62: cat(prompt, completion), arange position ids, advantage.repeat(len),

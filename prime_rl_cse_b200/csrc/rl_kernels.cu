@@ -508,6 +508,91 @@ __global__ void __launch_bounds__(256) masked_moments_kernel(const float* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// exact median of the logged values (N1): order-preserving u32 keys + 3-pass radix select (11 + 11 + 10 bits), so that ranks
+// exchange three 2048-bin histograms per step instead of every masked token (trainer/utils.py:241-247)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_order_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// appends key(f(x[i])) for every unmasked i to keys[*counter ...] (warp-aggregated atomic; order is irrelevant for a selection)
+__global__ void __launch_bounds__(256) masked_keys_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask, int64_t n,
+                                                          int transform, uint32_t* __restrict__ keys, int64_t capacity,
+                                                          unsigned long long* __restrict__ counter) {
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = (n + 31) / 32 * 32;  // whole warps take part in every ballot
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool take = i < n && (mask == nullptr || mask[i]);
+    const unsigned ballot = __ballot_sync(FULL, take);
+    if (ballot == 0) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(FULL, base, 0);
+    if (take) {
+      float v = x[i];
+      if (transform == 1) v = expf(v);
+      const int64_t pos = (int64_t)base + __popc(ballot & ((1u << lane) - 1u));
+      if (pos < capacity) keys[pos] = float_order_key(v);
+    }
+  }
+}
+
+// state = {prefix, prefix_mask, k, unused}: histogram of bits [shift, shift + bits) over the keys whose masked bits equal prefix
+__global__ void __launch_bounds__(256) radix_hist_kernel(const uint32_t* __restrict__ keys, const unsigned long long* __restrict__ counter,
+                                                         int64_t capacity, const int64_t* __restrict__ state, int shift, int bits,
+                                                         unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[2048];
+  for (int b = threadIdx.x; b < 2048; b += blockDim.x) sh[b] = 0;
+  __syncthreads();
+  int64_t n = (int64_t)*counter;
+  if (n > capacity) n = capacity;
+  const uint32_t prefix = (uint32_t)state[0], pmask = (uint32_t)state[1], bmask = (1u << bits) - 1u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t k = keys[i];
+    if ((k & pmask) == prefix) atomicAdd(&sh[(k >> shift) & bmask], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < 2048; b += blockDim.x)
+    if (sh[b]) atomicAdd(&hist[b], (unsigned long long)sh[b]);
+}
+
+// one warp: find the bin holding the k-th (0-based) remaining element, extend the prefix, clear the histogram for the next pass
+__global__ void radix_pick_kernel(unsigned long long* __restrict__ hist, int64_t* __restrict__ state, int shift, int bits) {
+  const int lane = threadIdx.x;
+  const int nb = 1 << bits, per = nb / 32;
+  int64_t k = state[2];
+  unsigned long long mine = 0;
+  for (int b = lane * per; b < (lane + 1) * per; ++b) mine += hist[b];
+  unsigned long long incl = mine;  // inclusive scan over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const unsigned long long excl = incl - mine;
+  const bool here = k >= 0 && (unsigned long long)k >= excl && (unsigned long long)k < incl;
+  const unsigned ballot = __ballot_sync(FULL, here);
+  if (here) {
+    unsigned long long cum = excl;
+    for (int b = lane * per; b < (lane + 1) * per; ++b) {
+      const unsigned long long c = hist[b];
+      if ((unsigned long long)k < cum + c) {
+        state[0] = (int64_t)((uint32_t)state[0] | ((uint32_t)b << shift));
+        state[1] = (int64_t)((uint32_t)state[1] | (((1u << bits) - 1u) << shift));
+        state[2] = k - (int64_t)cum;
+        break;
+      }
+      cum += c;
+    }
+  }
+  if (ballot == 0 && lane == 0) state[2] = -1;  // k out of range (no elements): stays unresolved
+  __syncwarp();
+  for (int b = lane; b < 2048; b += 32) hist[b] = 0;
+}
+
 __global__ void masked_moments_finalize_kernel(const double* __restrict__ partial, int nblocks, double* __restrict__ acc) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     double cnt = acc[0], sum = acc[1], sq = acc[2], mn = acc[3], mx = acc[4];
@@ -694,6 +779,34 @@ int prl_masked_moments_f32(const float* x, const uint8_t* mask, int64_t n, int32
   if (rc) return rc;
   masked_moments_finalize_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const double*>(workspace), grid, acc);
   return check_launch("masked_moments_finalize_kernel");
+}
+
+int prl_masked_keys_u32(const float* x, const uint8_t* mask, int64_t n, int32_t transform, uint32_t* keys, int64_t capacity,
+                        unsigned long long* counter, void* stream) {
+  PRL_REQUIRE(n >= 0 && capacity >= 0, PRL_ERR_BAD_ARG, "masked_keys: negative size");
+  PRL_REQUIRE(transform == 0 || transform == 1, PRL_ERR_BAD_ARG, "masked_keys: unknown transform");
+  if (n == 0) return PRL_OK;
+  PRL_REQUIRE(x && keys && counter, PRL_ERR_BAD_ARG, "masked_keys: null pointer");
+  const int64_t need = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  masked_keys_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(x, mask, n, transform, keys, capacity, counter);
+  return check_launch("masked_keys_kernel");
+}
+
+int prl_radix_select_hist(const uint32_t* keys, const unsigned long long* counter, int64_t capacity, const int64_t* state, int32_t shift,
+                          int32_t bits, unsigned long long* hist, void* stream) {
+  PRL_REQUIRE(capacity >= 0 && shift >= 0 && bits >= 1 && bits <= 11 && shift + bits <= 32, PRL_ERR_BAD_ARG, "radix_select_hist: bad sizes");
+  if (capacity == 0) return PRL_OK;
+  PRL_REQUIRE(keys && counter && state && hist, PRL_ERR_BAD_ARG, "radix_select_hist: null pointer");
+  const int64_t need = (capacity + 255) / 256, cap = (int64_t)sm_count() * 4;
+  radix_hist_kernel<<<(int)(need < cap ? need : cap), 256, 0, (cudaStream_t)stream>>>(keys, counter, capacity, state, shift, bits, hist);
+  return check_launch("radix_hist_kernel");
+}
+
+int prl_radix_select_pick(unsigned long long* hist, int64_t* state, int32_t shift, int32_t bits, void* stream) {
+  PRL_REQUIRE(shift >= 0 && bits >= 5 && bits <= 11 && shift + bits <= 32, PRL_ERR_BAD_ARG, "radix_select_pick: bad sizes");
+  PRL_REQUIRE(hist && state, PRL_ERR_BAD_ARG, "radix_select_pick: null pointer");
+  radix_pick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(hist, state, shift, bits);
+  return check_launch("radix_pick_kernel");
 }
 
 int prl_logits_stats_f32(const float* logits, const int64_t* ids, int64_t rows, int64_t seq, int64_t V, float inv_temp,

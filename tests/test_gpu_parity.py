@@ -3,6 +3,7 @@ C-ABI library and compared with the CPU oracle (`oracle/`) and with the golden f
 the unmodified reference.  Tolerances are the ones BASELINE.json's north_star states:
 advantages bit-exact; logp / entropy <= 1e-3 abs; loss <= 1e-4 rel; gradients <= 1e-2 rel-L2."""
 
+import math
 import os
 
 import numpy as np
@@ -436,6 +437,41 @@ def test_next_row_on_device_logging_stats(P):
         np.testing.assert_allclose(got[f"{key}/max"], ref.max(), rtol=1e-6)
         assert got[f"{key}/count"] == len(ref)
     assert got["all/count"] == 1000 + 16384 + 77 and st.compute_stats() == {}
+    # the median is torch.median's lower median of the same fp32 values, bit for bit
+    assert got["entropy/median"] == torch.median(torch.from_numpy(np.concatenate(vals))).item()
+    np.testing.assert_allclose(got["probs/median"], torch.median(torch.exp(cu(np.concatenate(vals)))).item(), rtol=2e-7)  # expf vs ATen exp
+
+
+@pytest.mark.parametrize("n,kind", [(1, "normal"), (2, "normal"), (7, "ties"), (100000, "ties"), (300001, "normal"), (4096, "signed-zero-inf"),
+                                    (70000, "many-adds")])
+def test_next_row_exact_median_by_radix_select(P, n, kind):
+    """`{key}/median` == torch.median (lower median) over every masked value of every add: odd / even counts, heavy ties, negative
+    values, +-0, +-inf, a buffer that has to grow, an all-masked add, and nan propagation."""
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, generator=g) * 3
+    if kind == "ties":
+        x = torch.round(x)  # a handful of distinct values, many duplicates
+    if kind == "signed-zero-inf":
+        x[::7] = 0.0
+        x[1::7] = -0.0
+        x[2::97] = float("inf")
+        x[3::89] = float("-inf")
+    mask = torch.rand(n, generator=g) < 0.7
+    mask[0] = True
+    st = P.TensorStats()
+    pieces = 9 if kind == "many-adds" else 2
+    for part, pm in zip(x.chunk(pieces), mask.chunk(pieces)):
+        st.add("v", part.cuda(), pm.cuda())
+    st.add("v", torch.ones(50).cuda(), torch.zeros(50, dtype=torch.bool).cuda())  # an all-masked micro-batch adds nothing
+    st.add("w", x.cuda())                                                          # no mask
+    got = st.compute_stats()
+    assert got["v/median"] == torch.median(x[mask]).item() and got["v/count"] == int(mask.sum())
+    assert got["w/median"] == torch.median(x).item()
+    if kind == "normal" and n > 2:
+        st.add("v", x.cuda(), mask.cuda())
+        st.add("v", torch.tensor([float("nan")]).cuda())
+        assert math.isnan(st.compute_stats()["v/median"])  # torch.median propagates nan
+    assert P.TensorStats(median=False).compute_stats() == {}
 
 
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
