@@ -46,6 +46,30 @@ def main():
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
 
+    # on-device logging statistics across ranks (row N1): every rank logs different values; mean / median / min / max must be
+    # those of the union (the reference all-gathers every masked token, trainer/utils.py:241-252)
+    gs = torch.Generator(device="cuda").manual_seed(77 + rank)
+    vals = torch.randn(5000 + 1000 * rank, device="cuda", generator=gs).round(decimals=2)
+    msk = torch.rand(vals.numel(), device="cuda", generator=gs) < 0.5
+    st = P.TensorStats()
+    st.add("x", vals[:3000], msk[:3000])
+    st.add("x", vals[3000:], msk[3000:])
+    got = st.compute_stats()
+    mine = vals[msk]
+    sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([mine.numel()], device="cuda"))
+    padded = torch.zeros(max(int(x) for x in sizes), device="cuda")
+    padded[: mine.numel()] = mine
+    bufs = [torch.zeros_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded)
+    union = torch.cat([b[: int(n)] for b, n in zip(bufs, sizes)])
+    ok_s = (got["x/median"] == torch.median(union).item() and got["x/count"] == union.numel() and got["x/min"] == union.min().item()
+            and got["x/max"] == union.max().item() and abs(got["x/mean"] - union.double().mean().item()) < 1e-9)
+    print(f"rank {rank}: TensorStats over {union.numel()} values of {world} ranks: median {got['x/median']} -> {'OK' if ok_s else 'MISMATCH'}", flush=True)
+    flag2 = torch.tensor([0 if ok_s else 1], device="cuda")
+    dist.all_reduce(flag2)
+    flag += flag2
+
     if perf:
         def step():
             hh = hidden.detach().requires_grad_(True)
