@@ -106,6 +106,14 @@ int prl_scale_f32(const float* a, const float* scale, float* out, int64_t n, voi
 int prl_logits_stats_f32(const float* logits, const int64_t* ids, int64_t rows, int64_t seq, int64_t V,
                          float inv_temp, int32_t shift, float* logp, float* entropy, void* stream);
 
+/* Backward of the pass above w.r.t. the materialised logits (what autograd does behind rl/loss.py:26-30 when the
+ * reference trainer is kept unchanged): dlogits[q, v] = dlogp[r] * inv_temp * (1[v == ids[r]] - softmax(z[r])_v), with
+ * r = q for shift == 0, r = q + 1 (and zero for the last position of each `seq`-long row) for shift != 0.
+ * logp[rows] is the forward's output (the row's logsumexp is rebuilt from it).  One read and one write of [rows, V]. */
+int prl_logits_logsoftmax_bwd_f32(const float* logits, const int64_t* ids, const float* logp, const float* dlogp,
+                                  int64_t rows, int64_t seq, int64_t V, float inv_temp, int32_t shift, float* dlogits,
+                                  void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused LM head: hidden[T,H] x W[V,H]^T with an online (max, sum-exp, sum exp*z, target) epilogue;
  * the [T,V] logits never reach HBM.  Replaces the chain

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "prl_radix_select_hist": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "prl_radix_select_pick": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "prl_logits_stats_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_int32, c_void_p, c_void_p, c_void_p]),
+    "prl_logits_logsoftmax_bwd_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_int32, c_void_p, c_void_p]),
     "prl_lmhead_fwd_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int64]),
     "prl_lmhead_fwd": (
         c_int32,

@@ -463,6 +463,46 @@ __global__ void __launch_bounds__(256) logits_stats_kernel(const float* __restri
   }
 }
 
+// backward of the same pass w.r.t. the materialised logits (autograd of rl/loss.py:26-30 as the reference trainer runs it):
+//   dlogits[q, v] = g[r] / tau * (1[v == ids[r]] - exp(logits[q, v] / tau - lse[r])),  r = q (+1 if shift; none for the last position)
+// lse is rebuilt from the forward's logp: lse[r] = logits[q, ids[r]] / tau - logp[r].  One read + one write of [rows, V] fp32.
+__global__ void __launch_bounds__(256) logits_logsoftmax_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ ids,
+                                                                    const float* __restrict__ logp, const float* __restrict__ g,
+                                                                    int64_t rows, int64_t seq, int64_t V, float inv_temp, int shift,
+                                                                    float* __restrict__ dlogits) {
+  for (int64_t q = blockIdx.x; q < rows; q += gridDim.x) {
+    const float* src = logits + q * V;
+    float* dst = dlogits + q * V;
+    const bool vec = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0;
+    const int64_t V4 = vec ? V / 4 : 0;
+    const bool has = !shift || (q % seq) + 1 < seq;
+    if (!has) {  // the position shift_logits drops (rl/loss.py:54): no gradient
+      for (int64_t k = threadIdx.x; k < V4; k += blockDim.x) reinterpret_cast<float4*>(dst)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t v = V4 * 4 + threadIdx.x; v < V; v += blockDim.x) dst[v] = 0.f;
+      continue;
+    }
+    const int64_t r = q + (shift ? 1 : 0);
+    const int64_t id = ids[r];
+    const float gr = g[r] * inv_temp;
+    const float lse = src[id] * inv_temp - logp[r];
+    for (int64_t k = threadIdx.x; k < V4; k += blockDim.x) {
+      const float4 x = reinterpret_cast<const float4*>(src)[k];
+      float4 d;
+      d.x = -gr * __expf(x.x * inv_temp - lse);
+      d.y = -gr * __expf(x.y * inv_temp - lse);
+      d.z = -gr * __expf(x.z * inv_temp - lse);
+      d.w = -gr * __expf(x.w * inv_temp - lse);
+      const int64_t off = id - 4 * k;
+      if (off == 0) d.x += gr;
+      if (off == 1) d.y += gr;
+      if (off == 2) d.z += gr;
+      if (off == 3) d.w += gr;
+      reinterpret_cast<float4*>(dst)[k] = d;
+    }
+    for (int64_t v = V4 * 4 + threadIdx.x; v < V; v += blockDim.x) dst[v] = -gr * __expf(src[v] * inv_temp - lse) + (v == id ? gr : 0.f);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // masked running moments for logging (train.py:313-333 + trainer/utils.py:228-256): 5 B/element read, fp64 sums,
 // fixed-order final combine (deterministic), accumulator updated in place.
@@ -819,6 +859,18 @@ int prl_logits_stats_f32(const float* logits, const int64_t* ids, int64_t rows, 
   logits_stats_kernel<<<(int)(rows < cap ? rows : cap), 256, 0, (cudaStream_t)stream>>>(logits, ids, rows, seq, V, inv_temp, shift,
                                                                                         logp, entropy);
   return check_launch("logits_stats_kernel");
+}
+
+int prl_logits_logsoftmax_bwd_f32(const float* logits, const int64_t* ids, const float* logp, const float* dlogp, int64_t rows,
+                                  int64_t seq, int64_t V, float inv_temp, int32_t shift, float* dlogits, void* stream) {
+  PRL_REQUIRE(rows >= 0 && seq >= 1 && V >= 1, PRL_ERR_BAD_ARG, "logits_logsoftmax_bwd: bad sizes");
+  if (rows == 0) return PRL_OK;
+  PRL_REQUIRE(logits && ids && logp && dlogp && dlogits, PRL_ERR_BAD_ARG, "logits_logsoftmax_bwd: null pointer");
+  PRL_REQUIRE(logits != dlogits, PRL_ERR_BAD_ARG, "logits_logsoftmax_bwd: in-place operation is not supported");
+  const int64_t cap = (int64_t)sm_count() * 16;
+  logits_logsoftmax_bwd_kernel<<<(int)(rows < cap ? rows : cap), 256, 0, (cudaStream_t)stream>>>(logits, ids, logp, dlogp, rows, seq, V,
+                                                                                                 inv_temp, shift, dlogits);
+  return check_launch("logits_logsoftmax_bwd_kernel");
 }
 
 }  // extern "C"

@@ -144,13 +144,43 @@ def _stats(logits: torch.Tensor, index: torch.Tensor | None, inv_temp: float, sh
     return logp, ent
 
 
+class _LogitsLogProb(torch.autograd.Function):
+    """log-prob of `index` under softmax(logits / tau) (optionally shifted) on MATERIALISED logits, differentiable w.r.t. the
+    logits: forward = one read of [B,S,V], backward = one read + one write (the reference's autograd chain makes ~6 passes)."""
+
+    @staticmethod
+    def forward(ctx, logits, index, inv_temp, shift):
+        logp, _ = _stats(logits, index, inv_temp, shift, True, False)
+        ctx.save_for_backward(logits, index, logp)
+        ctx.cfg = (inv_temp, shift)
+        return logp
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, index, logp = ctx.saved_tensors
+        inv_temp, shift = ctx.cfg
+        lib = _lib.load()
+        B, S, V = logits.shape
+        x = logits.detach().contiguous().float()
+        idx = index.contiguous().to(torch.int64)
+        gg = g.detach().contiguous().float()
+        d = torch.empty(B, S, V, dtype=torch.float32, device=x.device)
+        rc = lib.prl_logits_logsoftmax_bwd_f32(_lib.ptr(x), _lib.ptr(idx), _lib.ptr(logp), _lib.ptr(gg), B * S, S, V, float(inv_temp),
+                                               1 if shift else 0, _lib.ptr(d), _lib.stream())
+        _lib.check(rc, "prl_logits_logsoftmax_bwd_f32")
+        return d.to(logits.dtype), None, None, None
+
+
 def selective_log_softmax(logits: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
-    """`log_softmax(logits)[index]` in one pass over materialised logits (rl/loss.py:13-39).  Forward
-    only: the differentiable path is `fused_lm_head_logprobs_entropy` (lm_head.py), which never
-    materialises the logits."""
+    """`log_softmax(logits)[index]` in one pass over materialised logits (rl/loss.py:13-39; fp32, bf16 and fp16 inputs, the
+    statistics are always fp32).  Differentiable w.r.t. `logits` (one more pass in the backward), so the reference trainer's
+    `selective_log_softmax(shift_logits(logits) / temperature, input_ids)` keeps working unchanged; the fast path that
+    never materialises fp32 logits is `fused_lm_head_logprobs_entropy` (lm_head.py)."""
     if logits.requires_grad and torch.is_grad_enabled():
-        raise RuntimeError("selective_log_softmax on materialised logits is forward-only here; "
-                           "use fused_lm_head_logprobs_entropy for the differentiable path")
+        _lib.require_cuda(logits, index)
+        if logits.dim() != 3 or tuple(index.shape) != tuple(logits.shape[:2]):
+            raise ValueError("logits must be [batch, seq, vocab] and index [batch, seq]")
+        return _LogitsLogProb.apply(logits, index, 1.0, False)
     return _stats(logits, index, 1.0, False, True, False)[0]
 
 
@@ -162,6 +192,12 @@ def compute_entropy(shifted_logits: torch.Tensor) -> torch.Tensor:
 def shifted_logprobs_entropy(logits: torch.Tensor, input_ids: torch.Tensor, temperature: float):
     """rl/train.py:286-288 + :302-303 on materialised logits in ONE pass: shift, / temperature,
     log-prob of `input_ids`, entropy.  Returns (logprobs[B,S], entropy[B,S])."""
+    if logits.requires_grad and torch.is_grad_enabled():  # log-probs differentiable, entropy detached (train.py:302-303)
+        _lib.require_cuda(logits, input_ids)
+        if logits.dim() != 3 or tuple(input_ids.shape) != tuple(logits.shape[:2]):
+            raise ValueError("logits must be [batch, seq, vocab] and input_ids [batch, seq]")
+        logp = _LogitsLogProb.apply(logits, input_ids, 1.0 / float(temperature), True)
+        return logp, _stats(logits, None, 1.0 / float(temperature), True, False, True)[1]
     return _stats(logits, input_ids, 1.0 / float(temperature), True, True, True)
 
 

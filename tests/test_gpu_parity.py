@@ -233,6 +233,53 @@ def test_gemm_engine(P, a_mn, b_mn, M, N, K):
     assert (C - 2 * want).abs().max().item() <= 4e-3 * max(1.0, want.abs().max().item())
 
 
+def test_reference_trainer_chain_with_drop_in_functions_is_differentiable(P):
+    """the reference's own chain (train.py:285-310) with ONLY the imports swapped — materialised logits,
+    `shift_logits`, `/ temperature`, `selective_log_softmax`, `compute_loss`, `compute_entropy` — gives the torch chain's loss and
+    gradients (`selective_log_softmax` is differentiable w.r.t. the logits)."""
+    from oracle import torch_port
+
+    T, H, V, tau = 300, 64, 1000, 0.7
+    hidden, weight, ids = _mk(T, H, V, 77, peaked=True)
+    rng = np.random.default_rng(2)
+    lens = [120, 100, 80]
+    pos = cu(np.concatenate([np.arange(n) for n in lens])).unsqueeze(0)
+    adv, mask = cu(rng.standard_normal(T).astype(np.float32)), cu(rng.random(T) < 0.8)
+    old = cu(-rng.random(T).astype(np.float32) * 3)
+    i_d = ids.cuda()
+    h0 = hidden.cuda().requires_grad_(True)
+    w0 = weight.cuda().requires_grad_(True)
+    loss0, lp0, ent0 = torch_port.micro_step_cpu(h0, w0, i_d, pos[0], old, adv, mask, tau, "token", False, 8.0, int(mask.sum()))
+
+    for variant in ("reference-calls", "one-pass"):
+        h = hidden.cuda().requires_grad_(True)
+        w = weight.cuda().requires_grad_(True)
+        logits = (h @ w.t()).float().unsqueeze(0).contiguous()                         # train.py:285
+        if variant == "reference-calls":
+            shifted = P.shift_logits(logits) / tau                                     # train.py:286-287
+            lp = P.selective_log_softmax(shifted, i_d.unsqueeze(0))                    # train.py:288
+            with torch.no_grad():
+                ent = P.compute_entropy(shifted)                                       # train.py:302-303
+        else:
+            lp, ent = P.shifted_logprobs_entropy(logits, i_d.unsqueeze(0), tau)        # the same three steps in one pass
+        seg = P.get_response_lengths(pos)                                              # train.py:291
+        assert seg == lens
+        loss, _ = P.compute_loss(lp.squeeze().split(seg), old.split(seg), adv.split(seg), mask.split(seg), P.LossConfig(), int(mask.sum()))
+        loss.backward()                                                                # train.py:310
+        assert (lp[0] - lp0).abs().max().item() < 1e-4 and (ent[0] - ent0).abs().max().item() < 1e-4
+        assert abs(loss.item() - loss0.item()) <= 1e-4 * abs(loss0.item()) + 1e-7
+        assert rel_l2(h.grad.float().cpu().numpy(), h0.grad.float().cpu().numpy()) < 2e-3, variant
+        assert rel_l2(w.grad.float().cpu().numpy(), w0.grad.float().cpu().numpy()) < 2e-3, variant
+    # low-precision logits (the reference's bf16 branch, loss.py:31-38): gradient comes back in the logits' dtype
+    z = torch.randn(2, 9, 513, device="cuda").bfloat16().requires_grad_(True)
+    idx = torch.randint(0, 513, (2, 9), device="cuda")
+    gw = torch.randn(2, 9, device="cuda")
+    (P.selective_log_softmax(z, idx) * gw).sum().backward()
+    zr = z.detach().float().requires_grad_(True)
+    (torch.log_softmax(zr, -1).gather(-1, idx.unsqueeze(-1)).squeeze(-1) * gw).sum().backward()
+    assert z.grad.dtype == torch.bfloat16 and (z.grad.float() - zr.grad).abs().max().item() <= 2.0 ** -8 * zr.grad.abs().max().item() + 1e-6
+
+
 # ------------------------------------------------------------------------------- fused LM head
 def _mk(T, H, V, seed, peaked=False):
     g = torch.Generator().manual_seed(seed)
