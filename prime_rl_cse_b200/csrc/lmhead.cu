@@ -170,12 +170,14 @@ static void set_hints(GemmParams& p, const char* family, int a, int b, int c) {
 template <int CG, int MS, bool A_MN, bool B_MN, int EPI>
 static int launch_gemm_cg(GemmParams p /* by value: the profiling knobs below edit the copy */, cudaStream_t st, const char* name) {
   using C = Cfg<CG, MS, EPI>;
-  static bool attr_set = false;
+  static bool attr_set[64] = {};  // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
   auto kern = gemm_kernel<CG, MS, A_MN, B_MN, EPI>;
-  if (!attr_set) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   if (p.num_items < 1) return PRL_OK;
   if (env_long("PRL_DEBUG_NOSTORE", 0)) p.epi.flags |= ST_DEBUG_SKIP;
