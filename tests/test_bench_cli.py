@@ -50,3 +50,8 @@ def test_b200_arm_json_contract():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"]) and d["roofline"]["bound"] == "tensor"
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"])
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    # both backward modes run and say which one they are; the saved-logits one launches fewer kernels per micro-batch
+    assert d["config"]["lm_head_backward"].startswith("saved-logits") and "dz_from_saved_logits_kernel" in d["hbm_kernels"]
+    r = run(["--workload", "tiny", "--steps", "3", "--warmup", "3", "--lm-head-backward", "recompute", "--no-cpu-baseline", "--no-torch-baseline"])
+    assert r["config"]["lm_head_backward"].startswith("recompute") and r["value"] > 0 and "hbm_kernels" not in r
+    assert r["frac_of_peak"]["executed_over_algorithmic"] > d["frac_of_peak"]["executed_over_algorithmic"] == 1.0
