@@ -66,6 +66,30 @@ def test_argument_validation_needs_no_gpu(lib):
     assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 0, 16, 100, 0, 1.0, 1, None, 104, None, 0, None, 0, 0, 0, None) == 0  # T == 0
 
 
+def test_header_is_plain_c_and_links_from_c(lib, tmp_path):
+    """The boundary is a C ABI, not a C++ or torch one: a C99 translation unit that includes the header compiles with
+    -pedantic, links against the shared library and gets the documented error code back (no GPU involved)."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "client.c"
+    src.write_text(
+        '#include "prl_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  int rc = prl_advantages_f32(NULL, NULL, 3, 2, PRL_ADV_DRGRPO, NULL, NULL, NULL, NULL);\n"
+        '  printf("%d %d %s|%s\\n", prl_version(), rc, prl_strerror(rc), prl_last_error_detail());\n'
+        "  return (rc == PRL_ERR_BAD_ARG && prl_lmhead_saved_logits_ld(1003) >= 1003) ? 0 : 1;\n}\n")
+    libdir = os.path.dirname(lib.LIB_PATH)
+    exe = tmp_path / "client"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-l:" + os.path.basename(lib.LIB_PATH), "-Wl,-rpath," + libdir]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "samples_per_problem" in r.stdout, r.stdout + r.stderr
+
+
 def test_no_cpu_fallback():
     import prime_rl_cse_b200 as P
 
