@@ -245,6 +245,7 @@ def run_b200(args):
         bwd_mode = "saved" if P.saved_logits_policy(T, V) else "recompute"
     save_flag = bwd_mode == "saved"
     saved_blk = torch.empty(T, int(lib.prl_lmhead_saved_logits_ld(V)), dtype=torch.bfloat16, device=dev) if save_flag else None
+    ws_bs = torch.empty(max(int(lib.prl_lmhead_bwd_saved_workspace_bytes(T, H, V)), 16), dtype=torch.uint8, device=dev)
 
     Wd = W.detach()
 
@@ -265,7 +266,7 @@ def run_b200(args):
                 cfg.ratio_length_norm, cfg.clip_ratio, loss_scale)
             if save_flag:
                 P.lm_head_backward_saved_raw(hid, Wd, ids, lse, dlogp, 1.0 / mb["temperature"], saved_blk, dweight=main_grad,
-                                             dweight_accumulate=True)
+                                             dweight_accumulate=True, workspace=ws_bs)
             else:
                 P.lm_head_backward_raw(hid, Wd, ids, lse, dlogp, 1.0 / mb["temperature"], dweight=main_grad, dweight_accumulate=True,
                                        workspace=ws_b)
@@ -375,7 +376,7 @@ def run_b200(args):
             vc, nchunks = V, 1
             fwd_s = lambda: P.lm_head_forward_save_raw(hid, Wd, ids, 1.0, workspace=ws_f, saved=saved_blk)
             bwd_s = lambda m: P.lm_head_backward_saved_raw(hid, Wd, ids, lse, dlogp, 1.0, saved_blk, dweight=main_grad,
-                                                           dweight_accumulate=True, phase_mask=m)
+                                                           dweight_accumulate=True, phase_mask=m, workspace=ws_bs)
             fam["lmhead_fwd_save_kernel"] = dict(ms_per_launch=ev_time(fwd_s, 8), launches_per_mb=1, flops_per_launch=2.0 * T * H * V)
             bwd_s(1)  # the block now holds real dlogits (tensor-core power is data dependent), as inside the step
             for name, mask in (("lmhead_bwd_dhidden_kernel", 2), ("lmhead_bwd_dweight_kernel", 4)):

@@ -173,8 +173,11 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
  *     1/temperature scaling) of source row r to saved_logits[r * saved_ld + v], r < T - shift, v < V.
  *   prl_lmhead_bwd_saved: converts saved_logits in place to dlogits (bit-identical to what the recompute
  *     backward produces; the block is CONSUMED), then runs the d_hidden / d_weight GEMMs over the whole
- *     vocabulary in one launch each (no vocab chunks, no fp32 d_hidden accumulator, no workspace).
+ *     vocabulary in one launch each (no vocab chunks).
  *     phase_mask: bit 0 = logits -> dlogits pass, bit 1 = d_hidden GEMM, bit 2 = d_weight GEMM; 0 = all.
+ *     workspace (optional, prl_lmhead_bwd_saved_workspace_bytes; 0 bytes at the large shapes): an fp32 [T, H]
+ *     accumulator that lets the d_hidden GEMM split K in two when T x H gives too few output tiles to fill
+ *     the 148 SMs; without it the GEMM runs unsplit (same result up to fp32 summation order).
  * saved_logits: 16-byte aligned, saved_ld >= V, saved_ld % 8 == 0, at least T * saved_ld bf16 elements.
  * ---------------------------------------------------------------------------------------- */
 int64_t prl_lmhead_saved_logits_ld(int64_t V);
@@ -186,7 +189,8 @@ int prl_lmhead_bwd_saved(const void* hidden, const void* weight, const int64_t* 
                          const float* dlogp, int64_t T, int32_t H, int64_t V, int64_t v_offset, float inv_temp,
                          int32_t shift, void* saved_logits, int64_t saved_ld, void* d_hidden,
                          int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw,
-                         int32_t phase_mask, void* stream);
+                         int32_t phase_mask, void* workspace, size_t workspace_bytes, void* stream);
+size_t prl_lmhead_bwd_saved_workspace_bytes(int64_t T, int32_t H, int64_t V);
 
 /* ------------------------------------------------------------------------------------------
  * On-device logging statistics ("next" row N1).  Replaces the per-micro-batch boolean-index + blocking .to("cpu")

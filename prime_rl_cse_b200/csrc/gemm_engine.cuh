@@ -76,6 +76,8 @@ struct GemmParams {
   int32_t tiles_per_split, n_splits, group_m, num_items;
   int32_t max_stages;   // > 0: use at most this many of the smem ring's stages (prefetch-depth experiments)
   int32_t split_group;  // 0: m-tile fastest inside a band; S > 0: splits fastest in groups of S (neighbouring workers share an m-tile)
+  int32_t k_splits;     // > 1: every output tile is produced by k_splits items over disjoint k ranges (epilogue must reduce-add)
+  int32_t k_per_split;  // k-blocks per item (== k_blocks without k-splitting)
   uint64_t a_desc_hi, b_desc_hi;  // smem descriptor templates (everything but the start address)
   uint32_t a_kstep, b_kstep;      // byte advance of the start address per UMMA_K step
   uint64_t hint_a, hint_b, hint_c;  // L2 eviction priority of the A / B loads and of the epilogue's stores
@@ -83,11 +85,12 @@ struct GemmParams {
 };
 
 struct Item {
-  int m_tile, split, n_begin, n_count;
+  int m_tile, split, n_begin, n_count, k_begin, k_count;
 };
 
 __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
-  const int per_band = p.group_m * p.n_splits;
+  const int ksp = p.k_splits > 1 ? p.k_splits : 1;  // k-splits of one tile are neighbouring items (they run concurrently)
+  const int per_band = p.group_m * p.n_splits * ksp;
   const int band = item / per_band;
   const int m0 = band * p.group_m;
   const int rows = min(p.group_m, p.m_tiles - m0);
@@ -101,9 +104,14 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
     const int r = idx - g * per_grp;
     it.split = g * p.split_group + r % s_here;
     it.m_tile = m0 + r / s_here;
+    it.k_begin = 0;
+    it.k_count = p.k_blocks;
   } else {
-    it.split = idx / rows;
+    const int vs = idx / rows;  // (n split, k split)
     it.m_tile = m0 + idx % rows;
+    it.split = vs / ksp;
+    it.k_begin = (vs - it.split * ksp) * p.k_per_split;
+    it.k_count = min(p.k_per_split, p.k_blocks - it.k_begin);
   }
   it.n_begin = it.split * p.tiles_per_split;
   it.n_count = min(p.tiles_per_split, p.n_tiles - it.n_begin);
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
         const int m0 = it.m_tile * C::kRowsPerTile + crank * BLOCK_M;
         for (int nt = it.n_begin; nt < it.n_begin + it.n_count; ++nt) {
           const int n0 = nt * BLOCK_N + rank * C::kBRows;
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
+          for (int kb = it.k_begin; kb < it.k_begin + it.k_count; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
             // profiling aid (PRL_DEBUG_SKIPB=1): skip the B load on odd k-blocks (stale data, WRONG results) to measure how
             // much of the power budget the L2->SM operand traffic costs
@@ -507,7 +515,7 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
             ptx::mbar_wait(&tempty_bar[1], acc_phase ^ 1);
           }
           ptx::tc_fence_after();
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
+          for (int kb = 0; kb < it.k_count; ++kb) {
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
             const uint32_t sa = ptx::smem_u32(smem_a + stage * C::kAStage);

@@ -206,6 +206,26 @@ static void set_tiling(GemmParams& p, int64_t M, int64_t N, int64_t K, int epi) 
   p.m_tiles = (int)((M + bm - 1) / bm);
   p.n_tiles = (int)((N + BLOCK_N - 1) / BLOCK_N);
   p.k_blocks = (int)((K + BLOCK_K - 1) / BLOCK_K);
+  p.k_splits = 1;
+  p.k_per_split = p.k_blocks;
+}
+
+// Two k-splits per output tile when that fills the machine markedly better (few output tiles, long K: d_hidden at small T x H).
+// Only 1 or 2: with two partial sums the fp32 reduce-add into a zeroed accumulator gives the same bits in either arrival order.
+static int pick_k_splits(int64_t M, int64_t N, int64_t K) {
+  const long forced = env_long("PRL_K_SPLITS", 0);
+  if (forced == 1 || forced == 2) return (int)forced;
+  const int64_t bm = (int64_t)BLOCK_M * cta_group() * msub(EPI_STORE);
+  const int64_t items = ((M + bm - 1) / bm) * ((N + BLOCK_N - 1) / BLOCK_N), w = workers();
+  const int64_t kb = (K + BLOCK_K - 1) / BLOCK_K;
+  if (kb < 16) return 1;
+  const double one = (double)((items + w - 1) / w), two = (double)((2 * items + w - 1) / w) / 2.0;
+  return two < 0.97 * one ? 2 : 1;
+}
+static void set_k_splits(GemmParams& p, int ks) {
+  if (ks <= 1) return;
+  p.k_per_split = (p.k_blocks + ks - 1) / ks;
+  p.k_splits = (p.k_blocks + p.k_per_split - 1) / p.k_per_split;
 }
 
 // one item per output tile, m-tiles in bands of `band` 128-row blocks (PRL_GROUP_M overrides) for L2 reuse of the B operand.
@@ -217,7 +237,7 @@ static void schedule_tiles(GemmParams& p, int band = 8) {
   p.group_m = (int)env_long("PRL_GROUP_M", band) / (cta_group() * msub(EPI_STORE));
   if (p.group_m < 1) p.group_m = 1;
   p.max_stages = (int)env_long("PRL_TILE_STAGES", 0);
-  p.num_items = p.m_tiles * p.n_splits;
+  p.num_items = p.m_tiles * p.n_splits * (p.k_splits > 1 ? p.k_splits : 1);
 }
 
 // items = (m_tile, n-range): pick the number of vocab splits that minimises the static makespan
@@ -466,6 +486,7 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
                             int64_t T, int32_t H, void* d_hidden, int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype,
                             int32_t accumulate_dw, int32_t phase_mask, bool first, bool last, int64_t nchunks, float* dh_acc,
                             int band, cudaStream_t st) {
+  const int64_t vc_full = nchunks > 1 ? vc : vce;  // every chunk of one backward takes the same k-split decision
   // ---- K2: d_hidden[T,H] += dz[T,vce] x W[c0:c0+vce, :]   (A K-major, B MN-major) ----
   if (d_hidden && (phase_mask & 2)) {
     GemmParams p;
@@ -475,12 +496,21 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
     rc = make_operand_map(&p.tma_b, W + c0 * H, true, H, vce, H, BLOCK_N);
     if (rc) return rc;
     set_tiling(p, T, H, vce, EPI_STORE);
+    const bool tma = epi_tma_enabled();
+    // k-splits need an fp32 accumulator that is reduced into: d_hidden itself (fp32 output) or dh_acc
+    const int ks = (tma && (d_hidden_f32 || dh_acc)) ? pick_k_splits(T, H, vc_full) : 1;
+    set_k_splits(p, ks);
+    const bool split = p.k_splits > 1;
     schedule_tiles(p, band);
     make_desc_defaults(p, false, true);
     p.epi.m_rows = T;
     p.epi.n_cols = H;
     p.epi.ldc = H;
-    const bool tma = epi_tma_enabled();
+    if (split && first) {  // every item of every chunk reduce-adds into a zeroed accumulator
+      cudaError_t e = cudaMemsetAsync(d_hidden_f32 ? d_hidden : (void*)dh_acc, 0, (size_t)T * H * sizeof(float), st);
+      if (e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(d_hidden accumulator)");
+    }
+    if (split) first = false;
     if (d_hidden_f32) {
       p.epi.c_f32 = reinterpret_cast<float*>(d_hidden);
       p.epi.flags = ST_STORE_F32 | (first ? 0 : ST_LOAD_F32);
@@ -488,7 +518,7 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
         rc = make_output_map(&p.tma_c, d_hidden, T, H, H, true);
         p.epi.flags |= ST_TMA;
       }
-    } else if (tma && nchunks == 1) {
+    } else if (tma && nchunks == 1 && !split) {
       p.epi.c_bf16 = reinterpret_cast<__nv_bfloat16*>(d_hidden);
       p.epi.flags = ST_STORE_BF16 | ST_TMA;
       rc = make_output_map(&p.tma_c, d_hidden, T, H, H, false);
@@ -507,7 +537,7 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
     set_hints(p, "DH", 0, 0, 0);
     rc = launch_gemm<false, true, EPI_STORE>(p, st, "lmhead_bwd_dhidden_kernel");
     if (rc) return rc;
-    if (last && tma && !d_hidden_f32 && nchunks > 1) {
+    if (last && tma && !d_hidden_f32 && (nchunks > 1 || split)) {
       const int64_t n = T * (int64_t)H;
       const int64_t need = (n / 8 + 255) / 256 + 1, cap = (int64_t)sm_count() * 8;
       f32_to_bf16_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(dh_acc, reinterpret_cast<__nv_bfloat16*>(d_hidden), n);
@@ -635,10 +665,16 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
   return PRL_OK;
 }
 
+size_t prl_lmhead_bwd_saved_workspace_bytes(int64_t T, int32_t H, int64_t V) {
+  // an fp32 [T, H] accumulator, needed only when the d_hidden GEMM is split along K (few output tiles: small T x H)
+  if (T <= 0 || H <= 0 || V <= 0 || pick_k_splits(T, H, V) <= 1) return 0;
+  return (size_t)T * (size_t)H * sizeof(float) + 1024;
+}
+
 int prl_lmhead_bwd_saved(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T,
                          int32_t H, int64_t V, int64_t v_offset, float inv_temp, int32_t shift, void* saved_logits, int64_t saved_ld,
                          void* d_hidden, int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw,
-                         int32_t phase_mask, void* stream) {
+                         int32_t phase_mask, void* workspace, size_t workspace_bytes, void* stream) {
   PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: bad sizes");
   PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: shift must be 0 or 1");
   PRL_REQUIRE(inv_temp > 0.f && inv_temp < INFINITY, PRL_ERR_BAD_ARG, "lmhead_bwd_saved: temperature must be positive and finite");
@@ -658,8 +694,12 @@ int prl_lmhead_bwd_saved(const void* hidden, const void* weight, const int64_t* 
     const int rc = check_launch("dz_from_saved_logits_kernel");
     if (rc) return rc;
   }
+  // optional fp32 [T, H] accumulator (1024-byte aligned inside the workspace); without it the d_hidden GEMM is not k-split
+  float* dh_acc = nullptr;
+  if (workspace && workspace_bytes >= (size_t)T * H * sizeof(float) + 1024)
+    dh_acc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   return lmhead_bwd_gemms(hidden, reinterpret_cast<const __nv_bfloat16*>(weight), dz, saved_ld, 0, V, T, H, d_hidden, d_hidden_f32, d_weight,
-                          d_weight_dtype, accumulate_dw, phase_mask, true, true, 1, nullptr, 4, st);
+                          d_weight_dtype, accumulate_dw, phase_mask, true, true, 1, dh_acc, 4, st);
 }
 
 int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn_major, int32_t b_mn_major,

@@ -106,7 +106,8 @@ def _dweight_arg(dweight, want_dweight, dweight_accumulate, V, H, dev):
 
 
 def lm_head_backward_saved_raw(hidden, weight, ids, lse, dlogp, inv_temp, saved, shift=True, v_offset=0, want_dhidden=True,
-                               dweight=None, dweight_accumulate=False, want_dweight=True, dhidden_f32=False, phase_mask=0):
+                               dweight=None, dweight_accumulate=False, want_dweight=True, dhidden_f32=False, phase_mask=0,
+                               workspace=None):
     """Backward from the logits kept by `lm_head_forward_save_raw`.  `saved` is overwritten (it holds the bf16 dlogits
     afterwards).  Returns (d_hidden, d_weight) like `lm_head_backward_raw`."""
     lib = _lib.load()
@@ -119,10 +120,14 @@ def lm_head_backward_saved_raw(hidden, weight, ids, lse, dlogp, inv_temp, saved,
     if want_dhidden:
         dh = torch.empty(T, H, dtype=torch.float32 if dhidden_f32 else torch.bfloat16, device=dev)
     dweight, dt, dweight_accumulate = _dweight_arg(dweight, want_dweight, dweight_accumulate, V, H, dev)
+    nb = lib.prl_lmhead_bwd_saved_workspace_bytes(T, H, V) if want_dhidden else 0
+    ws = None
+    if nb > 0:
+        ws = workspace if workspace is not None and workspace.numel() >= nb else _ws(nb, dev)
     rc = lib.prl_lmhead_bwd_saved(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), _lib.ptr(lse), _lib.ptr(dlogp), T, H, V, v_offset,
                                   float(inv_temp), 1 if shift else 0, _lib.ptr(saved), saved.shape[1], _lib.ptr(dh),
                                   1 if dhidden_f32 else 0, _lib.ptr(dweight), dt, 1 if dweight_accumulate else 0, phase_mask,
-                                  _lib.stream())
+                                  _lib.ptr(ws), ws.numel() if ws is not None else 0, _lib.stream())
     _lib.check(rc, "prl_lmhead_bwd_saved")
     return dh, dweight
 

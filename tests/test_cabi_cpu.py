@@ -61,9 +61,12 @@ def test_argument_validation_needs_no_gpu(lib):
         assert ld >= V and ld % 8 == 0
     assert L.prl_lmhead_fwd_save(None, None, None, 8, 16, 100, 0, 100, 1.0, 1, None, None, None, None, None, 96, None, 0, None) == -1
     assert L.prl_lmhead_fwd_save(None, None, None, 8, 16, 100, 0, 100, 1.0, 1, None, None, None, None, 16, 100, None, 0, None) == -1
-    assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 8, 16, 100, 0, 1.0, 1, None, 104, None, 0, None, 0, 0, 0, None) == -1
-    assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 8, 16, 100, 0, 0.0, 1, None, 104, None, 0, None, 0, 0, 0, None) == -1
-    assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 0, 16, 100, 0, 1.0, 1, None, 104, None, 0, None, 0, 0, 0, None) == 0  # T == 0
+    assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 8, 16, 100, 0, 1.0, 1, None, 104, None, 0, None, 0, 0, 0, None, 0, None) == -1
+    assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 8, 16, 100, 0, 0.0, 1, None, 104, None, 0, None, 0, 0, 0, None, 0, None) == -1
+    assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 0, 16, 100, 0, 1.0, 1, None, 104, None, 0, None, 0, 0, 0, None, 0, None) == 0
+    # the optional workspace is only asked for where a K-split of the d_hidden GEMM pays off (few output tiles)
+    assert L.prl_lmhead_bwd_saved_workspace_bytes(16384, 4096, 151936) == 0
+    assert L.prl_lmhead_bwd_saved_workspace_bytes(4096, 1024, 151936) >= 4096 * 1024 * 4
 
 
 def test_header_is_plain_c_and_links_from_c(lib, tmp_path):

@@ -645,6 +645,37 @@ def test_saved_logits_mode_is_the_recompute_mode_bit_for_bit(P, T, H, V, shift):
         assert rel_l2(dh3.cpu().numpy(), dh1.float().cpu().numpy()) < 5e-3
 
 
+def test_dhidden_k_split_matches_unsplit_and_is_deterministic(P):
+    """Few output tiles (small T x H) and a long K: the d_hidden GEMM runs as two k-splits that reduce-add into a zeroed fp32
+    accumulator.  Same result as the unsplit GEMM up to fp32 summation order, and run-to-run identical (two addends commute)."""
+    from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_backward_saved_raw, lm_head_forward_save_raw
+
+    T, H, V, tau = 600, 256, 20000 + 64, 0.8
+    hidden, weight, ids = _mk(T, H, V, 17, peaked=True)
+    h, w, i = hidden.cuda(), weight.cuda(), ids.cuda()
+    g = torch.randn(T, device="cuda") / T
+    out = {}
+    try:
+        for ks in ("1", "2"):
+            os.environ["PRL_K_SPLITS"] = ks
+            for f32 in (False, True):
+                lse = lm_head_forward_save_raw(h, w, i, 1 / tau)[2]
+                a = lm_head_backward_raw(h, w, i, lse, g, 1 / tau, vchunk=V, dhidden_f32=f32)[0]
+                b = lm_head_backward_raw(h, w, i, lse, g, 1 / tau, vchunk=4096, dhidden_f32=f32)[0]
+                blk = lm_head_forward_save_raw(h, w, i, 1 / tau)[4]
+                c = lm_head_backward_saved_raw(h, w, i, lse, g, 1 / tau, blk, dhidden_f32=f32)[0]
+                blk = lm_head_forward_save_raw(h, w, i, 1 / tau)[4]
+                c2 = lm_head_backward_saved_raw(h, w, i, lse, g, 1 / tau, blk, dhidden_f32=f32)[0]
+                assert torch.equal(c, c2) and torch.equal(a, c)  # deterministic; single-chunk recompute == saved
+                out[(ks, f32)] = (a.float(), b.float(), c.float())
+    finally:
+        os.environ.pop("PRL_K_SPLITS", None)
+    for f32 in (False, True):
+        ref = out[("1", f32)][0]
+        for t in out[("2", f32)] + out[("1", f32)][1:]:
+            assert ((t - ref).norm() / ref.norm()).item() < 2e-3
+
+
 def test_saved_logits_policy_and_second_backward(P):
     """Autograd integration: size policy, and a second backward through a retained graph (the kept block is consumed by the
     first one) falls back to the recompute and gives the same gradients."""
