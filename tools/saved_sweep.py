@@ -47,3 +47,7 @@ if "ab" in what:  # interleaved A/B of the candidates (order / temperature effec
             measure("FWDS", {"PRL_FWD_STAGES": st})
         for st in (4, 5):
             measure("FWD", {"PRL_FWD_STAGES": st})
+if "dwc" in what:  # L2 policy of the fp32 reduce-add into main_grad (d_weight GEMM output), interleaved
+    for _ in range(3):
+        for c in (0, 1, 2):
+            measure("SDW", {"PRL_HINT_DW_C": c})
