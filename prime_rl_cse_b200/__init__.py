@@ -20,6 +20,7 @@ from .lm_head import (FusedLMHead, fused_lm_head_logprobs_entropy, lm_head_backw
 from .loss import compute_entropy, compute_loss, selective_log_softmax, shift_logits, shifted_logprobs_entropy
 from .extras import fused_linear_cross_entropy, recompute_logprobs
 from .micro_step import rl_micro_step
+from .rollout_io import DataLoader, FakeDataLoader, save_step, upload_micro_batches
 from .segments import get_response_lengths, segments_from_position_ids
 from .stats import TensorStats
 from .parallel import (exchange_partials, local_loss_scale, shard_micro_batches, vocab_parallel_lm_head_logprobs_entropy,
@@ -31,5 +32,5 @@ __all__ = [
     "lm_head_forward_raw", "lm_head_forward_save_raw", "lm_head_backward_saved_raw", "saved_logits_policy", "compute_entropy", "compute_loss", "selective_log_softmax", "shift_logits",
     "shifted_logprobs_entropy", "rl_micro_step", "get_response_lengths", "segments_from_position_ids",
     "fused_linear_cross_entropy", "recompute_logprobs", "TensorStats", "prepare_batch", "first_fit_decreasing",
-    "exchange_partials", "local_loss_scale", "shard_micro_batches", "vocab_parallel_lm_head_logprobs_entropy", "vocab_shard_bounds",
+    "DataLoader", "FakeDataLoader", "save_step", "upload_micro_batches", "exchange_partials", "local_loss_scale", "shard_micro_batches", "vocab_parallel_lm_head_logprobs_entropy", "vocab_shard_bounds",
 ]

@@ -307,17 +307,49 @@ def gen_packed_layout():
             out[f"rank{r}/mb{i}/temperature"] = np.asarray(mb["temperature"])
             out[f"rank{r}/mb{i}/lengths"] = np.asarray(get_response_lengths(mb["position_ids"]), dtype=np.int64)
     np.savez_compressed(os.path.join(HERE, "packed_layout.npz"), **out)
+    gen_rollout_files(per_rank)
+
+
+def gen_rollout_files(per_rank, step=7):
+    """The orchestrator -> trainer on-disk format: `<output_dir>/rollouts/step_<n>/rank_<r>.pt` = torch.save(list[MicroBatch]),
+    written to a .tmp file and renamed (src/prime_rl/orchestrator/orchestrator.py:356-363), read back by the reference's own
+    `DataLoader` (src/prime_rl/trainer/rl/data.py:57-75) to confirm the fixture is what the trainer consumes."""
+    from pathlib import Path
+
+    from prime_rl.utils.utils import get_rollout_dir
+
+    step_path = get_rollout_dir(Path(HERE)) / f"step_{step}"
+    step_path.mkdir(parents=True, exist_ok=True)
+    for i, batches in enumerate(per_rank):
+        batch_path = step_path / f"rank_{i}.pt"
+        tmp_path = batch_path.with_suffix(".tmp")
+        torch.save(batches, tmp_path)
+        tmp_path.rename(batch_path)
+    os.environ.setdefault("RANK", "0")
+    os.environ.setdefault("WORLD_SIZE", "1")
+    os.environ.setdefault("LOCAL_RANK", "0")
+    os.environ.setdefault("LOCAL_WORLD_SIZE", "1")
+    from prime_rl.trainer.rl.data import DataLoader
+
+    import logging
+
+    import prime_rl.utils.logger as ref_logger
+
+    ref_logger._LOGGER = logging.getLogger("golden")  # wait_for_path logs through the reference's global logger
+    dl = DataLoader(Path(HERE), step)
+    dl.wait_for_batch()
+    got = dl.get_batch()
+    assert len(got) == len(per_rank[0]) and all(torch.equal(a["input_ids"], b["input_ids"]) for a, b in zip(got, per_rank[0]))
+    print(f"rollouts/step_{step}: {len(per_rank)} rank files, read back by the reference DataLoader")
 
 
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(1)  # fixed reduction order for reproducible fixtures
-    gen_advantages()
-    gen_segments()
-    gen_loss()
-    gen_lmhead()
-    gen_sft()
-    gen_packed_layout()
+    gens = dict(advantages=gen_advantages, segments=gen_segments, loss=gen_loss, lmhead=gen_lmhead, sft=gen_sft,
+                packed_layout=gen_packed_layout)
+    for name in (sys.argv[1:] or list(gens)):  # `python make_golden.py packed_layout` regenerates one family
+        gens[name]()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

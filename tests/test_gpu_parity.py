@@ -784,6 +784,27 @@ def test_forward_active_only(P, save):
     assert ((dh1 - dh0).norm() / dh0.norm()).item() < 2e-3 and ((dw1 - dw0).norm() / dw0.norm()).item() < 2e-3
 
 
+def test_loader_uploads_one_buffer_per_micro_batch(P):
+    """The trainer-side data format: the rank file written by the reference (tests/golden/rollouts) streamed to the device with
+    one pinned staging buffer + one H2D copy per micro-batch (replaces train.py:275-279), then through the fused micro-step."""
+    dl = P.DataLoader(G, 7, rank=0)
+    host = P.DataLoader(G, 7, rank=0).get_batch()
+    dev = list(dl.get_batch_on_device("cuda"))
+    assert len(dev) == len(host) and dl.current_step == 8
+    H, V = 64, 1000
+    gen = torch.Generator().manual_seed(9)
+    w = (torch.randn(V, H, generator=gen) * 0.4).bfloat16().cuda().requires_grad_(True)
+    for a, b in zip(dev, host):
+        for k in ("input_ids", "position_ids", "advantages", "logprobs", "loss_mask"):
+            assert a[k].is_cuda and a[k].dtype == b[k].dtype and torch.equal(a[k].cpu(), b[k])
+        assert a["temperature"] == b["temperature"]
+        T = a["input_ids"].shape[1]
+        h = torch.randn(1, T, H, generator=gen).bfloat16().cuda().requires_grad_(True)
+        ref = P.rl_micro_step(h, w, P.to_device(b, "cuda"), P.LossConfig(), 7, backward=False)
+        out = P.rl_micro_step(h, w, a, P.LossConfig(), 7, backward=False)
+        assert torch.equal(out["logprobs"], ref["logprobs"]) and torch.equal(out["loss"], ref["loss"])
+
+
 def test_next_row_prepare_batch_on_device(P):
     """`prepare_batch` drop-in (host first-fit-decreasing + one packing kernel) reproduces the reference
     orchestrator's micro-batches bit for bit, including the padding micro-batch and the per-worker split."""
