@@ -62,6 +62,22 @@ class TensorStats:
             _lib.check(rc, "prl_masked_keys_u32")
             self.keys[key][2] = offered + x.numel()
 
+    def add_micro_step(self, out: dict, micro_batch: dict, ratio_type: str = "token", recomputed_logprob_error: torch.Tensor | None = None) -> None:
+        """Everything rl/train.py:313-333 appends after a micro-step, under the same keys, without leaving the device:
+        `out` is what `rl_micro_step` returns (loss, logprobs, entropy, importance_ratio, clipped_importance_ratio, is_clipped),
+        `micro_batch` the MicroBatch it ran on.  probs = exp(logprobs)[mask], old_probs = exp(old logprobs)[mask], entropy[mask],
+        recomputed_logprob_error[mask] (if given), loss, and the three loss tensors ([mask] in token mode, per sequence otherwise)."""
+        mask = micro_batch["loss_mask"]
+        self.add("probs", out["logprobs"], mask, exp=True)                       # train.py:313
+        self.add("old_probs", micro_batch["logprobs"], mask, exp=True)           # train.py:314
+        self.add("entropy", out["entropy"], mask)                                # train.py:315
+        if recomputed_logprob_error is not None:
+            self.add("recomputed_logprob_error", recomputed_logprob_error, mask)  # train.py:316-318
+        self.add("loss", out["loss"].reshape(1))                                 # train.py:319
+        for key in ("importance_ratio", "clipped_importance_ratio", "is_clipped"):
+            if key in out:                                                       # train.py:328-333
+                self.add(key, out[key], None if ratio_type == "sequence" else mask)
+
     def _medians(self, keys: list[str], counts: torch.Tensor, group) -> torch.Tensor:
         """[nkeys] int64 device tensor: the order-preserving key of the global lower median of every logged key (-1 if empty).
         `counts` = the all-reduced element counts (fp64)."""

@@ -489,6 +489,43 @@ def test_next_row_on_device_logging_stats(P):
     np.testing.assert_allclose(got["probs/median"], torch.median(torch.exp(cu(np.concatenate(vals)))).item(), rtol=2e-7)  # expf vs ATen exp
 
 
+@pytest.mark.parametrize("mode", ["token", "sequence"])
+def test_next_row_micro_step_logging_keys(P, mode):
+    """`TensorStats.add_micro_step` logs what rl/train.py:313-333 logs, under the same keys; values checked against the
+    boolean-index + torch statistics the reference computes (trainer/utils.py:246-250)."""
+    T, H, V, tau = 300, 64, 1000, 0.9
+    hidden, weight, ids = _mk(T, H, V, 3)
+    rng = np.random.default_rng(3)
+    lens = [100, 120, 80]
+    mask = cu(rng.random(T) < 0.7).unsqueeze(0)
+    mb = dict(input_ids=ids.cuda().unsqueeze(0), position_ids=cu(np.concatenate([np.arange(n) for n in lens])).unsqueeze(0),
+              advantages=cu(rng.standard_normal(T).astype(np.float32)).unsqueeze(0),
+              logprobs=cu(-rng.random(T).astype(np.float32) * 4).unsqueeze(0), loss_mask=mask, temperature=tau)
+    st = P.TensorStats()
+    ref = {}
+    for _ in range(2):  # two micro-batches of one step
+        out = P.rl_micro_step(hidden.cuda().unsqueeze(0).requires_grad_(True), weight.cuda().requires_grad_(True), mb,
+                              P.LossConfig(mode, mode == "sequence", 8.0), 5)
+        err = torch.exp(out["logprobs"] - mb["logprobs"])
+        st.add_micro_step(out, mb, ratio_type=mode, recomputed_logprob_error=err)
+        per = {"probs": torch.exp(out["logprobs"])[mask], "old_probs": torch.exp(mb["logprobs"])[mask], "entropy": out["entropy"][mask],
+               "recomputed_logprob_error": err[mask], "loss": out["loss"].reshape(1)}
+        for k in ("importance_ratio", "clipped_importance_ratio", "is_clipped"):
+            per[k] = out[k].float() if mode == "sequence" else out[k].float()[mask.squeeze()]
+        for k, v in per.items():
+            ref.setdefault(k, []).append(v.float())
+    got = st.compute_stats()
+    for k, parts in ref.items():
+        v = torch.cat(parts)
+        assert got[f"{k}/count"] == v.numel()
+        np.testing.assert_allclose(got[f"{k}/mean"], v.double().mean().item(), rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(got[f"{k}/median"], torch.median(v).item(), rtol=2e-7, atol=0)
+        np.testing.assert_allclose(got[f"{k}/min"], v.min().item(), rtol=2e-7)
+        np.testing.assert_allclose(got[f"{k}/max"], v.max().item(), rtol=2e-7)
+        if v.numel() > 1:
+            np.testing.assert_allclose(got[f"{k}/std"], v.double().std().item(), rtol=1e-5, atol=1e-9)
+
+
 @pytest.mark.parametrize("n,kind", [(1, "normal"), (2, "normal"), (7, "ties"), (100000, "ties"), (300001, "normal"), (4096, "signed-zero-inf"),
                                     (70000, "many-adds")])
 def test_next_row_exact_median_by_radix_select(P, n, kind):
