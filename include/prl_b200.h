@@ -241,6 +241,12 @@ int prl_pack_rollouts(const int64_t* tokens, const uint8_t* mask, const float* c
 int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn_major,
                       int32_t b_mn_major, int32_t accumulate, void* stream);
 
+/* Test hook (host only, no GPU): the work decomposition the GEMM engine would use for an M x N x K problem.
+ * kind 0 = forward sweep, 1 = dlogits sweep, 2 / 3 = store tiles of the recompute / saved-logits backward (incl. the
+ * K-split decision).  items[6 * i ..] = (m_tile, n_begin, n_count, k_begin, k_count, split) for item i (up to `capacity`
+ * items; may be NULL); dims[8] = (m_tiles, n_tiles, k_blocks, num_items, workers, k_splits, n_splits, rows per m-tile). */
+int prl_debug_schedule(int32_t kind, int64_t M, int64_t N, int64_t K, int32_t* items, int64_t capacity, int32_t* dims);
+
 /* number of kernel launches issued by this library on this host thread since the last reset
  * (bench.py's `gpu_launches`) */
 int64_t prl_launch_count(int32_t reset);

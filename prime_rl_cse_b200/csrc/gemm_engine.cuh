@@ -88,19 +88,22 @@ struct Item {
   int m_tile, split, n_begin, n_count, k_begin, k_count;
 };
 
-__device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
+__host__ __device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+
+// (also compiled for the host: prl_debug_schedule lets the CPU tests check that a decomposition covers every tile once)
+__host__ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
   const int ksp = p.k_splits > 1 ? p.k_splits : 1;  // k-splits of one tile are neighbouring items (they run concurrently)
   const int per_band = p.group_m * p.n_splits * ksp;
   const int band = item / per_band;
   const int m0 = band * p.group_m;
-  const int rows = min(p.group_m, p.m_tiles - m0);
+  const int rows = imin(p.group_m, p.m_tiles - m0);
   const int idx = item - band * per_band;
   Item it;
   if (p.split_group > 0) {
     // the workers that sweep the same vocab range are spread over the whole chip (both dies), neighbours share the A panel
     const int per_grp = rows * p.split_group;
     const int g = idx / per_grp;
-    const int s_here = min(p.split_group, p.n_splits - g * p.split_group);
+    const int s_here = imin(p.split_group, p.n_splits - g * p.split_group);
     const int r = idx - g * per_grp;
     it.split = g * p.split_group + r % s_here;
     it.m_tile = m0 + r / s_here;
@@ -111,10 +114,10 @@ __device__ __forceinline__ Item decode_item(const GemmParams& p, int item) {
     it.m_tile = m0 + idx % rows;
     it.split = vs / ksp;
     it.k_begin = (vs - it.split * ksp) * p.k_per_split;
-    it.k_count = min(p.k_per_split, p.k_blocks - it.k_begin);
+    it.k_count = imin(p.k_per_split, p.k_blocks - it.k_begin);
   }
   it.n_begin = it.split * p.tiles_per_split;
-  it.n_count = min(p.tiles_per_split, p.n_tiles - it.n_begin);
+  it.n_count = imin(p.tiles_per_split, p.n_tiles - it.n_begin);
   return it;
 }
 

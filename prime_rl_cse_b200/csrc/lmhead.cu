@@ -702,6 +702,30 @@ int prl_lmhead_bwd_saved(const void* hidden, const void* weight, const int64_t* 
                           d_weight_dtype, accumulate_dw, phase_mask, true, true, 1, dh_acc, 4, st);
 }
 
+int prl_debug_schedule(int32_t kind, int64_t M, int64_t N, int64_t K, int32_t* items, int64_t capacity, int32_t* dims) {
+  PRL_REQUIRE(kind >= 0 && kind <= 3 && M >= 1 && N >= 1 && K >= 1 && dims, PRL_ERR_BAD_ARG, "debug_schedule: bad arguments");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int epi = kind == 0 ? EPI_STATS : (kind == 1 ? EPI_DZ : EPI_STORE);
+  set_tiling(p, M, N, K, epi);
+  if (kind <= 1) {
+    schedule_sweeps(p, MAX_SPLITS, epi);
+  } else {
+    set_k_splits(p, pick_k_splits(M, N, K));
+    schedule_tiles(p, kind == 2 ? 8 : 4);
+  }
+  dims[0] = p.m_tiles, dims[1] = p.n_tiles, dims[2] = p.k_blocks, dims[3] = p.num_items;
+  dims[4] = workers(), dims[5] = p.k_splits, dims[6] = p.n_splits, dims[7] = BLOCK_M * cta_group() * msub(epi);
+  if (items) {
+    for (int i = 0; i < p.num_items && i < capacity; ++i) {
+      const Item it = decode_item(p, i);
+      int32_t* o = items + 6 * (int64_t)i;
+      o[0] = it.m_tile, o[1] = it.n_begin, o[2] = it.n_count, o[3] = it.k_begin, o[4] = it.k_count, o[5] = it.split;
+    }
+  }
+  return PRL_OK;
+}
+
 int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn_major, int32_t b_mn_major,
                       int32_t accumulate, void* stream) {
   PRL_REQUIRE(M >= 1 && N >= 1 && K >= 1, PRL_ERR_BAD_ARG, "gemm: bad sizes");
