@@ -1,4 +1,4 @@
-// Fused LM head (forward statistics + recompute-based backward) and the plain bring-up GEMM, host side:
+// Fused LM head (forward statistics, saved-logits and recompute backward) and the plain bring-up GEMM, host side:
 // TMA tensor maps, work decomposition, kernel launches, C ABI.  The device code is gemm_engine.cuh.
 #include <stdlib.h>
 
@@ -6,10 +6,26 @@
 
 namespace prl {
 
+// diagnostic knobs (PRL_*) are read from the environment at every call
+static long env_long(const char* name, long dflt) {
+  const char* s = getenv(name);
+  return s ? strtol(s, nullptr, 0) : dflt;
+}
+
+// CTAs per cluster: 1 = one CTA per 128x256 tile; 2 = a CTA pair (cta_group::2) per 256x256 tile; 4 = two pairs per
+// 512x256 tile sharing B by TMA multicast
+static int cta_group() {
+  static int cg = 0;
+  if (cg == 0) {
+    const long v = env_long("PRL_CTA_GROUP", 2);
+    cg = (v == 1) ? 1 : (v == 4 ? 4 : 2);
+  }
+  return cg;
+}
+
 // ------------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------------
-static long env_long_fwd(const char* name, long dflt);
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -27,7 +43,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // L2 promotion of TMA requests (PRL_L2_PROMO = 0 none | 64 | 128 | 256; default 256)
 static CUtensorMapL2promotion l2_promotion() {
-  const long v = env_long_fwd("PRL_L2_PROMO", 256);
+  const long v = env_long("PRL_L2_PROMO", 256);
   return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                 : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
 }
@@ -51,11 +67,10 @@ static int make_tmap_t(CUtensorMap* map, const void* base, int64_t inner, int64_
   return PRL_OK;
 }
 
-static int cta_group_fwd();
 static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
   return make_tmap_t(map, base, inner, outer, ld, box_inner, box_outer, false);
 }
-static bool epi_tma_enabled() { return env_long_fwd("PRL_EPI_TMA", 1) != 0; }
+static bool epi_tma_enabled() { return env_long("PRL_EPI_TMA", 1) != 0; }
 // output map of the TMA-store epilogues: [rows, cols] row-major with pitch ld; fp32 boxes 32 x 32, bf16 boxes 64 x 32 (128 B rows)
 static int make_output_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool f32) {
   return make_tmap_t(map, base, cols, rows, ld, f32 ? 32 : 64, 32, f32);
@@ -63,16 +78,10 @@ static int make_output_map(CUtensorMap* map, const void* base, int64_t rows, int
 // operand description: K-major => stored [rows, K]; MN-major => stored [K, rows]
 static int make_operand_map(CUtensorMap* map, const void* base, bool mn_major, int64_t rows, int64_t K, int64_t ld, int block_rows) {
   // B: a CTA of a pair stages half of the tile's rows; with two pairs per cluster it fetches only a quarter itself
-  if (block_rows == BLOCK_N) block_rows = BLOCK_N / cta_group_fwd();
+  if (block_rows == BLOCK_N) block_rows = BLOCK_N / cta_group();
   if (!mn_major) return make_tmap(map, base, K, rows, ld, BLOCK_K, block_rows);
   return make_tmap(map, base, rows, K, ld, 64, BLOCK_K);
 }
-
-static long env_long(const char* name, long dflt) {
-  const char* s = getenv(name);
-  return s ? strtol(s, nullptr, 0) : dflt;
-}
-static long env_long_fwd(const char* name, long dflt) { return env_long(name, dflt); }
 
 static void make_desc_defaults(GemmParams& p, bool a_mn, bool b_mn) {
   // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused (16 B); one UMMA_K step = +32 B.
@@ -85,19 +94,6 @@ static void make_desc_defaults(GemmParams& p, bool a_mn, bool b_mn) {
   p.b_desc_hi = b_mn ? ptx::make_smem_desc_hi_sw128(mn_lbo, mn_sbo) : ptx::make_smem_desc_hi_sw128(16, 1024);
   p.a_kstep = a_mn ? mn_kstep : UMMA_K * 2;
   p.b_kstep = b_mn ? mn_kstep : UMMA_K * 2;
-}
-
-static int cta_group();
-static int cta_group_fwd() { return cta_group(); }
-// CTAs per cluster: 1 = one CTA per 128x256 tile; 2 = a CTA pair (cta_group::2) per 256x256 tile; 4 = two pairs per
-// 512x256 tile sharing B by TMA multicast
-static int cta_group() {
-  static int cg = 0;
-  if (cg == 0) {
-    const long v = env_long("PRL_CTA_GROUP", 2);
-    cg = (v == 1) ? 1 : (v == 4 ? 4 : 2);
-  }
-  return cg;
 }
 
 // M sub-tiles per CTA-pair tile: 1 = 256 x 256 tiles with double-buffered accumulators; 2 = 512 x 256 tiles (two sub-tiles
