@@ -36,6 +36,37 @@ def test_library_exports_every_declared_symbol(lib):
     assert sorted(lib.exported_symbols()) == declared, "ctypes signature table and header disagree"
 
 
+def test_ctypes_signatures_match_the_header_argument_by_argument(lib):
+    """Every prototype of include/prl_b200.h against the ctypes table: same number of parameters, and per parameter the same
+    class (pointer / 64-bit integer / 32-bit integer / float / double / size_t) — an ABI drift between the header and the
+    Python binding would otherwise only show up as garbage arguments on the GPU box."""
+    import ctypes
+
+    text = open(os.path.join(ROOT, "include", "prl_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(prl_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text)
+    assert len(protos) == len(lib._SIGNATURES)
+
+    def klass(decl):
+        decl = decl.strip()
+        if decl in ("void", ""):
+            return None
+        if "*" in decl:
+            return "ptr"
+        for key, val in (("int64_t", "i64"), ("int32_t", "i32"), ("size_t", "size"), ("float", "f32"), ("double", "f64"), ("int", "i32")):
+            if re.search(rf"\b{key}\b", decl):
+                return val
+        raise AssertionError(f"unrecognised parameter {decl!r}")
+
+    ct = {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int64: "i64", ctypes.c_int32: "i32", ctypes.c_size_t: "size",
+          ctypes.c_float: "f32", ctypes.c_double: "f64"}
+    for ret, name, params in protos:
+        res, args = lib._SIGNATURES[name]
+        want = [k for k in (klass(p) for p in params.split(",")) if k is not None]
+        assert [ct[a] for a in args] == want, f"{name}: header {want} vs ctypes {[ct[a] for a in args]}"
+        assert ct[res] == klass(ret + (" x" if "*" not in ret else "")), f"{name}: return type"
+
+
 def test_version_and_strerror(lib):
     L = lib.load()
     assert L.prl_version() >= 100
