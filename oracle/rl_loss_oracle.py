@@ -256,14 +256,17 @@ def lm_head_backward(
     dlogp: np.ndarray,
     round_bf16: bool,
     dtype=np.float64,
+    logits: np.ndarray | None = None,
 ):
     """dz[t,v] = dlogp[t] * (1[v == ids[t]] - softmax(z[t])[v]); dlogits[t-1] =
     dz[t] / tau for t >= 1 (row 0 of the shifted tensor is a constant, the last
     un-shifted row is dropped: rl/loss.py:54-57); with `round_bf16` dlogits is
     rounded to bf16 (backward of `.float()` on bf16 logits, rl/train.py:285).
-    dHidden = dlogits @ W, dW = dlogits^T @ hidden.  Returns (dHidden, dW)."""
+    dHidden = dlogits @ W, dW = dlogits^T @ hidden.  Returns (dHidden, dW).
+    `logits` (optional, [T,V]): use these un-shifted logits instead of recomputing them (the "same-logits" checker:
+    the GPU kernel's own bf16 logits block, so that accumulation-order effects of the GEMM are taken out)."""
     T = hidden.shape[0]
-    logits = lm_head_logits(hidden, weight, round_bf16, dtype)
+    logits = lm_head_logits(hidden, weight, round_bf16, dtype) if logits is None else np.asarray(logits, dtype=dtype)
     z = shift_rows(logits) / dtype(tau)
     p = np.exp(z - np.asarray(lse, dtype=dtype)[:, None])
     dz = -p * np.asarray(dlogp, dtype=dtype)[:, None]
@@ -278,16 +281,18 @@ def lm_head_backward(
 
 
 def micro_step(
-    hidden, weight, ids, position_ids, old, adv, mask, tau, cfg: LossCfg, loss_scale, round_bf16=True, dtype=np.float64
+    hidden, weight, ids, position_ids, old, adv, mask, tau, cfg: LossCfg, loss_scale, round_bf16=True, dtype=np.float64,
+    logits=None,
 ):
     """The whole of rl/train.py:285-310 for one packed micro-batch, given the
     final hidden states: returns a dict with logp, entropy, lse, loss, the three
-    logging tensors, dlogp, dHidden, dW."""
-    logits = lm_head_logits(hidden, weight, round_bf16, dtype)
+    logging tensors, dlogp, dHidden, dW.  `logits` (optional, [T,V] un-shifted): start from these logits instead of
+    hidden @ W^T (same-logits checker, see `lm_head_backward`)."""
+    logits = lm_head_logits(hidden, weight, round_bf16, dtype) if logits is None else np.asarray(logits, dtype=dtype)
     logp, ent, lse = logprobs_entropy(shift_rows(logits), ids, tau, dtype)
     lens = response_lengths(position_ids)
     loss, ratio, clipped, flag, dlogp = loss_fwd_bwd(logp, old, adv, mask, lens, cfg, loss_scale, dtype)
-    d_hidden, d_weight = lm_head_backward(hidden, weight, ids, tau, lse, dlogp, round_bf16, dtype)
+    d_hidden, d_weight = lm_head_backward(hidden, weight, ids, tau, lse, dlogp, round_bf16, dtype, logits=logits)
     return dict(
         logp=logp,
         entropy=ent,

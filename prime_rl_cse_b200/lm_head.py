@@ -1,16 +1,18 @@
 """Fused LM head: hidden x W_lm^T -> (log-prob of the sampled token, entropy) without materialising
-the fp32 [T, V] logits.  Replaces rl/train.py:285-288,302-303 of the reference
+the [T, V] logits.  Replaces rl/train.py:285-288,302-303 of the reference
 (src/prime_rl/trainer/rl/train.py) and the autograd chain behind `loss.backward()` (:310).
 
 Two backward modes, same results:
-  * saved logits (default when the block fits, see `saved_logits_policy`): the forward keeps ONE bf16 copy of
-    the logits (T x V x 2 bytes, 5 GB for a 16384-token micro-batch of Qwen3; the reference keeps the fp32
-    logits plus their gradient), the backward rewrites it in place into dlogits and runs two GEMMs;
-  * recompute: nothing but lse[T] is kept, the backward recomputes the logits per vocab chunk (one more GEMM)."""
+  * recompute (DEFAULT; BASELINE.json north_star's design): nothing but lse[T] is kept, the backward recomputes the logits
+    per vocab chunk (one more GEMM) -- the [T, V] logits never exist in HBM;
+  * saved logits (OPT-IN: `save_logits=True` or PRL_SAVE_LOGITS=1|auto): the forward keeps ONE bf16 copy of the logits
+    (T x V x 2 bytes, 4.6 GiB for a 16384-token micro-batch of Qwen3; the reference keeps the fp32 logits plus their
+    gradient), the backward rewrites it in place into dlogits and runs two GEMMs: ~25 % faster, at that memory cost."""
 
 from __future__ import annotations
 
 import os
+import warnings
 
 import torch
 from torch import nn
@@ -43,19 +45,38 @@ def lm_head_forward_raw(hidden, weight, ids, inv_temp, shift=True, round_bf16=Tr
     return logp, ent, lse, parts
 
 
-def saved_logits_policy(T: int, V: int, override: bool | None = None) -> bool:
+def saved_logits_policy(T: int, V: int, override: bool | None = None, device=None) -> bool:
     """Whether the forward keeps the bf16 logits for the backward.  `override` wins; else the environment variable
-    PRL_SAVE_LOGITS = 0 | 1 | auto (default); `auto` keeps them when the block is at most PRL_SAVE_LOGITS_MAX_GIB
-    (default 12 GiB: a 32768-token packed row at V = 151936 is 9.3 GiB)."""
+    PRL_SAVE_LOGITS = 0 (default: recompute, nothing of size [T, V] is ever stored) | 1 | auto.  `auto` keeps them when the
+    block is at most PRL_SAVE_LOGITS_MAX_GIB (default 12 GiB: a 32768-token packed row at V = 151936 is 9.3 GiB) AND at
+    most half of the device memory that is free right now."""
     if override is not None:
         return bool(override)
-    env = os.environ.get("PRL_SAVE_LOGITS", "auto").strip().lower()
-    if env in ("0", "off", "false", "no"):
+    env = os.environ.get("PRL_SAVE_LOGITS", "0").strip().lower()
+    if env in ("0", "off", "false", "no", ""):
         return False
     if env in ("1", "on", "true", "yes"):
         return True
+    need = T * saved_logits_ld(V) * 2
     limit = float(os.environ.get("PRL_SAVE_LOGITS_MAX_GIB", "12")) * 2**30
-    return 0 < T * saved_logits_ld(V) * 2 <= limit
+    if not 0 < need <= limit:
+        return False
+    if torch.cuda.is_available():
+        free, _total = torch.cuda.mem_get_info(device)
+        return need <= free // 2
+    return True
+
+
+_warned_fallback = False
+
+
+def _warn_fallback(why: str) -> None:
+    """one line, once per process: the saved-logits backward was asked for but the recompute backward runs (~25 % slower)"""
+    global _warned_fallback
+    if not _warned_fallback:
+        _warned_fallback = True
+        warnings.warn(f"prime_rl_cse_b200: saved-logits backward unavailable ({why}); using the recompute backward "
+                      "(one more GEMM per micro-batch). Reported once.", RuntimeWarning, stacklevel=3)
 
 
 def saved_logits_ld(V: int) -> int:
@@ -161,7 +182,7 @@ def _forward_any(h, w, i, inv_temp, shift, round_bf16, save):
             logp, ent, lse, _, saved = lm_head_forward_save_raw(h, w, i, inv_temp, shift)
             return logp, ent, lse, saved
         except torch.OutOfMemoryError:
-            pass  # no room for the block: recompute mode needs lse only
+            _warn_fallback(f"no room for the {h.shape[0]} x {w.shape[0]} bf16 logits block")  # recompute mode needs lse only
     logp, ent, lse, _ = lm_head_forward_raw(h, w, i, inv_temp, shift, round_bf16)
     return logp, ent, lse, None
 
@@ -176,6 +197,7 @@ class _FusedLMHead(torch.autograd.Function):
         i2 = ids.detach().reshape(-1).contiguous().to(torch.int64)
         ctx.compact = None
         ctx.saved_logits = None   # bf16 logits kept for the backward (consumed by it)
+        ctx.had_saved = False
         ctx.saved_rows = "all"    # which rows the block covers: "all" source rows or "compact" (the active rows only)
         needs_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         if active_positions is not None:
@@ -222,6 +244,9 @@ class _FusedLMHead(torch.autograd.Function):
         need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         none_tail = (None,) * 8
         # the kept logits are consumed by the first backward; a second one (retain_graph) falls back to the recompute
+        if ctx.saved_logits is None and getattr(ctx, "had_saved", False):
+            _warn_fallback("second backward through the same graph: the block was consumed by the first")
+        ctx.had_saved = ctx.had_saved or ctx.saved_logits is not None
         saved, ctx.saved_logits = ctx.saved_logits, None
         dw_target = main_grad if (main_grad is not None and need_w) else None
 
@@ -284,9 +309,10 @@ def fused_lm_head_logprobs_entropy(
     `loss_mask.nonzero()`): the backward then skips every other row (prompt / environment tokens) — identical gradients,
     proportionally less recompute.  By default the forward still covers all T positions, as the reference does; with
     `forward_active_only=True` it visits the active positions only and returns 0 for log-prob and entropy elsewhere.
-    `save_logits`: True keeps one bf16 copy of the logits (T x V x 2 bytes) between forward and backward so that the backward
-    needs two GEMMs instead of three; False recomputes; None (default) decides by size (`saved_logits_policy`).  Both give the
-    same gradients (same bf16 dlogits)."""
+    `save_logits`: False / None (default) recomputes the logits in the backward, so nothing of size [T, V] is ever stored;
+    True keeps one bf16 copy of the logits (T x V x 2 bytes) between forward and backward so that the backward needs two
+    GEMMs instead of three (opt-in; None follows PRL_SAVE_LOGITS, `saved_logits_policy`).  Both give the same gradients
+    (same bf16 dlogits)."""
     _lib.require_cuda(hidden, weight, input_ids)
     if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise ValueError("fused_lm_head_logprobs_entropy needs bf16 hidden and weight (FSDP param_dtype=bf16, model.py:103)")
@@ -310,7 +336,7 @@ class FusedLMHead(nn.Module):
         super().__init__()
         self.weight = weight
         self.main_grad = main_grad
-        self.save_logits = save_logits  # None: by size (saved_logits_policy)
+        self.save_logits = save_logits  # None: recompute unless PRL_SAVE_LOGITS says otherwise (saved_logits_policy)
         self._ctx: tuple[torch.Tensor, float] | None = None
 
     @classmethod

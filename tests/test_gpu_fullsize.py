@@ -9,6 +9,8 @@ import numpy as np
 import pytest
 import torch
 
+from tests.same_logits import allowed_flip_outliers
+
 pytestmark = pytest.mark.gpu
 
 
@@ -67,18 +69,19 @@ def test_forward_properties_full_size(P, T, H, V, tau):
     assert (lp_m - logp).abs().max().item() < 5e-4 and (ent_m - ent).abs().max().item() < 5e-4 and (lse_m - lse).abs().max().item() < 5e-4
 
     # sampled rows against torch fp32 on the same bf16-rounded logits
-    rows = torch.randint(1, T, (96,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    rows = torch.randint(1, T, (1024,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
     z = (hidden[rows - 1].float() @ W.float().t()).bfloat16().float() / tau
     ref_lse = torch.logsumexp(z, -1)
     ref_lp = z.gather(1, ids[rows].unsqueeze(1)).squeeze(1) - ref_lse
     ref_ent = ref_lse - (torch.softmax(z, -1) * z).sum(-1)
-    # tcgen05 and cuBLAS/ATen accumulate in different orders, so a logit that sits on a bf16 rounding boundary can round the
-    # other way: at most ONE bf16 ulp of that logit (2^-7 relative), everything else is within 1e-3
+    # tcgen05 and cuBLAS/ATen accumulate in different orders, so a logit that sits on a bf16 rounding midpoint can round the
+    # other way: at most ONE bf16 ulp of that logit (2^-7 relative), for at most 0.1 % of the tokens; everything else is
+    # within 1e-3 (tests/test_gpu_same_logits.py holds every token to 1e-3 from the kernel's own logits)
     bound = 1.05 * z.abs().max().item() * 2.0**-7 + 1e-3
     d = (logp[rows] - ref_lp).abs()
-    assert (d < 1e-3).float().mean().item() >= 0.97 and d.max().item() < bound, (d.max().item(), bound)
+    assert int((d >= 1e-3).sum()) <= allowed_flip_outliers(rows.numel()) and d.max().item() < bound, (d.max().item(), int((d >= 1e-3).sum()))
     de = (ent[rows] - ref_ent).abs()  # same caveat: a flipped high-probability logit moves H
-    assert (de < 1e-3).float().mean().item() >= 0.97 and de.max().item() < bound, (de.max().item(), bound)
+    assert int((de >= 1e-3).sum()) <= allowed_flip_outliers(rows.numel()) and de.max().item() < bound, (de.max().item(), int((de >= 1e-3).sum()))
 
 
 @pytest.mark.parametrize("mode", ["recompute", "saved-logits"])
@@ -228,10 +231,12 @@ def test_micro_step_vs_torch_reference_chain_on_gpu(P):
     # |logit| reaches ~16 here: one bf16 ulp (2^-7 relative) of a boundary logit, divided by tau, is ~0.2
     bound = 16.0 * 2.0**-7 / tau
     d = (out["logprobs"][0] - lp_ref).abs()
-    assert (d < 1e-3).float().mean().item() >= 0.98 and d.max().item() < bound, (d.max().item(), (d < 1e-3).float().mean().item())
+    n_out = int((d >= 1e-3).sum())
+    assert n_out <= allowed_flip_outliers(T) and d.max().item() < bound, (d.max().item(), n_out)
     de = (out["entropy"][0] - ent_ref).abs()
-    assert (de < 1e-3).float().mean().item() >= 0.98 and de.max().item() < bound
-    assert abs(out["loss"].item() - loss_ref.item()) <= 5e-3 * abs(loss_ref.item()) + 1e-6
+    assert int((de >= 1e-3).sum()) <= allowed_flip_outliers(T) and de.max().item() < bound
+    # the loss moves with the flipped tokens only: 1e-4 when there is none
+    assert abs(out["loss"].item() - loss_ref.item()) <= (1e-4 if n_out == 0 else 5e-3) * abs(loss_ref.item()) + 1e-6
     rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()  # noqa: E731
     assert rel(h.grad, h_ref.grad) < 1e-2 and rel(w.grad, w_ref.grad) < 1e-2
 

@@ -1,7 +1,13 @@
 """GPU parity tests (run on the B200 box: `pytest -m gpu`).  The CUDA path is called through the
 C-ABI library and compared with the CPU oracle (`oracle/`) and with the golden fixtures produced by
 the unmodified reference.  Tolerances are the ones BASELINE.json's north_star states:
-advantages bit-exact; logp / entropy <= 1e-3 abs; loss <= 1e-4 rel; gradients <= 1e-2 rel-L2."""
+advantages bit-exact; logp / entropy <= 1e-3 abs; loss <= 1e-4 rel; gradients <= 1e-2 rel-L2.
+
+Fused LM-head path: the stated tolerances are held for EVERY token against the oracle started from the kernel's own bf16
+logits (`tests/same_logits.py`: what is left out is only which way an accumulator on a bf16 rounding midpoint rounds, and
+`rn_bf16_violations` proves the kernel's logits are the correctly rounded product up to accumulation noise).  Against the
+exact-product oracle / the reference's fixtures the log-probs are within 1e-3 for >= 99.9 % of tokens (at most one token of a
+row shorter than 1000: `allowed_flip_outliers`); tests/test_gpu_same_logits.py does the same at the BASELINE shapes."""
 
 import math
 import os
@@ -12,6 +18,7 @@ import torch
 
 import oracle
 from oracle import LossCfg
+from tests.same_logits import allowed_flip_outliers, assert_same_logits_micro_step, kernel_logits, rn_bf16_violations
 
 pytestmark = pytest.mark.gpu
 
@@ -300,9 +307,15 @@ def test_lmhead_forward_vs_oracle(P, T, H, V, tau):
     dl = np.abs(lp[0].cpu().numpy() - wl)
     de = np.abs(ent[0].cpu().numpy() - we)
     # tcgen05 and the fp64 oracle accumulate in different orders: a logit that sits on a bf16 rounding
-    # boundary may round the other way (SURVEY §7 "bf16 rounding"), moving logp by <= 1 bf16 ulp of the logit.
-    assert np.mean(dl < 1e-3) >= 0.99 and dl.max() < 0.07, (dl.max(), np.mean(dl < 1e-3))
+    # midpoint may round the other way (SURVEY §7 "bf16 rounding"), moving logp by <= 1 bf16 ulp of the logit.
+    assert int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T) and dl.max() < 0.07, (dl.max(), int((dl >= 1e-3).sum()))
     assert de.max() < 1e-3, de.max()
+    # ... and that is all there is: the kernel's logits are the correctly rounded product, and from THOSE logits every token matches
+    klog, blk = kernel_logits(hidden, weight, ids, tau)
+    rn = rn_bf16_violations(blk, hidden.cuda(), weight.cuda(), torch.arange(T - 1, device="cuda"))
+    assert rn["violations"] == 0, rn
+    kl, ke, _ = oracle.logprobs_entropy(oracle.shift_rows(klog), ids.numpy(), tau)
+    assert np.abs(lp[0].cpu().numpy() - kl).max() < 2e-4 and np.abs(ent[0].cpu().numpy() - ke).max() < 2e-4
     # closed-form first row (shift_logits' zero row): logp = -ln V, entropy = ln V
     assert abs(lp[0, 0].item() + np.log(V)) < 1e-5 and abs(ent[0, 0].item() - np.log(V)) < 1e-5
 
@@ -336,9 +349,17 @@ def test_lmhead_fixtures_from_reference(P):
                   loss_mask=cu(d[f"{name}/mask"]).unsqueeze(0), temperature=tau)
         cfg = P.LossConfig() if cname == "token" else P.LossConfig("sequence", True, 8.0)
         out = P.rl_micro_step(hidden.unsqueeze(0), weight, mb, cfg, int(d[f"{key}/scale"]))
+        # every token, from the kernel's own logits
+        klog, _ = kernel_logits(hidden.detach(), weight.detach(), mb["input_ids"][0], tau)
+        same = oracle.micro_step(d[f"{name}/hidden"], d[f"{name}/weight"], d[f"{name}/ids"], d[f"{name}/pos"], d[f"{key}/old"],
+                                 d[f"{name}/adv"], d[f"{name}/mask"], tau, LossCfg(*((cname,) if cname == "token" else ("sequence", True, 8.0))),
+                                 int(d[f"{key}/scale"]), logits=klog)
+        assert_same_logits_micro_step(out, same, hidden.grad, weight.grad)
+        # the reference's own numbers (its GEMM rounds midpoint logits its own way)
         dl = np.abs(out["logprobs"][0].cpu().numpy() - d[f"{key}/logp"])
-        assert np.mean(dl < 1e-3) > 0.97 and dl.max() < 0.07, (key, dl.max())
-        np.testing.assert_allclose(out["loss"].item(), d[f"{key}/loss"], rtol=5e-3, atol=1e-5)
+        n_out = int((dl >= 1e-3).sum())
+        assert n_out <= allowed_flip_outliers(dl.size) and dl.max() < 0.07, (key, dl.max(), n_out)
+        np.testing.assert_allclose(out["loss"].item(), d[f"{key}/loss"], rtol=1e-4 if n_out == 0 else 5e-3, atol=1e-6)
         assert rel_l2(hidden.grad.float().cpu().numpy(), d[f"{key}/d_hidden"]) < 1e-2, key
         assert rel_l2(weight.grad.float().cpu().numpy(), d[f"{key}/d_weight"]) < 1e-2, key
 
@@ -371,10 +392,13 @@ def test_micro_step_vs_oracle(P, T, H, V, tau, mode, vchunk, save):
         mb = dict(input_ids=ids.cuda().unsqueeze(0), position_ids=cu(pos).unsqueeze(0), advantages=cu(adv).unsqueeze(0),
                   logprobs=cu(old).unsqueeze(0), loss_mask=cu(mask).unsqueeze(0), temperature=tau)
         out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(mode, mode == "sequence", 8.0), scale, save_logits=save)
+        klog, _ = kernel_logits(hidden, weight, ids, tau)
+        same = oracle.micro_step(hidden.float().numpy(), weight.float().numpy(), ids.numpy(), pos, old, adv, mask, tau, cfg_o, scale, logits=klog)
+        assert_same_logits_micro_step(out, same, h.grad, w.grad)  # every token at the stated tolerances
         dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
-        assert np.mean(dl < 1e-3) >= 0.99 and dl.max() < 0.07, (dl.max(), np.mean(dl < 1e-3))
-        assert np.abs(out["entropy"][0].cpu().numpy() - want["entropy"]).max() < 2e-3
-        np.testing.assert_allclose(out["loss"].item(), want["loss"], rtol=5e-3, atol=1e-6)
+        n_out = int((dl >= 1e-3).sum())
+        assert n_out <= allowed_flip_outliers(T) and dl.max() < 0.07, (dl.max(), n_out)
+        np.testing.assert_allclose(out["loss"].item(), want["loss"], rtol=1e-4 if n_out == 0 else 5e-3, atol=1e-6)
         assert rel_l2(h.grad.float().cpu().numpy(), want["d_hidden"]) < 1e-2
         assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1e-2
         assert h.grad.dtype == torch.bfloat16 and w.grad.dtype == torch.bfloat16
@@ -425,8 +449,8 @@ def test_fused_lm_head_module_in_hf_qwen3(P):
     assert out.shape == (1, T, 2)
     lp, ent = out[..., 0], out[..., 1].detach()
     d = (lp - ref_lp).abs()
-    assert (d < 1e-3).float().mean().item() > 0.98 and d.max().item() < 0.07
-    assert (ent - ref_ent).abs().max().item() < 5e-3
+    assert int((d >= 1e-3).sum()) <= allowed_flip_outliers(T) and d.max().item() < 0.07
+    assert int(((ent - ref_ent).abs() >= 1e-3).sum()) <= allowed_flip_outliers(T)
     (lp * 0.01).sum().backward()
     gw = model.lm_head.weight.grad.float()
     ge = model.model.embed_tokens.weight.grad.float()
@@ -458,7 +482,10 @@ def test_next_rows_sft_cross_entropy_and_logprob_recompute(P):
     old = torch.from_numpy(wl).float().cuda() + 0.1
     lp, err = P.recompute_logprobs(h.cuda().unsqueeze(0), w.cuda(), ids.cuda().unsqueeze(0), tau, old.unsqueeze(0))
     dl = np.abs(lp[0].cpu().numpy() - wl)
-    assert np.mean(dl < 1e-3) >= 0.99 and dl.max() < 0.07
+    assert int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T) and dl.max() < 0.07
+    klog, _ = kernel_logits(h, w, ids, tau)
+    kl, _, _ = oracle.logprobs_entropy(oracle.shift_rows(klog), ids.numpy(), tau)
+    assert np.abs(lp[0].cpu().numpy() - kl).max() < 2e-4  # every token, from the kernel's own logits
     np.testing.assert_allclose(err[0].cpu().numpy(), np.exp(lp[0].cpu().numpy() - old.cpu().numpy()), rtol=1e-5)
 
 
@@ -579,9 +606,11 @@ def test_micro_step_edge_shapes(P, T, H, V, save):
     mb = dict(input_ids=ids.cuda().unsqueeze(0), position_ids=cu(pos).unsqueeze(0), advantages=cu(adv).unsqueeze(0),
               logprobs=cu(old).unsqueeze(0), loss_mask=cu(mask).unsqueeze(0), temperature=tau)
     out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), T, response_lengths=want["lengths"], save_logits=save)
+    klog, _ = kernel_logits(hidden, weight, ids, tau)
+    same = oracle.micro_step(hidden.float().numpy(), weight.float().numpy(), ids.numpy(), pos, old, adv, mask, tau, LossCfg(), T, logits=klog)
+    assert_same_logits_micro_step(out, same, h.grad if T > 1 else None, w.grad if T > 1 else None)
     dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
-    assert dl.max() < 0.07 and np.mean(dl < 1e-3) >= 0.97
-    np.testing.assert_allclose(out["loss"].item(), want["loss"], rtol=2e-2, atol=1e-5)
+    assert dl.max() < 0.07 and int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T)
     if T > 1:
         assert rel_l2(h.grad.float().cpu().numpy(), want["d_hidden"]) < 1.5e-2
         assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1.5e-2
@@ -714,11 +743,20 @@ def test_dhidden_k_split_matches_unsplit_and_is_deterministic(P):
 
 
 def test_saved_logits_policy_and_second_backward(P):
-    """Autograd integration: size policy, and a second backward through a retained graph (the kept block is consumed by the
-    first one) falls back to the recompute and gives the same gradients."""
+    """Autograd integration: the default is the recompute backward (nothing of size [T, V] is stored); PRL_SAVE_LOGITS=auto
+    decides by size; a second backward through a retained graph (the kept block is consumed by the first one) falls back to
+    the recompute, says so once, and gives the same gradients."""
+    import warnings
+
     from prime_rl_cse_b200 import saved_logits_policy
 
-    assert saved_logits_policy(16384, 151936) and not saved_logits_policy(10**6, 151936) and not saved_logits_policy(0, 1000)
+    assert os.environ.get("PRL_SAVE_LOGITS") is None
+    assert not saved_logits_policy(16384, 151936) and not saved_logits_policy(16, 1000)  # default: recompute
+    os.environ["PRL_SAVE_LOGITS"] = "auto"
+    try:
+        assert saved_logits_policy(16384, 151936) and not saved_logits_policy(10**6, 151936) and not saved_logits_policy(0, 1000)
+    finally:
+        os.environ.pop("PRL_SAVE_LOGITS")
     assert saved_logits_policy(10**6, 151936, True) and not saved_logits_policy(16, 1000, False)
     T, H, V = 300, 128, 3000
     hidden, weight, ids = _mk(T, H, V, 5)
@@ -729,7 +767,13 @@ def test_saved_logits_policy_and_second_backward(P):
     loss.backward(retain_graph=True)
     g1 = (h.grad.clone(), w.grad.clone())
     h.grad = w.grad = None
-    loss.backward()
+    import prime_rl_cse_b200.lm_head as lm_head_mod
+
+    lm_head_mod._warned_fallback = False
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        loss.backward()
+    assert any("recompute backward" in str(c.message) for c in caught)  # the 25 % cliff is announced (once per process)
     assert torch.equal(g1[0], h.grad) and torch.equal(g1[1], w.grad)
     with torch.no_grad():  # nothing is kept when no gradient can flow
         lp2, _ = P.fused_lm_head_logprobs_entropy(hidden.cuda().unsqueeze(0), weight.cuda(), ids.cuda().unsqueeze(0), 0.9, save_logits=True)
@@ -760,9 +804,13 @@ def test_micro_step_on_reference_packed_batches(P):
             w = weight.cuda().requires_grad_(True)
             out = P.rl_micro_step(h.unsqueeze(0), w, P.to_device(mb, "cuda"), P.LossConfig(), scale)
             assert P.get_response_lengths(mb["position_ids"].cuda()) == want["lengths"]
+            klog, _ = kernel_logits(hidden, weight, mb["input_ids"][0], mb["temperature"])
+            same = oracle.micro_step(hidden.float().numpy(), weight.float().numpy(), mb["input_ids"][0].numpy(), mb["position_ids"][0].numpy(),
+                                     mb["logprobs"][0].numpy(), mb["advantages"][0].numpy(), mb["loss_mask"][0].numpy(), mb["temperature"],
+                                     LossCfg(), scale, logits=klog)
+            assert_same_logits_micro_step(out, same, h.grad, w.grad)
             dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
-            assert np.mean(dl < 1e-3) >= 0.97 and dl.max() < 0.07
-            np.testing.assert_allclose(out["loss"].item(), want["loss"], rtol=1e-2, atol=1e-6)
+            assert int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T) and dl.max() < 0.07
             if mb["loss_mask"].any():
                 assert rel_l2(h.grad.float().cpu().numpy(), want["d_hidden"]) < 1.5e-2
                 assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1.5e-2

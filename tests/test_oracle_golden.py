@@ -204,3 +204,57 @@ def test_first_fit_decreasing_matches_reference_bins():
     got = [[lens[i] for i in b] for b in bins]
     want = [d["rank0/mb0/lengths"].tolist(), d["rank0/mb1/lengths"].tolist(), d["rank1/mb0/lengths"].tolist()]
     assert got == want
+
+
+# ----------------------------------------------------------------- same-logits checker (tests/same_logits.py)
+def test_torch_checker_matches_numpy_oracle():
+    """the torch fp64 restatement used for device-side checks at the BASELINE shapes == the numpy oracle"""
+    import torch
+
+    from tests.same_logits import bf16_ulp, chain_from_block, logprobs_entropy_t, rn_bf16_violations
+
+    rng = np.random.default_rng(0)
+    T, H, V, tau = 97, 48, 531, 0.6
+    hidden = oracle.bf16_round(rng.standard_normal((T, H)).astype(np.float32))
+    weight = oracle.bf16_round((rng.standard_normal((V, H)) * 0.4).astype(np.float32))
+    ids = rng.integers(0, V, T)
+    logits = oracle.lm_head_logits(hidden, weight, True)
+    wl, we, wlse = oracle.logprobs_entropy(oracle.shift_rows(logits), ids, tau)
+    lp, en, ls = logprobs_entropy_t(torch.from_numpy(oracle.shift_rows(logits)), torch.from_numpy(ids), tau)
+    np.testing.assert_allclose(lp.numpy(), wl, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(en.numpy(), we, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ls.numpy(), wlse, rtol=0, atol=1e-12)
+    # block form (un-shifted rows, padded pitch), chunked
+    blk = torch.zeros(T, 576, dtype=torch.bfloat16)
+    blk[:, :V] = torch.from_numpy(logits.astype(np.float32)).bfloat16()
+    lp2, en2, ls2 = chain_from_block(blk, V, torch.from_numpy(ids), tau, shift=True, chunk=13)
+    np.testing.assert_allclose(lp2.numpy(), wl, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(en2.numpy(), we, rtol=0, atol=1e-12)
+    # ulp helper and the rounding check: the oracle's own block has no violation; a block that is 1 ulp off has
+    assert bf16_ulp(torch.tensor([1.0, 1.5, 2.0, 0.75, -3.0])).tolist() == [2.0**-7, 2.0**-7, 2.0**-6, 2.0**-8, 2.0**-6]
+    h_t, w_t = torch.from_numpy(hidden).bfloat16(), torch.from_numpy(weight).bfloat16()
+    rows = torch.arange(T)
+    ok = rn_bf16_violations(blk, h_t, w_t, rows, chunk=40)
+    assert ok["n"] == T * V and ok["violations"] == 0 and ok["flips"] == 0
+    off = blk.clone()
+    off[5, 7] = (off[5, 7].double() + bf16_ulp(off[5, 7].double())).to(torch.bfloat16)
+    bad = rn_bf16_violations(off, h_t, w_t, rows)
+    assert bad["violations"] == 1 and bad["flips"] == 1 and bad["worst_excess_ulp"] > 0.4
+
+
+def test_micro_step_from_given_logits_equals_recomputed():
+    """oracle.micro_step(logits=...) with the oracle's own logits == oracle.micro_step()"""
+    rng = np.random.default_rng(1)
+    T, H, V, tau = 60, 32, 200, 0.8
+    hidden = oracle.bf16_round(rng.standard_normal((T, H)).astype(np.float32))
+    weight = oracle.bf16_round((rng.standard_normal((V, H)) * 0.3).astype(np.float32))
+    ids = rng.integers(0, V, T)
+    pos = np.concatenate([np.arange(25), np.arange(35)])
+    old = -rng.random(T).astype(np.float32) * 5
+    adv = rng.standard_normal(T).astype(np.float32)
+    mask = rng.random(T) < 0.7
+    a = oracle.micro_step(hidden, weight, ids, pos, old, adv, mask, tau, LossCfg(), int(mask.sum()))
+    b = oracle.micro_step(hidden, weight, ids, pos, old, adv, mask, tau, LossCfg(), int(mask.sum()),
+                          logits=oracle.lm_head_logits(hidden, weight, True))
+    for k in ("logp", "entropy", "loss", "dlogp", "d_hidden", "d_weight"):
+        np.testing.assert_array_equal(np.asarray(a[k]), np.asarray(b[k]))

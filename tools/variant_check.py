@@ -32,7 +32,7 @@ logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, 1 / tau)
 z = torch.zeros(T, V, device=dev); z[1:] = (hidden[:-1].float() @ W.float().t()).bfloat16().float() / tau
 ref_lse = torch.logsumexp(z, -1); ref_lp = z.gather(1, ids[:, None])[:, 0] - ref_lse
 d = (logp - ref_lp).abs()
-good = (d < 1e-3).float().mean().item() > 0.98 and d.max().item() < 0.07
+good = int((d >= 1e-3).sum()) <= 1 and d.max().item() < 0.07  # a midpoint flip of a target logit: at most one of 700 tokens
 ok &= good
 dh, dw = lm_head_backward_raw(hidden, W, ids, lse, g, 1 / tau, vchunk=8192)
 p = torch.exp(z - lse[:, None]); dz = -p * g[:, None]; dz[torch.arange(T), ids] += g
@@ -44,11 +44,18 @@ ok &= r1 < 1e-2 and r2 < 1e-2
 from prime_rl_cse_b200 import lm_head_backward_saved_raw, lm_head_forward_save_raw
 logp_s, ent_s, lse_s, _, saved = lm_head_forward_save_raw(hidden, W, ids, 1 / tau)
 ok &= bool(torch.equal(logp_s, logp) and torch.equal(ent_s, ent) and torch.equal(lse_s, lse))
+# every token from the variant's own logits (fp64), at the stated tolerance
+zk = torch.zeros(T, V, device=dev, dtype=torch.float64); zk[1:] = saved[: T - 1, :V].double() / tau
+k_lse = torch.logsumexp(zk, -1); k_lp = zk.gather(1, ids[:, None])[:, 0] - k_lse
+k_ent = k_lse - (torch.softmax(zk, -1) * zk).sum(-1)
+same_logits = max((logp.double() - k_lp).abs().max().item(), (ent.double() - k_ent).abs().max().item())
+ok &= same_logits < 2e-4
 dh_s, dw_s = lm_head_backward_saved_raw(hidden, W, ids, lse, g, 1 / tau, saved)
 dh_1, dw_1 = lm_head_backward_raw(hidden, W, ids, lse, g, 1 / tau, vchunk=V)
 s1 = ((dh_s.float() - ref_dh).norm() / ref_dh.norm()).item(); s2 = ((dw_s.float() - ref_dw).norm() / ref_dw.norm()).item()
 same = bool(torch.equal(dh_s, dh_1) and torch.equal(dw_s, dw_1))
 ok &= s1 < 1e-2 and s2 < 1e-2 and same
+print(f"same-logits max |dlogp|,|dH|: {same_logits:.2e}")
 print(f"saved-logits: dH rel {s1:.2e}, dW rel {s2:.2e}, bit-identical to single-chunk recompute: {same}")
 print(f"MSUB={os.environ.get('PRL_MSUB','1')} CTA_GROUP={os.environ.get('PRL_CTA_GROUP','2')} EPI_TMA={os.environ.get('PRL_EPI_TMA','1')}: logp max err {d.max().item():.2e}, "
       f"dH rel {r1:.2e}, dW rel {r2:.2e} -> {'OK' if ok else 'FAIL'}")
