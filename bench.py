@@ -4,13 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one pass of the hot path over one rank's share of a training batch at BASELINE.json's
-Qwen3-8B shape (configs[2], the config the metric is quoted on): 32 packed micro-batches of [1, 16384]
-tokens (4 x 4096-token rollouts each), hidden 4096, vocab 151936, bf16 -- per micro-batch: fused LM-head
-forward (log-probs + entropy), packed clipped-ratio loss, recompute-based backward to d_hidden and
-d_W_lm (fp32 accumulation across micro-batches), plus the step's group advantages.  Weak scaling: every
-rank processes its own 32 micro-batches (token shards = FSDP ranks); for N > 1 the accumulated d_W_lm is
+A "step" is one pass of the hot path over one rank's share of a training batch at BASELINE.json's Qwen3-8B shape
+(configs[2], the config the metric is quoted on): 32 packed micro-batches of [1, 16384] tokens (4 x 4096-token rollouts
+each), hidden 4096, vocab 151936, bf16 -- per micro-batch: fused LM-head forward (log-probs + entropy), packed clipped-ratio
+loss, backward to d_hidden and d_W_lm (fp32 accumulation across micro-batches), plus the step's group advantages.  Weak
+scaling: every rank processes its own 32 micro-batches (token shards = FSDP ranks); for N > 1 the accumulated d_W_lm is
 reduce-scattered once per step over NCCL as FSDP2 does.
+
+ONE run times BOTH backward modes of the LM head:
+  * recompute (the HEADLINE: top-level `value`, `e2e`, `roofline`): BASELINE.json north_star's design -- the [T, V] logits
+    never exist in HBM, the backward recomputes them per vocab chunk (4 GEMMs of T*H*V per micro-batch, 3 credited);
+  * saved_logits (`modes.saved_logits`, a labelled opt-in): one bf16 [T, V] block per micro-batch is kept between forward
+    and backward (3 GEMMs, 4.6 GiB).
+`regimes` holds short end-to-end runs of the other measurement regimes of SURVEY §8(d) (peaked logits, tau = 0.6, a clipping-
+heavy run, prompt and multi-turn masks, sequence-level loss on 32k-token rows, the 1.7B and 0.6B shapes).
+`--workload qwen3-32b-vocab8` (torchrun x N) is BASELINE config 4: the LM head vocab-sharded over the ranks.
 
 Prints ONE JSON line on rank 0.
 """
@@ -19,6 +27,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -52,29 +61,10 @@ SHAPES = {
     "qwen3-1.7b-wordle": (2048, 151936, 16384, 8, 8, 16, "token"),
     "qwen3-0.6b-reverse": (1024, 151936, 4096, 32, 1, 8, "token"),
     "qwen3-8b-deepscaler": (4096, 151936, 32768, 1, 8, 32, "sequence"),
+    "qwen3-32b-vocab8": (5120, 151936, 16384, 4, 8, 16, "token"),  # BASELINE config 4: run under torchrun, vocab-sharded
     "tiny": (128, 2048, 512, 4, 2, 4, "token"),  # CI smoke of this script only, not a benchmark
 }
-
-
-# DRAM bytes (read + write) per launch of each kernel family at the Qwen3-8B shape (T=16384, H=4096), from `ncu --set full`
-# captures (dram__bytes_read.sum + dram__bytes_write.sum).  "recompute": vocab chunk 16384, profiles/r1_lmhead_final_ncu_summary.txt
-# (the forward capture there covers a 32768-row vocabulary slice; it is scaled to V=151936).  "saved": whole-vocabulary
-# launches, profiles/r1_saved_logits_ncu_summary.txt.
-NCU_TRAFFIC_BYTES = {
-    "recompute": {
-        "lmhead_bwd_dz_kernel": 2.81e9 + 0.508e9,
-        "lmhead_bwd_dhidden_kernel": 2.05e9 + 0.245e9,
-        "lmhead_bwd_dweight_kernel": 2.06e9 + 0.242e9,
-        "lmhead_fwd_kernel": (4.75e9 + 0.007e9) * 151936 / 32768,
-    },
-    "saved": {
-        "lmhead_fwd_save_kernel": 7.834e9 + 4.972e9,
-        "dz_from_saved_logits_kernel": 4.979e9 + 4.921e9,
-        "lmhead_bwd_dhidden_kernel": 23.650e9 + 0.128e9,
-        "lmhead_bwd_dweight_kernel": 18.218e9 + 2.488e9,
-    },
-}
-NCU_TRAFFIC_SOURCE = {"recompute": "profiles/r1_lmhead_final_ncu_summary.txt", "saved": "profiles/r1_saved_logits_ncu_summary.txt"}
+VCHUNK = 16384  # default vocab chunk of prl_lmhead_bwd
 
 
 # algorithmic bytes per launch (operands read once + outputs written once), for comparison with `traffic`; vc = vocab columns
@@ -91,6 +81,25 @@ def algorithmic_bytes(kernel, T, H, V, vc):
     if kernel == "lmhead_bwd_dhidden_kernel":
         return 2.0 * (T * vc + vc * H) + (8.0 if vc < V else 2.0) * T * H
     return 2.0 * (T * vc + T * H) + 8.0 * vc * H
+
+
+def ncu_traffic(mode: str, kernel: str, workload: str):
+    """DRAM read+write bytes per launch of `kernel` from the newest committed ncu capture (profiles/*traffic.json, written by
+    tools/ncu_traffic.py from `ncu --set full` reports): {"bytes": ..., "source": ...} or None."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    if os.path.isdir(pdir):
+        for name in sorted(os.listdir(pdir)):
+            if name.endswith("traffic.json"):
+                try:
+                    with open(os.path.join(pdir, name)) as f:
+                        d = json.load(f)
+                    rec = d.get(workload, {}).get(mode, {}).get(kernel)
+                    if rec:
+                        best = {"bytes": rec["dram_bytes_per_launch"], "source": f"profiles/{name}: {rec.get('source', '')}"}
+                except Exception:  # noqa: BLE001
+                    continue
+    return best
 
 
 def measured_peaks():
@@ -116,6 +125,7 @@ class ClockSampler:
         self.index = index
 
     def start(self):
+        self.rows = []
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
@@ -139,6 +149,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        self.proc = None
         sm, mx, reasons, pw = [], [], set(), []
         for r in self.rows:
             try:
@@ -157,13 +168,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# synthetic workload
+# synthetic workload (SURVEY §8d)
 # ------------------------------------------------------------------------------------------------
-def make_workload(shape: str, rank: int, n_distinct: int, pin: bool, device="cpu", prompt_frac: float = 0.0):
-    """Micro-batches of the named shape (SURVEY §8d "D-uniform": W ~ N(0, 0.02^2), hidden ~ N(0,1)), generated on
-    `device` (the GPU for the B200 arm: seconds instead of a single-threaded CPU randn under torchrun) and returned as
-    HOST tensors (pinned when `pin`), exactly what a data loader hands the trainer; `weight` stays on `device`."""
-    H, V, T, nseg, n_mb, group, ratio_type = SHAPES[shape]
+DEFAULT_REGIME = dict(dist="uniform", tau=1.0, sigma=0.15, prompt_frac=0.0, multi_turn=False)
+
+
+def make_workload(shape: str, rank: int, n_distinct: int, pin: bool, device="cpu", regime: dict | None = None, n_mb: int = 0):
+    """Micro-batches of the named shape, generated on `device` (the GPU for the B200 arm: seconds instead of a single-threaded
+    CPU randn under torchrun) and returned as HOST tensors (pinned when `pin`), exactly what a data loader hands the trainer;
+    `weight` stays on `device`.  Regime: dist "uniform" = W ~ N(0, 0.02^2), hidden ~ N(0, 1), ids uniform
+    (near-uniform softmax, worst case: nothing is sparse); "peaked" = a rank-1 answer component lifts the sampled token's logit
+    by N(ln V + 1, 2^2) (entropy from ~0 to a few nats, what RL sees).  `prompt_frac` masks the first part of every rollout
+    (mask 0, old log-prob 0: orchestrator/batch.py:41-42), `multi_turn` additionally masks alternating environment runs.
+    Old log-probs here are a placeholder near ln(1/V); the B200 arm replaces them by (its own log-probs + N(0, sigma^2))."""
+    rg = dict(DEFAULT_REGIME, **(regime or {}))
+    H, V, T, nseg, n_mb_shape, group, ratio_type = SHAPES[shape]
+    n_mb = n_mb if n_mb > 0 else n_mb_shape
     g = torch.Generator(device=device).manual_seed(1234 + rank)
     weight = (torch.randn(V, H, generator=g, dtype=torch.float32, device=device) * 0.02).to(torch.bfloat16)
     seg = [T // nseg] * nseg
@@ -175,183 +195,228 @@ def make_workload(shape: str, rank: int, n_distinct: int, pin: bool, device="cpu
     lengths = torch.full((n_rollouts,), T // nseg, dtype=torch.int64)
     adv_r = (rewards.view(-1, group) - rewards.view(-1, group).mean(dim=1, keepdim=True)).reshape(-1)  # drgrpo, data only
     for i in range(n_distinct):
-        hidden = torch.randn(T, H, generator=g, dtype=torch.float32, device=device).to(torch.bfloat16).cpu()
-        ids = torch.randint(0, V, (T,), generator=g, device=device).cpu()
+        hidden = torch.randn(T, H, generator=g, dtype=torch.float32, device=device)
+        ids = torch.randint(0, V, (T,), generator=g, device=device)
+        if rg["dist"] == "peaked":
+            tgt = weight[ids[1:]].float()  # position t is predicted from hidden row t-1 (shift_logits)
+            lift = math.log(V) + 1.0 + 2.0 * torch.randn(T - 1, 1, generator=g, device=device)
+            hidden[:-1] += lift * tgt / (tgt * tgt).sum(-1, keepdim=True)
+        hidden = hidden.to(torch.bfloat16).cpu()
+        ids = ids.cpu()
         pos = torch.cat([torch.arange(n) for n in seg])
         mask = torch.ones(T, dtype=torch.bool)  # headline: all ones, as FakeDataLoader (rl/data.py:53)
-        old = (-11.9 + 0.15 * torch.randn(T, generator=g, device=device)).cpu()  # near ln(1/V): ratios ~ 1 (near-uniform softmax)
-        if prompt_frac > 0:  # --prompt-frac: the first part of every rollout is a prompt (mask 0, old log-prob 0, batch.py:41-42)
-            o = 0
-            for n in seg:
-                mask[o : o + int(n * prompt_frac)] = False
-                o += n
-            old[~mask] = 0.0
+        o = 0
+        for n in seg:
+            p = int(n * rg["prompt_frac"])
+            mask[o : o + p] = False
+            if rg["multi_turn"]:  # wordle-style: model turn (mask 1) / environment turn (mask 0), orchestrator/config.py:463-468
+                turn = max(8, n // 16)
+                k = o + p + turn
+                while k < o + n:
+                    mask[k : min(k + turn // 2, o + n)] = False
+                    k += 2 * turn
+            o += n
+        old = (-11.9 + rg["sigma"] * torch.randn(T, generator=g, device=device)).cpu()
+        old[~mask] = 0.0
         mb = dict(hidden=hidden.unsqueeze(0), input_ids=ids.unsqueeze(0), position_ids=pos.unsqueeze(0),
                   advantages=torch.cat([adv_r[(i * nseg + j) % n_rollouts].repeat(n) for j, n in enumerate(seg)]).unsqueeze(0),
-                  logprobs=old.unsqueeze(0), loss_mask=mask.unsqueeze(0), temperature=1.0)
+                  logprobs=old.unsqueeze(0), loss_mask=mask.unsqueeze(0), temperature=float(rg["tau"]))
         if pin:
             for k, v in mb.items():
                 if torch.is_tensor(v):
                     mb[k] = v.pin_memory()
         mbs.append(mb)
-    return dict(H=H, V=V, T=T, seg=seg, n_mb=n_mb, group=group, ratio_type=ratio_type, weight=weight, mbs=mbs,
-                rewards=rewards, lengths=lengths)
+    return dict(shape=shape, H=H, V=V, T=T, seg=seg, n_mb=n_mb, group=group, ratio_type=ratio_type, weight=weight, mbs=mbs,
+                rewards=rewards, lengths=lengths, regime=rg)
+
+
+def describe(wl, world=1) -> str:
+    rg = wl["regime"]
+    mask = ("all-ones mask" if rg["prompt_frac"] == 0 and not rg["multi_turn"] else
+            f"first {rg['prompt_frac']:.0%} of every rollout masked (prompt)" + (" + alternating environment turns masked" if rg["multi_turn"] else ""))
+    return (f"{wl['shape']}: H={wl['H']} V={wl['V']}, {wl['n_mb']} packed micro-batches x [1,{wl['T']}] tokens per GPU per step "
+            f"({len(wl['seg'])} x {wl['seg'][0]}-token rollouts each), ratio_type={wl['ratio_type']}, {mask}, tau={rg['tau']}, "
+            f"D-{rg['dist']}, old log-probs = new + N(0, {rg['sigma']}^2)")
 
 
 # ------------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import prime_rl_cse_b200 as P
-    from prime_rl_cse_b200 import _lib
-    from prime_rl_cse_b200.loss import _loss_packed_raw
+class Runner:
+    """One workload resident on one GPU: the raw C-ABI loop (`step_resident`) and the public-API loop from host buffers
+    (`step_e2e`), in either backward mode."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
+    def __init__(self, wl, dev, dist, world, args):
+        import prime_rl_cse_b200 as P
+        from prime_rl_cse_b200 import _lib
 
-        dist = dist_mod
-        dist.init_process_group(backend="nccl", device_id=dev)
-    _lib.load()
+        self.P, self._lib, self.wl, self.dev, self.dist, self.world, self.args = P, _lib, wl, dev, dist, world, args
+        H, V, T = wl["H"], wl["V"], wl["T"]
+        self.n_mb = wl["n_mb"]
+        self.cfg = P.LossConfig(ratio_type=wl["ratio_type"], ratio_length_norm=wl["ratio_type"] == "sequence", clip_ratio=8.0)
+        self.mode_id = 0 if self.cfg.ratio_type == "token" else 1
+        self.W = wl["weight"].to(dev).requires_grad_(True)  # lm_head.weight is a trainable parameter
+        self.Wd = self.W.detach()
+        self.main_grad = torch.zeros(V, H, dtype=torch.float32, device=dev)  # fp32 accumulation across micro-batches
+        self.rs_out = torch.empty((V // world) * H, dtype=torch.float32, device=dev) if world > 1 and V % world == 0 else None
+        lib = _lib.load()
+        self.ws_f = torch.empty(lib.prl_lmhead_fwd_workspace_bytes(T, H, V), dtype=torch.uint8, device=dev)
+        self.ws_b = torch.empty(lib.prl_lmhead_bwd_workspace_bytes(T, H, V, 0), dtype=torch.uint8, device=dev)
+        self.ws_bs = torch.empty(max(int(lib.prl_lmhead_bwd_saved_workspace_bytes(T, H, V)), 16), dtype=torch.uint8, device=dev)
+        self.saved_blk = None
+        # old log-probs = the path's own log-probs + N(0, sigma^2) (0 at masked positions), so that ratios are ~ exp(N(0, sigma^2))
+        g = torch.Generator(device=dev).manual_seed(99)
+        for mb in wl["mbs"]:
+            lp, _, _, _ = P.lm_head_forward_raw(mb["hidden"][0].to(dev), self.Wd, mb["input_ids"][0].to(dev), 1.0 / mb["temperature"],
+                                                workspace=self.ws_f)
+            noise = wl["regime"]["sigma"] * torch.randn(T, generator=g, device=dev)
+            if self.cfg.ratio_type == "sequence":
+                noise = noise / math.sqrt(T / len(wl["seg"]))
+            old = (lp + noise) * mb["loss_mask"][0].to(dev)
+            mb["logprobs"].copy_(old.unsqueeze(0).cpu())
+        self.dev_mbs = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in mb.items()} for mb in wl["mbs"]]
+        self.rewards_d, self.lengths_d = wl["rewards"].to(dev), wl["lengths"].to(dev)
+        bounds = [0]
+        for n in wl["seg"]:
+            bounds.append(bounds[-1] + n)
+        self.cu = torch.tensor(bounds, dtype=torch.int32, device=dev)
+        n_unmasked = int(wl["mbs"][0]["loss_mask"].sum())
+        self.loss_scale = self.n_mb * n_unmasked if self.mode_id == 0 else self.n_mb  # rl/train.py:263-267
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in wl["mbs"][0].values() if torch.is_tensor(v)) * self.n_mb
+        self.loss_host = torch.empty(self.n_mb, dtype=torch.float32).pin_memory()
+        self.rs_events = None  # (start, end) CUDA events around the last step's d_W_lm reduce-scatter
+        self.compute_end = None
 
-    wl = make_workload(args.workload, rank, n_distinct=args.distinct, pin=True, device=dev, prompt_frac=args.prompt_frac)
-    H, V, T, n_mb = wl["H"], wl["V"], wl["T"], wl["n_mb"] if args.micro_batches <= 0 else args.micro_batches
-    cfg = P.LossConfig(ratio_type=wl["ratio_type"], ratio_length_norm=False, clip_ratio=8.0)
-    mode = 0 if cfg.ratio_type == "token" else 1
-    W = wl["weight"].to(dev).requires_grad_(True)  # lm_head.weight is a trainable parameter
-    main_grad = torch.zeros(V, H, dtype=torch.float32, device=dev)  # fp32 accumulation across micro-batches
-    rs_out = torch.empty((V // world) * H, dtype=torch.float32, device=dev) if world > 1 and V % world == 0 else None
-    dev_mbs = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in mb.items()} for mb in wl["mbs"]]
-    rewards_d, lengths_d = wl["rewards"].to(dev), wl["lengths"].to(dev)
-    bounds = [0]
-    for n in wl["seg"]:
-        bounds.append(bounds[-1] + n)
-    cu = torch.tensor(bounds, dtype=torch.int32, device=dev)
-    nseg = len(wl["seg"])
-    n_unmasked = int(wl["mbs"][0]["loss_mask"].sum())
-    loss_scale = n_mb * n_unmasked if mode == 0 else n_mb  # rl/train.py:263-267
-    lib = _lib.load()
-    ws_f = torch.empty(lib.prl_lmhead_fwd_workspace_bytes(T, H, V), dtype=torch.uint8, device=dev)
-    ws_b = torch.empty(lib.prl_lmhead_bwd_workspace_bytes(T, H, V, 0), dtype=torch.uint8, device=dev)
-    # backward mode: "saved" keeps one bf16 copy of the logits per micro-batch (T x V x 2 bytes) between forward and backward,
-    # "recompute" keeps lse[T] only and recomputes the logits per vocab chunk; "auto" = the library's size policy
-    bwd_mode = args.lm_head_backward
-    if bwd_mode == "auto":
-        bwd_mode = "saved" if P.saved_logits_policy(T, V) else "recompute"
-    save_flag = bwd_mode == "saved"
-    saved_blk = torch.empty(T, int(lib.prl_lmhead_saved_logits_ld(V)), dtype=torch.bfloat16, device=dev) if save_flag else None
-    ws_bs = torch.empty(max(int(lib.prl_lmhead_bwd_saved_workspace_bytes(T, H, V)), 16), dtype=torch.uint8, device=dev)
+    def ensure_saved_block(self):
+        if self.saved_blk is None:
+            lib = self._lib.load()
+            self.saved_blk = torch.empty(self.wl["T"], int(lib.prl_lmhead_saved_logits_ld(self.wl["V"])), dtype=torch.bfloat16, device=self.dev)
 
-    Wd = W.detach()
+    def _grad_sync(self):
+        """FSDP2's gradient sync of the [lm_head, norm] group (model.py:126-131): fp32 reduce-scatter of d_W_lm, once per step"""
+        if self.dist is not None and self.rs_out is not None:
+            self.compute_end = torch.cuda.Event(enable_timing=True)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.compute_end.record()
+            a.record()
+            self.dist.reduce_scatter_tensor(self.rs_out, self.main_grad.view(-1))
+            b.record()
+            self.rs_events = (a, b)
 
-    def step_resident():
+    def step_resident(self, save: bool):
         """inputs already in HBM; raw C-ABI calls, no autograd bookkeeping"""
-        adv_all, = (P.compute_advantages_tensor(rewards_d, lengths_d, wl["group"], "drgrpo"),)
+        P, wl = self.P, self.wl
+        P.compute_advantages_tensor(self.rewards_d, self.lengths_d, wl["group"], "drgrpo")
         last = None
-        for i in range(n_mb):
-            mb = dev_mbs[i % len(dev_mbs)]
-            hid = mb["hidden"][0]
-            ids = mb["input_ids"][0]
-            if save_flag:
-                logp, ent, lse, _, _ = P.lm_head_forward_save_raw(hid, Wd, ids, 1.0 / mb["temperature"], workspace=ws_f, saved=saved_blk)
+        if save:
+            self.ensure_saved_block()
+        for i in range(self.n_mb):
+            mb = self.dev_mbs[i % len(self.dev_mbs)]
+            hid, ids, inv = mb["hidden"][0], mb["input_ids"][0], 1.0 / mb["temperature"]
+            if save:
+                logp, ent, lse, _, _ = P.lm_head_forward_save_raw(hid, self.Wd, ids, inv, workspace=self.ws_f, saved=self.saved_blk)
             else:
-                logp, ent, lse, _ = P.lm_head_forward_raw(hid, Wd, ids, 1.0 / mb["temperature"], workspace=ws_f)
+                logp, ent, lse, _ = P.lm_head_forward_raw(hid, self.Wd, ids, inv, workspace=self.ws_f)
+            from prime_rl_cse_b200.loss import _loss_packed_raw
+
             loss, ratio, clipped, is_clipped, dlogp = _loss_packed_raw(
-                logp, mb["logprobs"][0], mb["advantages"][0], mb["loss_mask"][0].view(torch.uint8), cu, nseg, mode,
-                cfg.ratio_length_norm, cfg.clip_ratio, loss_scale)
-            if save_flag:
-                P.lm_head_backward_saved_raw(hid, Wd, ids, lse, dlogp, 1.0 / mb["temperature"], saved_blk, dweight=main_grad,
-                                             dweight_accumulate=True, workspace=ws_bs)
+                logp, mb["logprobs"][0], mb["advantages"][0], mb["loss_mask"][0].view(torch.uint8), self.cu, len(wl["seg"]), self.mode_id,
+                self.cfg.ratio_length_norm, self.cfg.clip_ratio, self.loss_scale)
+            if save:
+                P.lm_head_backward_saved_raw(hid, self.Wd, ids, lse, dlogp, inv, self.saved_blk, dweight=self.main_grad,
+                                             dweight_accumulate=True, workspace=self.ws_bs)
             else:
-                P.lm_head_backward_raw(hid, Wd, ids, lse, dlogp, 1.0 / mb["temperature"], dweight=main_grad, dweight_accumulate=True,
-                                       workspace=ws_b)
+                P.lm_head_backward_raw(hid, self.Wd, ids, lse, dlogp, inv, dweight=self.main_grad, dweight_accumulate=True,
+                                       workspace=self.ws_b)
             last = loss
-        if dist is not None and rs_out is not None:
-            dist.reduce_scatter_tensor(rs_out, main_grad.view(-1))
+        self._grad_sync()
         return last
 
-    copy_stream = torch.cuda.Stream(device=dev)
-    h2d_bytes = sum(v.numel() * v.element_size() for v in wl["mbs"][0].values() if torch.is_tensor(v)) * n_mb
-    loss_host = torch.empty(n_mb, dtype=torch.float32).pin_memory()
-
-    def step_e2e():
+    def step_e2e(self, save: bool, forward_skips_masked: bool = False):
         """public API (`rl_micro_step`), HOST micro-batches: H2D of every micro-batch from pinned memory
         (prefetched one ahead on a copy stream), D2H of every micro-batch's loss."""
-        r_host = wl["rewards"].tolist()
-        adv = P.compute_advantages(r_host, wl["lengths"].tolist(), wl["group"], "drgrpo")  # host lists in/out
+        P, wl, dev = self.P, self.wl, self.dev
+        adv = P.compute_advantages(wl["rewards"].tolist(), wl["lengths"].tolist(), wl["group"], "drgrpo")  # host lists in/out
         del adv
         cur = torch.cuda.current_stream()
 
         def upload(i):
             src = wl["mbs"][i % len(wl["mbs"])]
-            with torch.cuda.stream(copy_stream):
+            with torch.cuda.stream(self.copy_stream):
                 out = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in src.items()}
                 ev = torch.cuda.Event()
-                ev.record(copy_stream)
+                ev.record(self.copy_stream)
             return out, ev
 
         nxt = upload(0)
-        for i in range(n_mb):
+        for i in range(self.n_mb):
             mb, ev = nxt
-            if i + 1 < n_mb:
+            if i + 1 < self.n_mb:
                 nxt = upload(i + 1)
             cur.wait_event(ev)
             for v in mb.values():
                 if torch.is_tensor(v):
                     v.record_stream(cur)
             hid = mb["hidden"].requires_grad_(True)
-            out = P.rl_micro_step(hid, W, mb, cfg, loss_scale, main_grad=main_grad, response_lengths=None,
-                                  forward_skips_masked=args.forward_skips_masked, save_logits=save_flag)
-            loss_host[i].copy_(out["loss"], non_blocking=True)
-        if dist is not None and rs_out is not None:
-            dist.reduce_scatter_tensor(rs_out, main_grad.view(-1))
+            out = P.rl_micro_step(hid, self.W, mb, self.cfg, self.loss_scale, main_grad=self.main_grad, response_lengths=None,
+                                  forward_skips_masked=forward_skips_masked, save_logits=save)
+            self.loss_host[i].copy_(out["loss"], non_blocking=True)
+        self._grad_sync()
         torch.cuda.current_stream().synchronize()
-        return float(loss_host[-1])
+        return float(self.loss_host[-1])
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    # ---- timing ----
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(self, fn, steps, warmup):
+        """W untimed warm-up steps, then K steps bracketed by barrier + synchronize; CUDA events; max over ranks.
+        Returns (ms for K steps [max over ranks], this rank's ms, this rank's d_W reduce-scatter ms of the last step or None)."""
         for _ in range(warmup):
             fn()
-        barrier()
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
-        wall = time.perf_counter() - t0
+        self.barrier()
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1])
+        rs_ms = self.rs_events[0].elapsed_time(self.rs_events[1]) if self.rs_events is not None else None
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0]), ms, rs_ms
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    _lib.launch_count(reset=True)
-    ms_res, _ = timed(step_resident, args.steps, args.warmup)
-    launches = _lib.launch_count(reset=True)
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
-    ms_e2e, wall_e2e = timed(step_e2e, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else {}
+    def rs_check(self):
+        """multi-GPU correctness in the record: the reduce-scattered d_W_lm shard of every rank equals the sum over ranks of
+        that shard of their local accumulators (fp64 checksums, all-reduced)"""
+        if self.dist is None or self.rs_out is None:
+            return None
+        V, H = self.wl["V"], self.wl["H"]
+        per = V // self.world
+        torch.cuda.synchronize()
+        local = self.main_grad.view(self.world, per * H).double()
+        sums = torch.stack([local.sum(dim=1), local.abs().sum(dim=1)])  # [2, world]
+        self.dist.all_reduce(sums)
+        rank = self.dist.get_rank()
+        got = self.rs_out.double().sum()
+        rel = float((got - sums[0, rank]).abs() / sums[1, rank].clamp_min(1e-300))
+        t = torch.tensor([rel], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return {"max_rel_checksum_error": float(t[0]), "ok": bool(float(t[0]) < 1e-6),
+                "what": "sum(reduce-scattered shard) vs sum over ranks of sum(local fp32 accumulator shard), relative to the sum of magnitudes"}
 
-    # per-kernel-family timing (one family per launch sequence, CUDA events on the launching stream)
-    fam = {}
-    if rank == 0 and not args.no_breakdown:
-        mb = dev_mbs[0]
+    # ---- per-kernel-family timing (one family per launch sequence, CUDA events on the launching stream) ----
+    def breakdown(self, save: bool):
+        P, wl, dev = self.P, self.wl, self.dev
+        H, V, T = wl["H"], wl["V"], wl["T"]
+        mb = self.dev_mbs[0]
         hid, ids = mb["hidden"][0], mb["input_ids"][0]
-        logp, ent, lse, _ = P.lm_head_forward_raw(hid, Wd, ids, 1.0, workspace=ws_f)
+        logp, ent, lse, _ = P.lm_head_forward_raw(hid, self.Wd, ids, 1.0, workspace=self.ws_f)
         dlogp = torch.randn(T, device=dev) / T
 
         def ev_time(fn, reps):
@@ -372,11 +437,13 @@ def run_b200(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / n
 
-        if save_flag:
+        fam = {}
+        if save:
+            self.ensure_saved_block()
             vc, nchunks = V, 1
-            fwd_s = lambda: P.lm_head_forward_save_raw(hid, Wd, ids, 1.0, workspace=ws_f, saved=saved_blk)
-            bwd_s = lambda m: P.lm_head_backward_saved_raw(hid, Wd, ids, lse, dlogp, 1.0, saved_blk, dweight=main_grad,
-                                                           dweight_accumulate=True, phase_mask=m, workspace=ws_bs)
+            fwd_s = lambda: P.lm_head_forward_save_raw(hid, self.Wd, ids, 1.0, workspace=self.ws_f, saved=self.saved_blk)  # noqa: E731
+            bwd_s = lambda m: P.lm_head_backward_saved_raw(hid, self.Wd, ids, lse, dlogp, 1.0, self.saved_blk, dweight=self.main_grad,  # noqa: E731
+                                                           dweight_accumulate=True, phase_mask=m, workspace=self.ws_bs)
             fam["lmhead_fwd_save_kernel"] = dict(ms_per_launch=ev_time(fwd_s, 8), launches_per_mb=1, flops_per_launch=2.0 * T * H * V)
             bwd_s(1)  # the block now holds real dlogits (tensor-core power is data dependent), as inside the step
             for name, mask in (("lmhead_bwd_dhidden_kernel", 2), ("lmhead_bwd_dweight_kernel", 4)):
@@ -385,71 +452,202 @@ def run_b200(args):
             fam["dz_from_saved_logits_kernel"] = dict(ms_per_launch=ev_time(lambda: bwd_s(1), 8), launches_per_mb=1, flops_per_launch=0.0,
                                                       bytes_per_launch=algorithmic_bytes("dz_from_saved_logits_kernel", T, H, V, V))
         else:
-            vc = 16384  # default vocab chunk of prl_lmhead_bwd
+            vc = min(VCHUNK, (V + 255) // 256 * 256)
             nchunks = (V + vc - 1) // vc
-            fam["lmhead_fwd_kernel"] = dict(ms_per_launch=ev_time(lambda: P.lm_head_forward_raw(hid, Wd, ids, 1.0, workspace=ws_f), 8),
+            fam["lmhead_fwd_kernel"] = dict(ms_per_launch=ev_time(lambda: P.lm_head_forward_raw(hid, self.Wd, ids, 1.0, workspace=self.ws_f), 8),
                                             launches_per_mb=1, flops_per_launch=2.0 * T * H * V)
             for name, mask in (("lmhead_bwd_dz_kernel", 1), ("lmhead_bwd_dhidden_kernel", 2), ("lmhead_bwd_dweight_kernel", 4)):
-                t_ms = ev_time(lambda: P.lm_head_backward_raw(hid, Wd, ids, lse, dlogp, 1.0, dweight=main_grad, dweight_accumulate=True,
-                                                              phase_mask=mask, workspace=ws_b), 4)
+                t_ms = ev_time(lambda: P.lm_head_backward_raw(hid, self.Wd, ids, lse, dlogp, 1.0, dweight=self.main_grad,
+                                                              dweight_accumulate=True, phase_mask=mask, workspace=self.ws_b), 4)
                 fam[name] = dict(ms_per_launch=t_ms / nchunks, launches_per_mb=nchunks, flops_per_launch=2.0 * T * H * V / nchunks)
+        return fam, vc
 
+
+def measure_mode(rn: Runner, save: bool, steps: int, warmup: int, sampler, rank: int, world: int, with_breakdown: bool):
+    """resident + end-to-end timing of one backward mode; returns the mode's record"""
+    wl, args = rn.wl, rn.args
+    H, V, T, n_mb = wl["H"], wl["V"], wl["T"], rn.n_mb
     peaks = measured_peaks()
+    mode = "saved" if save else "recompute"
+    if sampler is not None:
+        sampler.start()
+    rn._lib.launch_count(reset=True)
+    ms_res, ms_res_local, rs_ms = rn.timed(lambda: rn.step_resident(save), steps, warmup)
+    launches = rn._lib.launch_count(reset=True)
+    ms_e2e, ms_e2e_local, _ = rn.timed(lambda: rn.step_e2e(save, args.forward_skips_masked), steps, warmup)
+    clocks = sampler.stop() if sampler is not None else {}
     tokens_per_step = n_mb * T
-    value = world * tokens_per_step * args.steps / (ms_res * 1e-3)
-    e2e_value = world * tokens_per_step * args.steps / (ms_e2e * 1e-3)
+    value = world * tokens_per_step * steps / (ms_res * 1e-3)
+    e2e_value = world * tokens_per_step * steps / (ms_e2e * 1e-3)
     flops_per_token = 6.0 * H * V
-    alg_tflops = value / world * flops_per_token / 1e12
-    result = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: H={H} V={V}, {n_mb} packed micro-batches x [1,{T}] tokens per GPU per step "
-                               f"({len(wl['seg'])} x {wl['seg'][0]}-token rollouts each), ratio_type={cfg.ratio_type}, "
-                               + ("all-ones mask" if args.prompt_frac == 0 else f"first {args.prompt_frac:.0%} of every rollout masked (prompt); the e2e arm's "
-                                  "backward skips masked positions, the resident arm visits all T like the reference") + ", tau=1",
-                   "tokens_per_gpu_per_step": tokens_per_step, "parallelism": f"token-sharded dp{world} (no data-path collective; "
-                   + ("d_W_lm fp32 reduce-scatter once per step)" if world > 1 else "single GPU)"),
-                   "l2_policy": "inputs larger than L2 (W_lm 1.24 GB + 134 MB hidden per micro-batch, rotating micro-batches)",
-                   "flops_per_token_algorithmic": flops_per_token,
-                   "lm_head_backward": (f"saved-logits: one bf16 [T, V] block ({T * V * 2 / 2**30:.2f} GiB) kept per micro-batch between "
-                                        "forward and backward, rewritten in place into dlogits; 3 GEMMs of T*H*V per micro-batch"
-                                        if save_flag else "recompute: lse[T] kept only, logits recomputed per 16384-column vocab "
-                                        "chunk; 4 GEMMs of T*H*V per micro-batch")},
-        "per_gpu": value / world,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4 * n_mb + 8 * n_mb,
-                "ms_per_step": ms_e2e / args.steps, "api": "prime_rl_cse_b200.rl_micro_step + compute_advantages (host buffers)"},
-        "gpu_launches": launches_timed,
+    alg = value / world * flops_per_token / 1e12
+    rec = {
+        "value": value, "per_gpu": value / world, "ms_per_step": ms_res / steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rn.h2d_bytes, "d2h_bytes_per_step": 4 * n_mb + 8 * n_mb,
+                "ms_per_step": ms_e2e / steps, "api": "prime_rl_cse_b200.rl_micro_step + compute_advantages (host buffers)"},
+        "gpu_launches": launches * steps // (steps + warmup),
         "clocks": clocks,
-        "tensor_tflops_algorithmic_per_gpu": alg_tflops,
-        "frac_of_peak": {"measured_burst": alg_tflops / peaks["burst"], "measured_sustained": alg_tflops / peaks["sustained"],
-                         "nominal_2250": alg_tflops / 2250.0, "executed_over_algorithmic": (6.0 if save_flag else 8.0) / 6.0},
+        "lm_head_backward": (f"saved-logits (opt-in): one bf16 [T, V] block ({T * V * 2 / 2**30:.2f} GiB) kept per micro-batch between forward and "
+                             "backward, rewritten in place into dlogits; 3 GEMMs of T*H*V per micro-batch" if save else
+                             f"recompute (default; north_star): lse[T] kept only, logits recomputed per {VCHUNK}-column vocab chunk, the "
+                             "[T, V] logits never exist in HBM; 4 GEMMs of T*H*V per micro-batch, 3 credited"),
+        "tensor_tflops_algorithmic_per_gpu": alg,
+        "frac_of_peak": {"measured_burst": alg / peaks["burst"], "measured_sustained": alg / peaks["sustained"],
+                         "nominal_2250": alg / 2250.0, "executed_over_algorithmic": (6.0 if save else 8.0) / 6.0},
     }
-    if fam:
+    # per-rank table (multi-GPU): this rank's own step time, its d_W reduce-scatter time, its SM clock under load
+    if rn.dist is not None:
+        mine = torch.tensor([ms_res_local / steps, rs_ms if rs_ms is not None else -1.0, clocks.get("sm_mhz") or -1.0, ms_e2e_local / steps],
+                            dtype=torch.float64, device=rn.dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        rn.dist.all_gather(allr, mine)
+        tab = torch.stack(allr).cpu()
+        rec["per_rank"] = {"ms_per_step": [round(float(x), 3) for x in tab[:, 0]], "dw_reduce_scatter_ms": [round(float(x), 3) for x in tab[:, 1]],
+                           "sm_mhz": [float(x) for x in tab[:, 2]], "e2e_ms_per_step": [round(float(x), 3) for x in tab[:, 3]],
+                           "note": "ms_per_step: each rank's own CUDA-event time over the timed region / steps (includes waiting in the "
+                                   "step-end reduce-scatter for the slowest rank); value uses the max"}
+        rec["dw_reduce_scatter_check"] = rn.rs_check()
+    if with_breakdown and rank == 0:
+        fam, vc = rn.breakdown(save)
         top = max(fam, key=lambda k: fam[k]["ms_per_launch"] * fam[k]["launches_per_mb"])
         f = fam[top]
         achieved = f["flops_per_launch"] / (f["ms_per_launch"] * 1e-3) / 1e12
-        result["roofline"] = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
-                              "frac": achieved / peaks["sustained"],
-                              "traffic": NCU_TRAFFIC_BYTES[bwd_mode].get(top) if args.workload == "qwen3-8b-hendrycks" else None,
-                              "traffic_source": NCU_TRAFFIC_SOURCE[bwd_mode] + " (dram read+write bytes per launch)",
-                              "algorithmic_bytes": algorithmic_bytes(top, T, H, V, vc),
-                              "flops_per_launch": f["flops_per_launch"], "ms_per_launch": f["ms_per_launch"],
-                              "peak_source": peaks["source"] + " sustained (kernel timed inside a long power-capped step)",
-                              "frac_of_burst": achieved / peaks["burst"]}
-        result["kernel_breakdown_ms_per_micro_batch"] = {k: v["ms_per_launch"] * v["launches_per_mb"] for k, v in fam.items()}
-        result["kernel_tflops"] = {k: v["flops_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e12 for k, v in fam.items() if v["flops_per_launch"]}
+        tr = ncu_traffic(mode, top, wl["shape"])
+        rec["roofline"] = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peaks["sustained"], "unit": "TFLOP/s",
+                           "frac": achieved / peaks["sustained"], "traffic": tr["bytes"] if tr else None,
+                           "traffic_source": tr["source"] if tr else "no ncu capture committed for this workload/kernel",
+                           "algorithmic_bytes": algorithmic_bytes(top, T, H, V, vc),
+                           "flops_per_launch": f["flops_per_launch"], "ms_per_launch": f["ms_per_launch"],
+                           "peak_source": peaks["source"] + " sustained (kernel timed in a ~1 s back-to-back loop under the power cap)",
+                           "frac_of_burst": achieved / peaks["burst"]}
+        rec["kernel_breakdown_ms_per_micro_batch"] = {k: v["ms_per_launch"] * v["launches_per_mb"] for k, v in fam.items()}
+        rec["kernel_tflops"] = {k: v["flops_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e12 for k, v in fam.items() if v["flops_per_launch"]}
         hbm = {k: v for k, v in fam.items() if v.get("bytes_per_launch")}
         if hbm:  # the HBM-bound pass of the saved-logits backward against the measured copy bandwidth
-            result["hbm_kernels"] = {k: {"achieved_gbs": v["bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9, "peak_gbs": peaks["hbm"],
-                                         "frac": v["bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9 / peaks["hbm"],
-                                         "algorithmic_bytes": v["bytes_per_launch"]} for k, v in hbm.items()}
+            rec["hbm_kernels"] = {k: {"achieved_gbs": v["bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9, "peak_gbs": peaks["hbm"],
+                                      "frac": v["bytes_per_launch"] / (v["ms_per_launch"] * 1e-3) / 1e9 / peaks["hbm"],
+                                      "algorithmic_bytes": v["bytes_per_launch"]} for k, v in hbm.items()}
+    return rec
+
+
+REGIMES = [
+    # name, shape, micro-batches per step, regime overrides
+    ("d_peaked", "qwen3-8b-hendrycks", 4, dict(dist="peaked")),
+    ("tau_0.6", "qwen3-8b-hendrycks", 4, dict(tau=0.6)),
+    ("sigma_1.5_clipping", "qwen3-8b-hendrycks", 4, dict(dist="peaked", sigma=1.5)),
+    ("masked_prompt_25pct", "qwen3-8b-hendrycks", 4, dict(prompt_frac=0.25)),
+    ("multi_turn_wordle_1.7b", "qwen3-1.7b-wordle", 4, dict(prompt_frac=0.25, multi_turn=True)),
+    ("qwen3_1.7b_wordle_all_ones", "qwen3-1.7b-wordle", 4, {}),
+    ("sequence_mode_deepscaler_32k", "qwen3-8b-deepscaler", 2, dict(tau=0.6)),
+    ("qwen3_0.6b_reverse_config1_shape", "qwen3-0.6b-reverse", 4, {}),
+]
+
+
+def run_regimes(args, dev, names=None):
+    """short end-to-end runs (public API, host buffers, recompute backward) of the other regimes of SURVEY §8(d): 1 warm-up +
+    2 timed steps each; not the headline, but in the driver's record"""
+    out = {}
+    for name, shape, n_mb, rg in REGIMES:
+        if names and name not in names:
+            continue
+        try:
+            wl = make_workload(shape, 0, n_distinct=2, pin=True, device=dev, regime=rg, n_mb=n_mb)
+            rn = Runner(wl, dev, None, 1, args)
+            ms, _, _ = rn.timed(lambda: rn.step_e2e(False), 2, 1)
+            mb = rn.dev_mbs[0]
+            rec = {"e2e_value": wl["n_mb"] * wl["T"] * 2 / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / 2, "workload": describe(wl),
+                   "lm_head_backward": "recompute", "masked_fraction": 1.0 - float(mb["loss_mask"].float().mean())}
+            if wl["ratio_type"] == "token":  # how much clipping the regime exercises
+                out_d = rn.P.rl_micro_step(mb["hidden"], rn.W, mb, rn.cfg, rn.loss_scale, backward=False)
+                rec["clipped_fraction"] = float(out_d["is_clipped"].float().mean())
+                rec["mean_entropy_nats"] = float(out_d["entropy"].mean())
+            rec["frac_of_measured_burst"] = rec["e2e_value"] * 6.0 * wl["H"] * wl["V"] / 1e12 / measured_peaks()["burst"]
+            out[name] = rec
+            del rn, wl
+        except Exception as e:  # noqa: BLE001  context records only: never fatal for the headline
+            out[name] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_b200(args):
+    import prime_rl_cse_b200 as P  # noqa: F401
+    from prime_rl_cse_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group(backend="nccl", device_id=dev)
+    _lib.load()
+    if args.workload == "qwen3-32b-vocab8":
+        return run_vocab_sharded(args, rank, world, dev, dist)
+
+    regime = dict(prompt_frac=args.prompt_frac)
+    wl = make_workload(args.workload, rank, n_distinct=args.distinct, pin=True, device=dev, regime=regime, n_mb=args.micro_batches)
+    rn = Runner(wl, dev, dist, world, args)
+    H, V, T, n_mb = wl["H"], wl["V"], wl["T"], rn.n_mb
+    sampler = ClockSampler(local)  # every rank samples its own GPU
+    modes = ["recompute", "saved"] if args.lm_head_backward == "both" else [args.lm_head_backward]
+    recs = {}
+    for m in modes:
+        recs[m] = measure_mode(rn, m == "saved", args.steps, args.warmup, sampler, rank, world, not args.no_breakdown)
+        if m == "saved":
+            rn.saved_blk = None
+            torch.cuda.empty_cache()
+    head_mode = modes[0]
+    head = recs[head_mode]
+    result = {
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": describe(wl, world), "tokens_per_gpu_per_step": n_mb * T,
+                   "parallelism": f"token-sharded dp{world} (no data-path collective; "
+                   + ("d_W_lm fp32 reduce-scatter once per step)" if world > 1 else "single GPU)"),
+                   "l2_policy": "inputs larger than L2 (W_lm 1.24 GB + 134 MB hidden per micro-batch, rotating micro-batches)",
+                   "flops_per_token_algorithmic": 6.0 * H * V, "lm_head_backward": head["lm_head_backward"],
+                   "headline_mode": head_mode},
+        "per_gpu": head["per_gpu"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+        "tensor_tflops_algorithmic_per_gpu": head["tensor_tflops_algorithmic_per_gpu"], "frac_of_peak": head["frac_of_peak"],
+    }
+    for k in ("roofline", "kernel_breakdown_ms_per_micro_batch", "kernel_tflops", "hbm_kernels", "per_rank", "dw_reduce_scatter_check"):
+        if k in head:
+            result[k] = head[k]
+    result["modes"] = {("saved_logits" if m == "saved" else m): recs[m] for m in modes}
+    del rn
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_regimes and args.workload == "qwen3-8b-hendrycks":
+        result["regimes"] = run_regimes(args, dev)
     if rank == 0 and not args.no_torch_baseline:
         result["torch_gpu_reference"] = torch_gpu_reference(wl, dev)
     if rank == 0:
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline:
             result["cpu_baseline"] = cpu_baseline(args.workload, steps=3, warmup=0)
+            if args.workload == "qwen3-8b-hendrycks" and world == 1:
+                result["cpu_baseline_config1"] = cpu_baseline_config1()
         emit(result)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 4: Qwen3-32B shape, LM head vocab-sharded over the ranks (torchrun x N)
+# ------------------------------------------------------------------------------------------------
+def run_vocab_sharded(args, rank, world, dev, dist):
+    from prime_rl_cse_b200.vocab_parallel import bench_vocab_sharded
+
+    res = bench_vocab_sharded(args, rank, world, dev, dist, SHAPES[args.workload], ClockSampler(dev.index), measured_peaks())
+    if rank == 0:
+        res.update({"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                    "vs_baseline": None, "dtype": "bf16", "data": "synthetic"})
+        emit(res)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -503,24 +701,32 @@ def torch_gpu_reference(wl, dev, T_s=4096, reps=3):
 CPU_SAMPLE_TOKENS = 2048
 
 
-def cpu_step(wl, T_s):
+def cpu_inputs(wl, T_s, nseg=4):
+    """leaf tensors and per-token inputs of one bounded CPU sample, prepared OUTSIDE any timed region"""
     from oracle import torch_port
 
-    H, V = wl["H"], wl["V"]
     mb = wl["mbs"][0]
-    nseg = 4
     seg = [T_s // nseg] * nseg
-    hidden = mb["hidden"][0, :T_s].float().clone().requires_grad_(True)  # config 1 runs fp32 on the CPU
-    weight = wl["weight"].float().clone().requires_grad_(True)
-    ids = mb["input_ids"][0, :T_s]
-    pos = torch.cat([torch.arange(n) for n in seg])
+    seg[-1] += T_s - sum(seg)
     adv_list = torch_port.advantages_cpu(wl["rewards"].tolist(), wl["lengths"].tolist(), wl["group"], "drgrpo")
-    adv = torch.cat([torch.full((n,), adv_list[i]) for i, n in enumerate(seg)])
-    mask = torch.ones(T_s, dtype=torch.bool)
-    old = mb["logprobs"][0, :T_s]
+    return dict(hidden=mb["hidden"][0, :T_s].float().clone(),  # config 1 runs fp32 on the CPU
+                weight=wl["weight"].float().clone(), ids=mb["input_ids"][0, :T_s], pos=torch.cat([torch.arange(n) for n in seg]),
+                adv=torch.cat([torch.full((n,), adv_list[i % len(adv_list)]) for i, n in enumerate(seg)]),
+                mask=torch.ones(T_s, dtype=torch.bool), old=mb["logprobs"][0, :T_s].clone(), T=T_s)
+
+
+def cpu_step(wl, inp):
+    """one timed CPU micro-step: train.py:285-310 (forward, loss, entropy, backward) + the step's advantages.  Returns seconds."""
+    from oracle import torch_port
+
+    hidden = inp["hidden"].detach().requires_grad_(True)
+    weight = inp["weight"].detach().requires_grad_(True)
+    hidden.grad = weight.grad = None
     t0 = time.perf_counter()
-    loss, _, _ = torch_port.micro_step_cpu(hidden, weight, ids, pos, old, adv, mask, 1.0, wl["ratio_type"], False, 8.0, T_s)
-    return time.perf_counter() - t0, float(loss)
+    torch_port.advantages_cpu(wl["rewards"].tolist(), wl["lengths"].tolist(), wl["group"], "drgrpo")
+    torch_port.micro_step_cpu(hidden, weight, inp["ids"], inp["pos"], inp["old"], inp["adv"], inp["mask"], 1.0, wl["ratio_type"],
+                              wl["ratio_type"] == "sequence", 8.0, inp["T"])
+    return time.perf_counter() - t0
 
 
 def cpu_baseline(workload: str, steps: int, warmup: int) -> dict:
@@ -528,16 +734,35 @@ def cpu_baseline(workload: str, steps: int, warmup: int) -> dict:
     torch.set_num_threads(cores)
     wl = make_workload(workload, 0, n_distinct=1, pin=False)
     T_s = min(CPU_SAMPLE_TOKENS, wl["T"])
+    inp = cpu_inputs(wl, T_s)
     for _ in range(warmup):
-        cpu_step(wl, T_s)
-    times = [cpu_step(wl, T_s)[0] for _ in range(max(steps, 1))]
+        cpu_step(wl, inp)
+    times = [cpu_step(wl, inp) for _ in range(max(steps, 1))]
     dt = statistics.median(times)
     return {"value": T_s / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"one packed row of {T_s} tokens (4 segments) at H={wl['H']} V={wl['V']}, fp32, torch CPU ops "
                       f"(oracle/torch_port.py restating rl/train.py:285-310), median of {max(steps,1)} run(s), {dt:.2f} s each"}
 
 
+def cpu_baseline_config1() -> dict:
+    """BASELINE config 1 EXACTLY: Qwen3-0.6B shape, 4 problems x 8 rollouts x 128 tokens = one packed
+    [1, 4096] row, fp32, all host cores, compute_advantages + RL loss fwd/bwd; 1 warm-up + 3 timed runs, median."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = make_workload("qwen3-0.6b-reverse", 0, n_distinct=1, pin=False)
+    inp = cpu_inputs(wl, wl["T"], nseg=32)
+    cpu_step(wl, inp)
+    times = [cpu_step(wl, inp) for _ in range(3)]
+    dt = statistics.median(times)
+    return {"value": wl["T"] / dt, "unit": UNIT, "cores": torch.get_num_threads(), "os_cpu_count": cores, "kind": "port",
+            "sample": f"config 1 exactly: T={wl['T']} (32 x 128-token rollouts, 4 groups of 8), H={wl['H']}, V={wl['V']}, fp32, "
+                      f"1 warm-up + 3 timed, median {dt:.2f} s per step"}
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU op sequence for the path (oracle/torch_port.py: the reference is pure Python
+    and /root/reference does not travel to the GPU box) on the host cores, each step a bounded sample of the B200 arm's
+    workload; inputs are prepared once, outside the timed loop."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
@@ -546,22 +771,22 @@ def run_reference(args):
     torch.set_num_threads(cores)
     wl = make_workload(args.workload, 0, n_distinct=1, pin=False)
     T_s = min(CPU_SAMPLE_TOKENS, wl["T"])
+    inp = cpu_inputs(wl, T_s)
     for _ in range(args.warmup):
-        cpu_step(wl, T_s)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_step(wl, T_s)
-    dt = time.perf_counter() - t0
+        cpu_step(wl, inp)
+    dt = sum(cpu_step(wl, inp) for _ in range(args.steps))
     value = T_s * args.steps / dt
     H, V = wl["H"], wl["V"]
     sample = (f"each step = one packed row of {T_s} tokens (4 segments) of the same workload shape, fp32, all host threads "
               f"(torch CPU ops, oracle/torch_port.py restating the reference's rl/train.py:285-310; the reference is pure Python "
-              f"and /root/reference does not travel to the GPU box)")
+              f"and /root/reference does not travel to the GPU box); leaf-tensor setup is outside the timed region")
     emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: H={H} V={V}, bounded sample of {T_s} tokens per step", "parallelism": "host CPU, rank 0 only"},
+        "config": {"workload": f"{args.workload}: H={H} V={V}, bounded sample of {T_s} tokens per step (the B200 arm runs "
+                               f"{wl['n_mb'] * wl['T']} tokens per step of the same shape)", "parallelism": "host CPU, rank 0 only",
+                   "same_config_as_b200_arm": False},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -579,11 +804,15 @@ def main():
     ap.add_argument("--distinct", type=int, default=3, help="distinct micro-batches kept resident and rotated")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--no-regimes", action="store_true", help="skip the short runs of the other measurement regimes (N=1 only)")
     ap.add_argument("--forward-skips-masked", action="store_true", help="e2e arm: also restrict the forward to unmasked positions")
     ap.add_argument("--prompt-frac", type=float, default=0.0, help="mask the first fraction of every rollout (default 0 = all-ones mask)")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-on-GPU reference-chain timing")
-    ap.add_argument("--lm-head-backward", default="auto", choices=["auto", "saved", "recompute"],
-                    help="saved = keep the bf16 logits between forward and backward (T*V*2 bytes); recompute = keep lse only")
+    ap.add_argument("--lm-head-backward", default="both", choices=["both", "saved", "recompute"],
+                    help="both (default): time the recompute backward (headline) and the saved-logits backward (modes.saved_logits); "
+                         "recompute / saved: only that one")
+    ap.add_argument("--fused-rs", type=int, default=1, help="vocab-sharded workload: 1 = d_hidden reduce-scatter fused into the GEMM "
+                    "epilogue over peer memory, 0 = NCCL reduce-scatter after the GEMM")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -193,6 +193,32 @@ int prl_lmhead_bwd_saved(const void* hidden, const void* weight, const int64_t* 
 size_t prl_lmhead_bwd_saved_workspace_bytes(int64_t T, int32_t H, int64_t V);
 
 /* ------------------------------------------------------------------------------------------
+ * Masked positions (prompt / environment tokens).  The reference multiplies their loss by the mask
+ * (src/prime_rl/trainer/rl/loss.py:104; mask built by src/prime_rl/orchestrator/batch.py:41-44), so their dlogits rows
+ * are zero: the LM-head GEMMs only need the ACTIVE positions.  These entry points replace host-side index tensors
+ * (nonzero / index_select / index_copy_) by device kernels:
+ *   prl_partition_positions: stable partition of positions [shift, T) of a packed row by mask (uint8, torch.bool storage):
+ *     order[j] = position in slot j (active ones first, then the others, each in order), j < T - shift;
+ *     slot[t] = slot of position t (-1 for t < shift: shift_logits' zero row has no source row); *n_active (device int32).
+ *   prl_gather_rows_bf16:  dst[j, :H] = src[order[j] - shift, :H] for j < n (bf16 rows, H % 8 == 0, 16-byte aligned)
+ *     and ids_out[j] = ids[order[j]] (ids / ids_out may be NULL).
+ *   prl_gather_tokens_f32: x_out[j] = x[order[j]], j < n, for up to three fp32 vectors (NULL pairs are skipped).
+ *   prl_scatter_tokens_f32: x_out[t] = x[slot[t]] if 0 <= slot[t] < n_valid, x_first if slot[t] < 0, else 0; t < T.
+ *   prl_scatter_rows_bf16: dst[r, :H] = src[slot[r + shift], :H] if that slot is in [0, n_valid), else zeros; r < T
+ *     (the gradient w.r.t. hidden back in source-row order; masked rows and the last `shift` rows get exact zeros).
+ * ---------------------------------------------------------------------------------------- */
+int prl_partition_positions(const uint8_t* mask, int64_t T, int32_t shift, int32_t* order, int32_t* slot, int32_t* n_active,
+                            void* stream);
+int prl_gather_rows_bf16(const void* src, const int64_t* ids, const int32_t* order, int64_t n, int32_t shift, int32_t H, void* dst,
+                         int64_t* ids_out, void* stream);
+int prl_gather_tokens_f32(const int32_t* order, int64_t n, const float* a, float* a_out, const float* b, float* b_out, const float* c,
+                          float* c_out, void* stream);
+int prl_scatter_tokens_f32(const int32_t* slot, int64_t T, int64_t n_valid, const float* a, float* a_out, float a_first, const float* b,
+                           float* b_out, float b_first, const float* c, float* c_out, float c_first, void* stream);
+int prl_scatter_rows_bf16(const void* src, const int32_t* slot, int64_t T, int64_t n_valid, int32_t shift, int32_t H, void* dst,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * On-device logging statistics ("next" row N1).  Replaces the per-micro-batch boolean-index + blocking .to("cpu")
  * of src/prime_rl/trainer/rl/train.py:313-333 and the padded all-gather of every masked token in
  * Tensors.compute_stats (src/prime_rl/trainer/utils.py:228-256) by five running moments per logged key:

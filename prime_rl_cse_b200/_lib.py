@@ -69,6 +69,12 @@ _SIGNATURES = {
          c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_size_t, c_void_p],
     ),
     "prl_lmhead_bwd_saved_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int64]),
+    "prl_partition_positions": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "prl_gather_rows_bf16": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "prl_gather_tokens_f32": (c_int32, [c_void_p, c_int64] + [c_void_p] * 6 + [c_void_p]),
+    "prl_scatter_tokens_f32": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float,
+                                         c_void_p, c_void_p, c_float, c_void_p]),
+    "prl_scatter_rows_bf16": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "prl_debug_schedule": (c_int32, [c_int32, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "prl_gemm_bf16_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
 }

@@ -17,7 +17,7 @@ import warnings
 import torch
 from torch import nn
 
-from . import _lib
+from . import _lib, rows
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -189,48 +189,43 @@ def _forward_any(h, w, i, inv_temp, shift, round_bf16, save):
 
 class _FusedLMHead(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, hidden, weight, ids, inv_temp, shift, round_bf16, main_grad, active_positions=None, forward_active_only=False,
+    def forward(ctx, hidden, weight, ids, inv_temp, shift, round_bf16, main_grad, partition=None, forward_active_only=False,
                 save_logits=None):
         lead = hidden.shape[:-1]
         h2 = hidden.detach().reshape(-1, hidden.shape[-1]).contiguous()
         w2 = weight.detach().contiguous()
         i2 = ids.detach().reshape(-1).contiguous().to(torch.int64)
-        ctx.compact = None
+        T, V = h2.shape[0], w2.shape[0]
+        ctx.part = None           # rows.Partition when the row was processed in "active positions first" order
         ctx.saved_logits = None   # bf16 logits kept for the backward (consumed by it)
         ctx.had_saved = False
-        ctx.saved_rows = "all"    # which rows the block covers: "all" source rows or "compact" (the active rows only)
         needs_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        if active_positions is not None:
-            # positions that can receive a gradient; position 0 of a shifted row is a constant (no source row)
-            pos = active_positions.reshape(-1).to(torch.int64)
-            pos = pos[pos >= int(shift)]
-            rows = pos - int(shift)
-            ctx.compact = (pos, rows)
-        if forward_active_only and ctx.compact is not None:
-            # forward on the compacted rows only: outputs at the other positions are 0 (nothing downstream reads them: the
-            # loss multiplies by the mask and the trainer logs `[loss_mask]` slices only, rl/train.py:313-333)
-            pos, rows = ctx.compact
-            T = h2.shape[0]
-            logp = torch.zeros(T, dtype=torch.float32, device=h2.device)
-            ent = torch.zeros(T, dtype=torch.float32, device=h2.device)
-            lse = torch.zeros(T, dtype=torch.float32, device=h2.device)
-            if pos.numel() > 0:
-                h_c, i_c = h2.index_select(0, rows), i2.index_select(0, pos)
-                save = needs_grad and saved_logits_policy(h_c.shape[0], w2.shape[0], save_logits)
-                lp_c, ent_c, lse_c, ctx.saved_logits = _forward_any(h_c, w2, i_c, inv_temp, False, round_bf16, save)
-                ctx.saved_rows = "compact"
-                logp.index_copy_(0, pos, lp_c)
-                ent.index_copy_(0, pos, ent_c)
-                lse.index_copy_(0, pos, lse_c)
-            if shift and T > 0:  # shift_logits' all-zero row: closed form (rl/loss.py:55-56)
-                import math
-
-                ln_v = math.log(float(w2.shape[0]))
-                logp[0], ent[0], lse[0] = -ln_v, ln_v, ln_v
+        # Masked positions get no gradient (loss.py:104): with a partition of the row (active positions first, rows.py) the
+        # backward -- and optionally the forward -- only visits the first n_active slots.  Nothing to gain when every
+        # position is active, or when no backward will follow and the forward has to cover the whole row anyway.
+        if partition is not None and T > 0 and (needs_grad or forward_active_only) and partition.n_active < partition.rows:
+            part = partition
+            n_fwd = part.n_active if forward_active_only else part.rows
+            # log-prob / entropy are 0 at positions the forward skipped (nothing downstream reads them: the loss multiplies by
+            # the mask and the trainer logs `[loss_mask]` slices only, rl/train.py:313-333); position 0 of a shifted row is the
+            # closed form of shift_logits' all-zero row (rl/loss.py:55-56)
+            lp_first, ent_first, lse_first = rows.first_row_values(V)
+            if n_fwd > 0:
+                h_p, i_p = rows.gather_rows(h2, i2, part, n_fwd)
+                save = needs_grad and saved_logits_policy(n_fwd, V, save_logits)
+                lp_p, ent_p, lse_p, ctx.saved_logits = _forward_any(h_p, w2, i_p, inv_temp, False, round_bf16, save)
+                logp, ent = rows.scatter_tokens(part, n_fwd, (lp_p, lp_first), (ent_p, ent_first))
+            else:
+                h_p = h2.new_empty(0, h2.shape[1])
+                i_p = i2.new_empty(0)
+                lse_p = torch.empty(0, dtype=torch.float32, device=h2.device)
+                logp, ent = rows.scatter_tokens(part, 0, (None, lp_first), (None, ent_first))
+            ctx.part = part
+            ctx.save_for_backward(h_p, w2, i_p, lse_p)
         else:
-            save = needs_grad and saved_logits_policy(h2.shape[0], w2.shape[0], save_logits)
+            save = needs_grad and saved_logits_policy(T, V, save_logits)
             logp, ent, lse, ctx.saved_logits = _forward_any(h2, w2, i2, inv_temp, shift, round_bf16, save)
-        ctx.save_for_backward(h2, w2, i2, lse)
+            ctx.save_for_backward(h2, w2, i2, lse)
         ctx.cfg = (inv_temp, shift, round_bf16, hidden.shape, main_grad)
         logp, ent = logp.reshape(lead), ent.reshape(lead)
         ctx.mark_non_differentiable(ent)
@@ -244,7 +239,7 @@ class _FusedLMHead(torch.autograd.Function):
         need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         none_tail = (None,) * 8
         # the kept logits are consumed by the first backward; a second one (retain_graph) falls back to the recompute
-        if ctx.saved_logits is None and getattr(ctx, "had_saved", False):
+        if ctx.saved_logits is None and ctx.had_saved:
             _warn_fallback("second backward through the same graph: the block was consumed by the first")
         ctx.had_saved = ctx.had_saved or ctx.saved_logits is not None
         saved, ctx.saved_logits = ctx.saved_logits, None
@@ -256,24 +251,18 @@ class _FusedLMHead(torch.autograd.Function):
                 return lm_head_backward_saved_raw(h, w2, i, l, gg, inv_temp, block, sh, **kw)
             return lm_head_backward_raw(h, w2, i, l, gg, inv_temp, sh, round_bf16, **kw)
 
-        if ctx.compact is not None:
-            # Only positions with a non-zero d loss / d logp contribute to d_hidden and d_W: run the backward on the
-            # compacted rows (exactly the same sums, minus the all-zero terms) and scatter d_hidden back.
-            pos, rows = ctx.compact
-            dh = torch.zeros(h2.shape, dtype=torch.bfloat16, device=h2.device) if need_h else None
-            dw = None
-            if pos.numel() > 0:
-                if saved is not None and ctx.saved_rows == "all":
-                    block = saved[: h2.shape[0]].index_select(0, rows)  # logits of the active rows
-                    del saved
-                else:
-                    block = saved
-                dh_c, dw = run(h2.index_select(0, rows), i2.index_select(0, pos), lse.index_select(0, pos), g.index_select(0, pos),
-                               False, block)
-                if need_h:
-                    dh.index_copy_(0, rows, dh_c)
+        if ctx.part is not None:
+            # Only the active positions contribute to d_hidden and d_W: they are the first n slots of the partitioned row the
+            # forward saved (exactly the same sums, minus the all-zero terms); d_hidden goes back to source-row order.
+            part, n = ctx.part, ctx.part.n_active
+            dh = dw = None
+            if n > 0:
+                (g_p,) = rows.gather_tokens(part, n, g)
+                dh_c, dw = run(h2[:n], i2[:n], lse[:n], g_p, False, saved)
             elif need_w and dw_target is None:
                 dw = torch.zeros_like(w2)
+            if need_h:
+                dh = rows.scatter_rows(dh_c if n > 0 else None, part, n, w2.shape[1])
             if dw_target is not None:
                 dw = None
             return ((dh.reshape(hshape) if dh is not None else None), dw) + none_tail
@@ -292,7 +281,7 @@ def fused_lm_head_logprobs_entropy(
     shift: bool = True,
     round_bf16: bool = True,
     main_grad: torch.Tensor | None = None,
-    active_positions: torch.Tensor | None = None,
+    loss_mask: torch.Tensor | rows.Partition | None = None,
     forward_active_only: bool = False,
     save_logits: bool | None = None,
 ) -> tuple[torch.Tensor, torch.Tensor]:
@@ -305,9 +294,10 @@ def fused_lm_head_logprobs_entropy(
     reference's `shift_logits` does for batch size 1 (packed micro-batches, rl/data.py:13-23).
     `main_grad`: optional fp32/bf16 [V,H] buffer; the weight gradient is then ACCUMULATED into it by the
     kernel and `weight.grad` is left untouched (fused gradient accumulation across micro-batches).
-    `active_positions`: optional int64 index tensor of the positions that can receive a non-zero gradient (e.g.
-    `loss_mask.nonzero()`): the backward then skips every other row (prompt / environment tokens) — identical gradients,
-    proportionally less recompute.  By default the forward still covers all T positions, as the reference does; with
+    `loss_mask`: optional bool [..., T] tensor (the micro-batch's `loss_mask`) or a `rows.Partition` built from it: positions
+    with mask False receive no gradient from the loss (rl/loss.py:104), so the backward skips their rows (prompt / environment
+    tokens) — identical gradients, proportionally less work; the row is reordered "active positions first" by the library's own
+    kernels (rows.py).  By default the forward still covers all T positions, as the reference does; with
     `forward_active_only=True` it visits the active positions only and returns 0 for log-prob and entropy elsewhere.
     `save_logits`: False / None (default) recomputes the logits in the backward, so nothing of size [T, V] is ever stored;
     True keeps one bf16 copy of the logits (T x V x 2 bytes) between forward and backward so that the backward needs two
@@ -322,8 +312,13 @@ def fused_lm_head_logprobs_entropy(
         raise ValueError("temperature must be positive (the online softmax tracks the maximum logit)")
     if hidden.dim() > 2 and hidden.shape[:-2].numel() != 1:
         raise ValueError("only one packed row per call (micro_batch_size == 1 for packed batches)")
+    partition = None
+    if loss_mask is not None:
+        partition = loss_mask if isinstance(loss_mask, rows.Partition) else rows.partition_positions(loss_mask, bool(shift))
+        if partition.T != input_ids.numel() or partition.shift != int(bool(shift)):
+            raise ValueError("loss_mask / partition does not match input_ids [..., T] and `shift`")
     return _FusedLMHead.apply(hidden, weight, input_ids, 1.0 / float(temperature), bool(shift), bool(round_bf16), main_grad,
-                              active_positions, bool(forward_active_only), save_logits)
+                              partition, bool(forward_active_only), save_logits)
 
 
 class FusedLMHead(nn.Module):

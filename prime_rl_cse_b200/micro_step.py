@@ -8,6 +8,7 @@ from typing import Any
 
 import torch
 
+from . import rows
 from .lm_head import fused_lm_head_logprobs_entropy
 from .loss import compute_loss
 from .segments import get_response_lengths
@@ -31,8 +32,8 @@ def rl_micro_step(
     caller wishes); `micro_batch` is a `MicroBatch` (rl/data.py:13-23) whose tensors are already on the
     device (train.py:275-279).  Returns loss, logprobs, entropy and the three logging tensors of
     `compute_loss`; with `backward=True` also runs `loss.backward()` (train.py:310).  `skip_masked`: tokens with
-    `loss_mask == False` get a zero gradient (loss.py:104), so the recompute backward only visits the unmasked positions;
-    skipped automatically when every token is unmasked.  `forward_skips_masked` (opt-in) also restricts the FORWARD to the
+    `loss_mask == False` get a zero gradient (loss.py:104), so the backward only visits the unmasked positions (the row is
+    partitioned "active first" on the device, rows.py); a no-op when every token is unmasked.  `forward_skips_masked` (opt-in) also restricts the FORWARD to the
     unmasked positions: log-probs / entropy come back as 0 at masked positions (the reference computes values there that
     nothing reads: the loss multiplies by the mask and the trainer logs `[loss_mask]` slices, train.py:313-333).
     `save_logits`: see `fused_lm_head_logprobs_entropy` (None = keep the bf16 logits for the backward when they fit)."""
@@ -43,19 +44,17 @@ def rl_micro_step(
     old_logprobs = micro_batch["logprobs"]
     temperature = micro_batch["temperature"]
 
+    # the partition kernel is queued before the segment lengths are fetched, so the one D2H sync of train.py:291 also
+    # covers its 4-byte active-position count
+    partition = rows.partition_positions(loss_mask, shift=True) if ((skip_masked and backward) or forward_skips_masked) else None
+
     # train.py:291 -- done first so its single D2H sync happens before the heavy kernels are queued
     if response_lengths is None:
         response_lengths = get_response_lengths(position_ids)
 
-    active = None
-    if skip_masked and backward:
-        nz = loss_mask.reshape(-1).nonzero().reshape(-1)  # sizes it on the host: same sync point as the segment lengths
-        if nz.numel() < loss_mask.numel():
-            active = nz
-
     # train.py:285-288 + 302-303
     logprobs, entropy = fused_lm_head_logprobs_entropy(hidden, lm_head_weight, input_ids, temperature, main_grad=main_grad,
-                                                       active_positions=active, forward_active_only=forward_skips_masked,
+                                                       loss_mask=partition, forward_active_only=forward_skips_masked,
                                                        save_logits=save_logits)
 
     # train.py:292-299

@@ -308,14 +308,14 @@ def test_lmhead_forward_vs_oracle(P, T, H, V, tau):
     de = np.abs(ent[0].cpu().numpy() - we)
     # tcgen05 and the fp64 oracle accumulate in different orders: a logit that sits on a bf16 rounding
     # midpoint may round the other way (SURVEY §7 "bf16 rounding"), moving logp by <= 1 bf16 ulp of the logit.
-    assert int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T) and dl.max() < 0.07, (dl.max(), int((dl >= 1e-3).sum()))
+    assert int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T, H) and dl.max() < 0.07, (dl.max(), int((dl >= 1e-3).sum()))
     assert de.max() < 1e-3, de.max()
     # ... and that is all there is: the kernel's logits are the correctly rounded product, and from THOSE logits every token matches
     klog, blk = kernel_logits(hidden, weight, ids, tau)
     rn = rn_bf16_violations(blk, hidden.cuda(), weight.cuda(), torch.arange(T - 1, device="cuda"))
     assert rn["violations"] == 0, rn
     kl, ke, _ = oracle.logprobs_entropy(oracle.shift_rows(klog), ids.numpy(), tau)
-    assert np.abs(lp[0].cpu().numpy() - kl).max() < 2e-4 and np.abs(ent[0].cpu().numpy() - ke).max() < 2e-4
+    assert np.abs(lp[0].cpu().numpy() - kl).max() < 5e-4 and np.abs(ent[0].cpu().numpy() - ke).max() < 5e-4
     # closed-form first row (shift_logits' zero row): logp = -ln V, entropy = ln V
     assert abs(lp[0, 0].item() + np.log(V)) < 1e-5 and abs(ent[0, 0].item() - np.log(V)) < 1e-5
 
@@ -358,7 +358,7 @@ def test_lmhead_fixtures_from_reference(P):
         # the reference's own numbers (its GEMM rounds midpoint logits its own way)
         dl = np.abs(out["logprobs"][0].cpu().numpy() - d[f"{key}/logp"])
         n_out = int((dl >= 1e-3).sum())
-        assert n_out <= allowed_flip_outliers(dl.size) and dl.max() < 0.07, (key, dl.max(), n_out)
+        assert n_out <= allowed_flip_outliers(dl.size, hidden.shape[-1]) and dl.max() < 0.07, (key, dl.max(), n_out)
         np.testing.assert_allclose(out["loss"].item(), d[f"{key}/loss"], rtol=1e-4 if n_out == 0 else 5e-3, atol=1e-6)
         assert rel_l2(hidden.grad.float().cpu().numpy(), d[f"{key}/d_hidden"]) < 1e-2, key
         assert rel_l2(weight.grad.float().cpu().numpy(), d[f"{key}/d_weight"]) < 1e-2, key
@@ -397,7 +397,7 @@ def test_micro_step_vs_oracle(P, T, H, V, tau, mode, vchunk, save):
         assert_same_logits_micro_step(out, same, h.grad, w.grad)  # every token at the stated tolerances
         dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
         n_out = int((dl >= 1e-3).sum())
-        assert n_out <= allowed_flip_outliers(T) and dl.max() < 0.07, (dl.max(), n_out)
+        assert n_out <= allowed_flip_outliers(T, H) and dl.max() < 0.07, (dl.max(), n_out)
         np.testing.assert_allclose(out["loss"].item(), want["loss"], rtol=1e-4 if n_out == 0 else 5e-3, atol=1e-6)
         assert rel_l2(h.grad.float().cpu().numpy(), want["d_hidden"]) < 1e-2
         assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1e-2
@@ -449,8 +449,8 @@ def test_fused_lm_head_module_in_hf_qwen3(P):
     assert out.shape == (1, T, 2)
     lp, ent = out[..., 0], out[..., 1].detach()
     d = (lp - ref_lp).abs()
-    assert int((d >= 1e-3).sum()) <= allowed_flip_outliers(T) and d.max().item() < 0.07
-    assert int(((ent - ref_ent).abs() >= 1e-3).sum()) <= allowed_flip_outliers(T)
+    assert int((d >= 1e-3).sum()) <= allowed_flip_outliers(T, cfg.hidden_size) and d.max().item() < 0.07
+    assert int(((ent - ref_ent).abs() >= 1e-3).sum()) <= allowed_flip_outliers(T, cfg.hidden_size)
     (lp * 0.01).sum().backward()
     gw = model.lm_head.weight.grad.float()
     ge = model.model.embed_tokens.weight.grad.float()
@@ -482,10 +482,10 @@ def test_next_rows_sft_cross_entropy_and_logprob_recompute(P):
     old = torch.from_numpy(wl).float().cuda() + 0.1
     lp, err = P.recompute_logprobs(h.cuda().unsqueeze(0), w.cuda(), ids.cuda().unsqueeze(0), tau, old.unsqueeze(0))
     dl = np.abs(lp[0].cpu().numpy() - wl)
-    assert int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T) and dl.max() < 0.07
+    assert int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T, H) and dl.max() < 0.07
     klog, _ = kernel_logits(h, w, ids, tau)
     kl, _, _ = oracle.logprobs_entropy(oracle.shift_rows(klog), ids.numpy(), tau)
-    assert np.abs(lp[0].cpu().numpy() - kl).max() < 2e-4  # every token, from the kernel's own logits
+    assert np.abs(lp[0].cpu().numpy() - kl).max() < 5e-4  # every token, from the kernel's own logits
     np.testing.assert_allclose(err[0].cpu().numpy(), np.exp(lp[0].cpu().numpy() - old.cpu().numpy()), rtol=1e-5)
 
 
@@ -610,7 +610,7 @@ def test_micro_step_edge_shapes(P, T, H, V, save):
     same = oracle.micro_step(hidden.float().numpy(), weight.float().numpy(), ids.numpy(), pos, old, adv, mask, tau, LossCfg(), T, logits=klog)
     assert_same_logits_micro_step(out, same, h.grad if T > 1 else None, w.grad if T > 1 else None)
     dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
-    assert dl.max() < 0.07 and int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T)
+    assert dl.max() < 0.07 and int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T, H)
     if T > 1:
         assert rel_l2(h.grad.float().cpu().numpy(), want["d_hidden"]) < 1.5e-2
         assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1.5e-2
@@ -810,7 +810,7 @@ def test_micro_step_on_reference_packed_batches(P):
                                      LossCfg(), scale, logits=klog)
             assert_same_logits_micro_step(out, same, h.grad, w.grad)
             dl = np.abs(out["logprobs"][0].cpu().numpy() - want["logp"])
-            assert int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T) and dl.max() < 0.07
+            assert int((dl >= 1e-3).sum()) <= allowed_flip_outliers(T, H) and dl.max() < 0.07
             if mb["loss_mask"].any():
                 assert rel_l2(h.grad.float().cpu().numpy(), want["d_hidden"]) < 1.5e-2
                 assert rel_l2(w.grad.float().cpu().numpy(), want["d_weight"]) < 1.5e-2
@@ -820,24 +820,95 @@ def test_micro_step_on_reference_packed_batches(P):
 
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
 def test_backward_skips_masked_positions_exactly(P, save):
-    """`active_positions`: the compacted backward gives the same gradients as the full one (masked rows contribute zeros)."""
+    """`loss_mask`: the backward over the active positions only gives the same gradients as the full one (masked rows
+    contribute zeros); no index tensors are built on the host."""
     T, H, V, tau = 900, 256, 6000, 0.7
     hidden, weight, ids = _mk(T, H, V, 31)
     mask = torch.rand(T) < 0.6
     mask[0] = True  # position 0 is active but has no source row: must be ignored
     g = (torch.randn(T) / T) * mask
     outs = []
-    for active in (None, mask.nonzero().reshape(-1).cuda()):
+    for lm in (None, mask.cuda().unsqueeze(0)):
         h = hidden.cuda().requires_grad_(True)
         w = weight.cuda().requires_grad_(True)
-        lp, _ = P.fused_lm_head_logprobs_entropy(h.unsqueeze(0), w, ids.cuda().unsqueeze(0), tau, active_positions=active,
-                                                 save_logits=save)
+        lp, _ = P.fused_lm_head_logprobs_entropy(h.unsqueeze(0), w, ids.cuda().unsqueeze(0), tau, loss_mask=lm, save_logits=save)
         (lp[0] * g.cuda()).sum().backward()
         outs.append((h.grad.float(), w.grad.float()))
     (dh0, dw0), (dh1, dw1) = outs
     assert ((dh1 - dh0).norm() / dh0.norm()).item() < 2e-3 and ((dw1 - dw0).norm() / dw0.norm()).item() < 2e-3
     inactive_rows = (~mask[1:]).nonzero().reshape(-1).cuda()
     assert float(dh1[inactive_rows].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("T,shift,p_active", [(1, 1, 1.0), (2, 1, 0.5), (700, 1, 0.6), (1024, 0, 0.3), (1025, 1, 0.0), (4099, 1, 1.0),
+                                              (40000, 1, 0.75), (33, 0, 0.5)])
+def test_row_partition_gather_scatter_kernels(P, T, shift, p_active):
+    """rows.py / prl_partition_positions & co. against numpy: stable partition (active positions first), row gather, token and
+    row scatter with exact zeros at masked rows."""
+    from prime_rl_cse_b200 import rows
+
+    rng = np.random.default_rng(T + shift)
+    mask = rng.random(T) < p_active
+    H = 64
+    part = rows.partition_positions(cu(mask), bool(shift))
+    idx = np.arange(shift, T)
+    act, ina = idx[mask[shift:]], idx[~mask[shift:]]
+    want_order = np.concatenate([act, ina])
+    assert part.n_active == len(act) and part.rows == T - shift
+    np.testing.assert_array_equal(part.order.cpu().numpy()[: T - shift], want_order)
+    want_slot = np.full(T, -1, dtype=np.int64)
+    want_slot[want_order] = np.arange(T - shift)
+    np.testing.assert_array_equal(part.slot.cpu().numpy()[:T], want_slot)
+    hidden = torch.randn(T, H).bfloat16()
+    ids = torch.from_numpy(rng.integers(0, 1000, T))
+    for n in sorted({0, len(act), T - shift}):
+        h_p, i_p = rows.gather_rows(hidden.cuda(), ids.cuda(), part, n)
+        assert torch.equal(h_p.cpu(), hidden[want_order[:n] - shift]) and torch.equal(i_p.cpu(), ids[want_order[:n]])
+        x, y = torch.randn(T), torch.randn(T)
+        (x_p, y_p) = rows.gather_tokens(part, n, x.cuda(), y.cuda())
+        assert torch.equal(x_p.cpu(), x[want_order[:n]]) and torch.equal(y_p.cpu(), y[want_order[:n]])
+        (x_back,) = rows.scatter_tokens(part, n, (x_p, -7.0))
+        want = torch.zeros(T)
+        want[want_order[:n]] = x[want_order[:n]]
+        want[:shift] = -7.0
+        assert torch.equal(x_back.cpu(), want)
+        dh = rows.scatter_rows(h_p if n > 0 else None, part, n, H)
+        want_dh = torch.zeros(T, H, dtype=torch.bfloat16)
+        want_dh[want_order[:n] - shift] = hidden[want_order[:n] - shift]
+        assert torch.equal(dh.cpu(), want_dh)
+
+
+@pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
+def test_masked_micro_step_edge_masks(P, save):
+    """all-masked rows (the orchestrator's padding batches, batch.py:153-161), a single active token, and an all-active row
+    through rl_micro_step: exact zeros where nothing is active, same results as the unpartitioned path otherwise"""
+    T, H, V, tau = 260, 64, 1000, 0.8
+    hidden, weight, ids = _mk(T, H, V, 77)
+    rng = np.random.default_rng(0)
+    pos = np.concatenate([np.arange(100), np.arange(160)])
+    adv = rng.standard_normal(T).astype(np.float32)
+    old = -rng.random(T).astype(np.float32) * 3
+    for kind in ("none", "one", "all"):
+        mask = np.zeros(T, dtype=bool) if kind != "all" else np.ones(T, dtype=bool)
+        if kind == "one":
+            mask[137] = True
+        res = []
+        for skip in (False, True):
+            h = hidden.cuda().requires_grad_(True)
+            w = weight.cuda().requires_grad_(True)
+            mb = dict(input_ids=ids.cuda().unsqueeze(0), position_ids=cu(pos).unsqueeze(0), advantages=cu(adv).unsqueeze(0),
+                      logprobs=cu(old).unsqueeze(0), loss_mask=cu(mask).unsqueeze(0), temperature=tau)
+            out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), max(int(mask.sum()), 1), skip_masked=skip, save_logits=save)
+            res.append((out, h.grad.float(), w.grad.float()))
+        (o0, dh0, dw0), (o1, dh1, dw1) = res
+        assert torch.equal(o0["logprobs"], o1["logprobs"]) and torch.equal(o0["entropy"], o1["entropy"])
+        assert o0["loss"].item() == o1["loss"].item()
+        if kind == "none":
+            assert float(dh1.abs().max()) == 0.0 and float(dw1.abs().max()) == 0.0 and o1["loss"].item() == 0.0
+        else:
+            assert ((dh1 - dh0).norm() / dh0.norm()).item() < 2e-3 and ((dw1 - dw0).norm() / dw0.norm()).item() < 2e-3
+        if kind == "one":
+            assert int((dh1.abs().sum(dim=1) > 0).sum()) == 1 and float(dh1[136].abs().max()) > 0.0  # only source row 136
 
 
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])

@@ -32,7 +32,7 @@ logp, ent, lse, _ = lm_head_forward_raw(hidden, W, ids, 1 / tau)
 z = torch.zeros(T, V, device=dev); z[1:] = (hidden[:-1].float() @ W.float().t()).bfloat16().float() / tau
 ref_lse = torch.logsumexp(z, -1); ref_lp = z.gather(1, ids[:, None])[:, 0] - ref_lse
 d = (logp - ref_lp).abs()
-good = int((d >= 1e-3).sum()) <= 1 and d.max().item() < 0.07  # a midpoint flip of a target logit: at most one of 700 tokens
+good = int((d >= 1e-3).sum()) <= 3 and d.max().item() < 0.07  # midpoint flips of target logits: 6e-7 x K per token (tests/same_logits.py)
 ok &= good
 dh, dw = lm_head_backward_raw(hidden, W, ids, lse, g, 1 / tau, vchunk=8192)
 p = torch.exp(z - lse[:, None]); dz = -p * g[:, None]; dz[torch.arange(T), ids] += g
