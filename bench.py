@@ -178,7 +178,7 @@ def make_workload(shape: str, rank: int, n_distinct: int, pin: bool, device="cpu
     CPU randn under torchrun) and returned as HOST tensors (pinned when `pin`), exactly what a data loader hands the trainer;
     `weight` stays on `device`.  Regime: dist "uniform" = W ~ N(0, 0.02^2), hidden ~ N(0, 1), ids uniform
     (near-uniform softmax, worst case: nothing is sparse); "peaked" = a rank-1 answer component lifts the sampled token's logit
-    by N(ln V + 1, 2^2) (entropy from ~0 to a few nats, what RL sees).  `prompt_frac` masks the first part of every rollout
+    by N(ln V + 3, 2^2) (mean entropy ~2-3 nats instead of ln V = 11.9: closer to what RL sees).  `prompt_frac` masks the first part of every rollout
     (mask 0, old log-prob 0: orchestrator/batch.py:41-42), `multi_turn` additionally masks alternating environment runs.
     Old log-probs here are a placeholder near ln(1/V); the B200 arm replaces them by (its own log-probs + N(0, sigma^2))."""
     rg = dict(DEFAULT_REGIME, **(regime or {}))
@@ -199,7 +199,7 @@ def make_workload(shape: str, rank: int, n_distinct: int, pin: bool, device="cpu
         ids = torch.randint(0, V, (T,), generator=g, device=device)
         if rg["dist"] == "peaked":
             tgt = weight[ids[1:]].float()  # position t is predicted from hidden row t-1 (shift_logits)
-            lift = math.log(V) + 1.0 + 2.0 * torch.randn(T - 1, 1, generator=g, device=device)
+            lift = math.log(V) + 3.0 + 2.0 * torch.randn(T - 1, 1, generator=g, device=device)
             hidden[:-1] += lift * tgt / (tgt * tgt).sum(-1, keepdim=True)
         hidden = hidden.to(torch.bfloat16).cpu()
         ids = ids.cpu()
@@ -587,7 +587,14 @@ def run_b200(args):
         dist.init_process_group(backend="nccl", device_id=dev)
     _lib.load()
     if args.workload == "qwen3-32b-vocab8":
-        return run_vocab_sharded(args, rank, world, dev, dist)
+        res = run_vocab_sharded(args, rank, world, dev, dist)
+        if rank == 0:
+            res.update({"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                        "vs_baseline": None, "dtype": "bf16", "data": "synthetic"})
+            emit(res)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     regime = dict(prompt_frac=args.prompt_frac)
     wl = make_workload(args.workload, rank, n_distinct=args.distinct, pin=True, device=dev, regime=regime, n_mb=args.micro_batches)
@@ -641,16 +648,159 @@ def run_b200(args):
 # BASELINE config 4: Qwen3-32B shape, LM head vocab-sharded over the ranks (torchrun x N)
 # ------------------------------------------------------------------------------------------------
 def run_vocab_sharded(args, rank, world, dev, dist):
-    from prime_rl_cse_b200.vocab_parallel import bench_vocab_sharded
+    """Every rank owns V/world rows of W_lm (FSDP2's dim-0 shard, model.py:100-135) and brings its own packed micro-batch per
+    round; see prime_rl_cse_b200.parallel.VocabShardedLMHead for the exchange steps.  Weak scaling in N: tokens per rank per
+    step are fixed, the shard shrinks as 1/N, so the work per rank per round (N*T tokens x V/N columns) is constant."""
+    import prime_rl_cse_b200 as P
+    from prime_rl_cse_b200.parallel import VocabShardedLMHead
 
-    res = bench_vocab_sharded(args, rank, world, dev, dist, SHAPES[args.workload], ClockSampler(dev.index), measured_peaks())
-    if rank == 0:
-        res.update({"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-                    "vs_baseline": None, "dtype": "bf16", "data": "synthetic"})
-        emit(res)
-    if dist is not None:
+    if dist is None:
+        raise SystemExit("--workload qwen3-32b-vocab8 needs torchrun with >= 2 ranks (python bench.py --gpus N --workload qwen3-32b-vocab8)")
+    H, V, T, nseg, n_mb, group, ratio_type = SHAPES[args.workload]
+    n_mb = args.micro_batches if args.micro_batches > 0 else n_mb
+    peaks = measured_peaks()
+    g = torch.Generator(device=dev).manual_seed(4321)  # the SAME W on every rank (each keeps its shard; the full copy is for the check)
+    W_full = (torch.randn(V, H, generator=g, dtype=torch.float32, device=dev) * 0.02).to(torch.bfloat16)
+    v0, v1 = P.vocab_shard_bounds(V, world, rank)
+    W_shard = W_full[v0:v1].clone()
+    main_grad = torch.zeros(v1 - v0, H, dtype=torch.float32, device=dev)
+    head = VocabShardedLMHead(W_shard, V, main_grad=main_grad, fused_rs=bool(args.fused_rs))
+    cfg = P.LossConfig(ratio_type=ratio_type, ratio_length_norm=False, clip_ratio=8.0)
+    gl = torch.Generator(device=dev).manual_seed(1234 + rank)  # different tokens on every rank
+    seg = [T // nseg] * nseg
+    mbs = []
+    for i in range(min(args.distinct, n_mb)):
+        hidden = torch.randn(T, H, generator=gl, device=dev).to(torch.bfloat16)
+        ids = torch.randint(0, V, (T,), generator=gl, device=dev)
+        lp, _, _, _ = P.lm_head_forward_raw(hidden, W_full, ids, 1.0)
+        old = lp + 0.15 * torch.randn(T, generator=gl, device=dev)
+        adv = torch.cat([torch.full((n,), float(a)) for n, a in zip(seg, (0.5, -0.25, 1.0, -0.5))]).to(dev)
+        mb = dict(hidden=hidden.unsqueeze(0), input_ids=ids.unsqueeze(0), position_ids=torch.cat([torch.arange(n) for n in seg]).unsqueeze(0).to(dev),
+                  advantages=adv.unsqueeze(0), logprobs=old.unsqueeze(0), loss_mask=torch.ones(1, T, dtype=torch.bool, device=dev), temperature=1.0)
+        mbs.append(mb)
+    host_mbs = [{k: (v.cpu().pin_memory() if torch.is_tensor(v) else v) for k, v in mb.items()} for mb in mbs]
+    loss_scale = n_mb * T
+    copy_stream = torch.cuda.Stream(device=dev)
+    loss_host = torch.empty(n_mb, dtype=torch.float32).pin_memory()
+
+    # ---- parity: one round from a zeroed accumulator against the UNSHARDED fused path on this GPU (same kernels, full W)
+    out = head.micro_step(mbs[0]["hidden"], mbs[0], cfg, T)
+    gathered = head.gather_inputs(mbs[0]["hidden"], mbs[0]["input_ids"])
+    torch.cuda.current_stream().wait_event(gathered["ready"])
+    lp_u, ent_u, lse_u, _ = P.lm_head_forward_raw(mbs[0]["hidden"][0], W_full, mbs[0]["input_ids"][0], 1.0)
+    from prime_rl_cse_b200.loss import _loss_packed_raw
+
+    cu = torch.tensor([0] + list(torch.tensor(seg).cumsum(0)), dtype=torch.int32, device=dev)
+    _, _, _, _, g_u = _loss_packed_raw(lp_u, mbs[0]["logprobs"][0], mbs[0]["advantages"][0], mbs[0]["loss_mask"][0].view(torch.uint8), cu, nseg, 0,
+                                       False, 8.0, T)
+    dh_u, _ = P.lm_head_backward_raw(mbs[0]["hidden"][0], W_full, mbs[0]["input_ids"][0], lse_u, g_u, 1.0, want_dweight=False)
+    # unsharded d_W needs every rank's tokens: gather (lse, dlogp) of all ranks, run the unsharded backward over world*T tokens
+    pair = torch.stack([lse_u, g_u], dim=1).contiguous()
+    pair[0, 1] = 0.0
+    pair_all = torch.empty(world * T, 2, device=dev)
+    dist.all_gather_into_tensor(pair_all, pair)
+    dw_u = torch.zeros(V, H, dtype=torch.float32, device=dev)
+    fix = pair_all[:, 1].contiguous()
+    P.lm_head_backward_raw(gathered["h_all"], W_full, gathered["i_all"], pair_all[:, 0].contiguous(), fix, 1.0, want_dhidden=False, dweight=dw_u,
+                           dweight_accumulate=True)
+
+    def rel(a, b):
+        return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+
+    par = torch.tensor([float((out["logprobs"] - lp_u).abs().max()), float((out["entropy"] - ent_u).abs().max()), rel(out["d_hidden"], dh_u),
+                        rel(main_grad, dw_u[v0:v1])], dtype=torch.float64, device=dev)
+    dist.all_reduce(par, op=dist.ReduceOp.MAX)
+    parity = {"max_abs_dlogp": float(par[0]), "max_abs_dentropy": float(par[1]), "rel_l2_d_hidden": float(par[2]), "rel_l2_d_weight_shard": float(par[3]),
+              "ok": bool(par[0] < 1e-3 and par[1] < 1e-3 and par[2] < 1e-2 and par[3] < 1e-2),
+              "what": f"{world}-rank vocab-sharded round vs the unsharded fused path on each rank's own tokens (max over ranks)"}
+    del dw_u, dh_u, pair_all, gathered, out
+    main_grad.zero_()
+    torch.cuda.empty_cache()
+
+    def step(e2e: bool):
+        cur = torch.cuda.current_stream()
+
+        def stage(i):
+            if not e2e:
+                mb = mbs[i % len(mbs)]
+            else:
+                with torch.cuda.stream(copy_stream):
+                    mb = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host_mbs[i % len(host_mbs)].items()}
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                cur.wait_event(ev)
+                for v in mb.values():
+                    if torch.is_tensor(v):
+                        v.record_stream(cur)
+            return mb, head.gather_inputs(mb["hidden"], mb["input_ids"])  # the all-gather runs ahead on the comm stream
+
+        nxt = stage(0)
+        for i in range(n_mb):
+            mb, gathered = nxt
+            if i + 1 < n_mb:
+                nxt = stage(i + 1)
+            o = head.micro_step(mb["hidden"], mb, cfg, loss_scale, gathered=gathered)
+            if e2e:
+                loss_host[i].copy_(o["loss"], non_blocking=True)
+        if e2e:
+            torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        mine = float(t[0])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), mine
+
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    from prime_rl_cse_b200 import _lib
+
+    _lib.launch_count(reset=True)
+    ms_res, ms_mine = timed(lambda: step(False), args.steps, args.warmup)
+    launches = _lib.launch_count(reset=True)
+    exch = head.exchange_ms()
+    ms_e2e, _ = timed(lambda: step(True), args.steps, args.warmup)
+    clocks = sampler.stop()
+    tab = torch.tensor([ms_mine / args.steps, clocks.get("sm_mhz") or -1.0], dtype=torch.float64, device=dev)
+    allr = [torch.empty_like(tab) for _ in range(world)]
+    dist.all_gather(allr, tab)
+    tokens = world * n_mb * T
+    value = tokens * args.steps / (ms_res * 1e-3)
+    alg = value / world * 6.0 * H * V / 1e12
+    return {
+        "value": value, "ms_per_step": ms_res / args.steps, "scaling": "weak", "per_gpu": value / world,
+        "config": {"workload": f"{args.workload}: H={H} V={V} vocab-sharded {world}-way ({v1 - v0} rows per rank), {n_mb} rounds per step, every rank "
+                               f"brings one packed micro-batch of [1,{T}] tokens per round ({world * T} tokens swept per rank per round), "
+                               "token-ratio loss, all-ones mask, tau=1, D-uniform",
+                   "parallelism": f"vocab-sharded tp{world}: all-gather hidden, all-to-all of 16 B/token partials, all-gather (lse, dlogp), "
+                                  + ("d_hidden reduce-scatter fused into the GEMM epilogue (TMA reduce-add into the owner's symmetric memory)"
+                                     if head.fused_rs else "NCCL reduce-scatter of d_hidden after the GEMM"),
+                   "lm_head_backward": "recompute", "flops_per_token_algorithmic": 6.0 * H * V,
+                   "l2_policy": "inputs larger than L2 (hidden of a round: 1.3 GB at 8 ranks)"},
+        "e2e": {"value": tokens * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n_mb * sum(v.numel() * v.element_size() for v in host_mbs[0].values() if torch.is_tensor(v)),
+                "d2h_bytes_per_step": 4 * n_mb, "ms_per_step": ms_e2e / args.steps, "api": "VocabShardedLMHead.micro_step (host buffers)"},
+        "gpu_launches": launches * args.steps // (args.steps + args.warmup), "clocks": clocks,
+        "exchange_ms_last_round": exch,
+        "parity_vs_unsharded": parity,
+        "per_rank": {"ms_per_step": [round(float(x[0]), 3) for x in allr], "sm_mhz": [float(x[1]) for x in allr]},
+        "tensor_tflops_algorithmic_per_gpu": alg,
+        "frac_of_peak": {"measured_burst": alg / peaks["burst"], "measured_sustained": alg / peaks["sustained"], "nominal_2250": alg / 2250.0,
+                         "executed_over_algorithmic": 8.0 / 6.0},
+        "roofline": {"kernel": "the four GEMM sweeps of a round (forward, dlogits recompute, d_hidden, d_weight) on one rank", "bound": "tensor",
+                     "achieved": alg * 8.0 / 6.0, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": alg * 8.0 / 6.0 / peaks["sustained"],
+                     "traffic": None, "note": "executed flops (8 H V per token) / step time, exchanges included"},
+    }
 
 
 def torch_gpu_reference(wl, dev, T_s=4096, reps=3):

@@ -163,6 +163,27 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
                    int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, int32_t phase_mask,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Vocab-sharded LM head (BASELINE.json config 4), backward with the reduce-scatter of d_hidden FUSED into the GEMM epilogue.
+ * hidden / ids / lse / dlogp hold T = n_peers * rows_per_peer tokens: the packed rows of all peers back to back (token-owner
+ * major), `weight` is this rank's vocab shard.  Instead of a local d_hidden, every output tile of the d_hidden GEMM is
+ * reduce-added (fp32, cp.reduce.async.bulk.tensor performed at the owner's L2, over NVLink for remote owners) into
+ * d_hidden_peers[owner][row - owner * rows_per_peer, :H], owner = row / rows_per_peer.  d_hidden_peers is a HOST array of
+ * n_peers device pointers to fp32 [rows_per_peer, H] accumulators that are mapped into this process (CUDA IPC / symmetric
+ * memory; entry self_index is this rank's own buffer).  The caller zeroes its accumulator and synchronises the peers before
+ * the call, and again before reading the result.  Replaces the NCCL reduce-scatter that follows the
+ * GEMM in the unfused path; everything else (dlogits recompute, d_weight shard) is as in prl_lmhead_bwd. */
+int prl_lmhead_bwd_scatter(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp,
+                           int64_t T, int32_t H, int64_t V, int64_t v_offset, float inv_temp, int32_t shift, int32_t round_bf16,
+                           void* const* d_hidden_peers, int32_t n_peers, int64_t rows_per_peer, int32_t self_index,
+                           void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, int32_t phase_mask,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* Peer memory for prl_lmhead_bwd_scatter: map a buffer another rank of the same node exported with cudaIpcGetMemHandle
+ * (64-byte handle) into this process under the CURRENT device, enabling peer access lazily; *dev_ptr_out is the base of the
+ * exporter's allocation.  HOST pointers in, device pointer out.  prl_ipc_close unmaps it. */
+int prl_ipc_open(const void* handle, void** dev_ptr_out);
+int prl_ipc_close(void* dev_ptr);
+
 /* ------------------------------------------------------------------------------------------
  * Saved-logits variant of the same forward / backward pair: trades T x saved_ld x 2 bytes of HBM for the
  * backward's logits recompute (one of the four [T,H]x[H,V]-sized GEMMs of a micro-step).  Still replaces

@@ -57,6 +57,13 @@ _SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_float, c_int32, c_int32,
          c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_size_t, c_void_p],
     ),
+    "prl_lmhead_bwd_scatter": (
+        c_int32,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_float, c_int32, c_int32,
+         c_void_p, c_int32, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_size_t, c_void_p],
+    ),
+    "prl_ipc_open": (c_int32, [c_void_p, c_void_p]),
+    "prl_ipc_close": (c_int32, [c_void_p]),
     "prl_lmhead_saved_logits_ld": (c_int64, [c_int64]),
     "prl_lmhead_fwd_save": (
         c_int32,

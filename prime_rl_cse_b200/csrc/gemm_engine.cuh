@@ -81,6 +81,13 @@ struct GemmParams {
   uint64_t a_desc_hi, b_desc_hi;  // smem descriptor templates (everything but the start address)
   uint32_t a_kstep, b_kstep;      // byte advance of the start address per UMMA_K step
   uint64_t hint_a, hint_b, hint_c;  // L2 eviction priority of the A / B loads and of the epilogue's stores
+  // Fused reduce-scatter of C over peer GPUs (vocab-sharded d_hidden): rows [j * peer_rows, (j + 1) * peer_rows)
+  // of C belong to peer j and are reduce-added (fp32, TMA, performed at the owner's L2 over NVLink) into ITS accumulator through
+  // tma_c_peer[j]; m_rot rotates the m-tile order so that the ranks do not all target the same owner at the same time.
+  int32_t n_peers;
+  int32_t peer_rows;
+  int32_t m_rot;
+  CUtensorMap tma_c_peer[8];
   EpiParams epi;
 };
 
@@ -112,6 +119,7 @@ __host__ __device__ __forceinline__ Item decode_item(const GemmParams& p, int it
   } else {
     const int vs = idx / rows;  // (n split, k split)
     it.m_tile = m0 + idx % rows;
+    if (p.m_rot > 0) it.m_tile = (it.m_tile + p.m_rot) % p.m_tiles;
     it.split = vs / ksp;
     it.k_begin = (vs - it.split * ksp) * p.k_per_split;
     it.k_count = imin(p.k_per_split, p.k_blocks - it.k_begin);
@@ -680,7 +688,12 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
                 const void* src = smem_stage + (ewarp * 2 + stage_buf) * 4096;
                 const int32_t col = (int32_t)(out_bf16 ? (n0 + (ch & ~1) * 32) : c0);
                 const bool reduce = (EPI == EPI_STORE) && (e.flags & ST_LOAD_F32);
-                if (p.hint_c == 0) {
+                if (EPI == EPI_STORE && p.n_peers > 0) {
+                  // fused reduce-scatter: this 32-row slab belongs to one owner (peer_rows % 32 == 0); add it into the owner's
+                  // fp32 accumulator (local or NVLink peer memory), rows beyond the owner's range are clipped by its map
+                  const int owner = row0_warp / p.peer_rows;
+                  if (owner < p.n_peers) ptx::tma_reduce_add_2d(&p.tma_c_peer[owner], src, col, row0_warp - owner * p.peer_rows);
+                } else if (p.hint_c == 0) {
                   if (reduce)
                     ptx::tma_reduce_add_2d(&p.tma_c, src, col, row0_warp);
                   else

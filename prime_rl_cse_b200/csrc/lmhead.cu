@@ -477,14 +477,49 @@ int prl_lmhead_merge_partials(const float* partials, int32_t nparts, int64_t T, 
 
 }  // extern "C"
 
+// fused reduce-scatter of d_hidden (vocab-sharded LM head): rows [j * rows_per_peer, (j + 1) * rows_per_peer) go to ptrs[j]
+struct PeerScatter {
+  void* const* ptrs;      // host array of n DEVICE pointers: every peer's fp32 [rows_per_peer, H] accumulator (own one included)
+  int32_t n;
+  int64_t rows_per_peer;
+  int32_t self;           // this rank's index (sets the m-tile rotation)
+};
+
 // d_hidden and d_weight GEMMs over one block of dlogits: dz[T][ldz] holds vocab columns [c0, c0 + vce) of this shard
 static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __nv_bfloat16* dz, int64_t vc, int64_t c0, int64_t vce,
                             int64_t T, int32_t H, void* d_hidden, int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype,
                             int32_t accumulate_dw, int32_t phase_mask, bool first, bool last, int64_t nchunks, float* dh_acc,
-                            int band, cudaStream_t st) {
+                            int band, cudaStream_t st, const PeerScatter* peers = nullptr) {
   const int64_t vc_full = nchunks > 1 ? vc : vce;  // every chunk of one backward takes the same k-split decision
   // ---- K2: d_hidden[T,H] += dz[T,vce] x W[c0:c0+vce, :]   (A K-major, B MN-major) ----
-  if (d_hidden && (phase_mask & 2)) {
+  if (peers && (phase_mask & 2)) {
+    // every tile is reduce-added into its owner's accumulator (zeroed by the owner before the round): no local d_hidden buffer
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    int rc = make_operand_map(&p.tma_a, dz, false, T, vce, vc, BLOCK_M);
+    if (rc) return rc;
+    rc = make_operand_map(&p.tma_b, W + c0 * H, true, H, vce, H, BLOCK_N);
+    if (rc) return rc;
+    set_tiling(p, T, H, vce, EPI_STORE);
+    schedule_tiles(p, band);
+    make_desc_defaults(p, false, true);
+    p.epi.m_rows = T;
+    p.epi.n_cols = H;
+    p.epi.ldc = H;
+    p.epi.flags = ST_STORE_F32 | ST_LOAD_F32 | ST_TMA;
+    p.n_peers = peers->n;
+    p.peer_rows = (int32_t)peers->rows_per_peer;
+    for (int j = 0; j < peers->n; ++j) {
+      rc = make_output_map(&p.tma_c_peer[j], peers->ptrs[j], peers->rows_per_peer, H, H, true);
+      if (rc) return rc;
+    }
+    // start at the tiles of the NEXT rank's tokens: at any time the ranks write to different owners
+    const int64_t rows_per_tile = (int64_t)BLOCK_M * cta_group() * msub(EPI_STORE);
+    p.m_rot = (int32_t)((((int64_t)(peers->self + 1) % peers->n) * peers->rows_per_peer) / rows_per_tile) % p.m_tiles;
+    set_hints(p, "DH", 0, 0, 0);
+    rc = launch_gemm<false, true, EPI_STORE>(p, st, "lmhead_bwd_dhidden_rs_kernel");
+    if (rc) return rc;
+  } else if (d_hidden && (phase_mask & 2)) {
     GemmParams p;
     memset(&p, 0, sizeof(p));
     int rc = make_operand_map(&p.tma_a, dz, false, T, vce, vc, BLOCK_M);
@@ -595,10 +630,10 @@ size_t prl_lmhead_bwd_workspace_bytes(int64_t T, int32_t H, int64_t V, int64_t v
   return round_up((int64_t)dz, 1024) + round_up((int64_t)dh, 1024) + 1024;
 }
 
-int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T, int32_t H,
-                   int64_t V, int64_t v_offset, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden, int32_t d_hidden_f32,
-                   void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, int32_t phase_mask, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+static int lmhead_bwd_impl(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T,
+                           int32_t H, int64_t V, int64_t v_offset, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden,
+                           int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk,
+                           int32_t phase_mask, void* workspace, size_t workspace_bytes, void* stream, const PeerScatter* peers) {
   PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_bwd: bad sizes");
   PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_bwd: shift must be 0 or 1");
   PRL_REQUIRE(inv_temp > 0.f && inv_temp < INFINITY, PRL_ERR_BAD_ARG, "lmhead_bwd: temperature must be positive and finite");
@@ -654,11 +689,36 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
     }
     {
       const int rc = lmhead_bwd_gemms(hidden, W, dz, vc, c0, vce, T, H, d_hidden, d_hidden_f32, d_weight, d_weight_dtype, accumulate_dw,
-                                      phase_mask, c == 0, c == nchunks - 1, nchunks, dh_acc, 8, st);
+                                      phase_mask, c == 0, c == nchunks - 1, nchunks, dh_acc, 8, st, peers);
       if (rc) return rc;
     }
   }
   return PRL_OK;
+}
+
+int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T, int32_t H,
+                   int64_t V, int64_t v_offset, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden, int32_t d_hidden_f32,
+                   void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, int32_t phase_mask, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  return lmhead_bwd_impl(hidden, weight, ids, lse, dlogp, T, H, V, v_offset, inv_temp, shift, round_bf16, d_hidden, d_hidden_f32, d_weight,
+                         d_weight_dtype, accumulate_dw, vchunk, phase_mask, workspace, workspace_bytes, stream, nullptr);
+}
+
+int prl_lmhead_bwd_scatter(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T,
+                           int32_t H, int64_t V, int64_t v_offset, float inv_temp, int32_t shift, int32_t round_bf16,
+                           void* const* d_hidden_peers, int32_t n_peers, int64_t rows_per_peer, int32_t self_index, void* d_weight,
+                           int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, int32_t phase_mask, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  PRL_REQUIRE(d_hidden_peers && n_peers >= 1 && n_peers <= 8 && self_index >= 0 && self_index < n_peers, PRL_ERR_BAD_ARG,
+              "lmhead_bwd_scatter: 1..8 peers");
+  PRL_REQUIRE(rows_per_peer >= 32 && rows_per_peer % 32 == 0 && rows_per_peer < ((int64_t)1 << 31), PRL_ERR_UNSUPPORTED,
+              "lmhead_bwd_scatter: rows_per_peer must be a multiple of 32 (one epilogue slab never straddles two owners)");
+  PRL_REQUIRE(T == rows_per_peer * n_peers, PRL_ERR_BAD_ARG, "lmhead_bwd_scatter: T must be n_peers * rows_per_peer");
+  PRL_REQUIRE(epi_tma_enabled(), PRL_ERR_UNSUPPORTED, "lmhead_bwd_scatter needs the TMA-store epilogue (PRL_EPI_TMA=1)");
+  for (int j = 0; j < n_peers; ++j) PRL_REQUIRE(d_hidden_peers[j], PRL_ERR_BAD_ARG, "lmhead_bwd_scatter: null peer pointer");
+  PeerScatter ps = {d_hidden_peers, n_peers, rows_per_peer, self_index};
+  return lmhead_bwd_impl(hidden, weight, ids, lse, dlogp, T, H, V, v_offset, inv_temp, shift, round_bf16, nullptr, 1, d_weight, d_weight_dtype,
+                         accumulate_dw, vchunk, phase_mask, workspace, workspace_bytes, stream, &ps);
 }
 
 size_t prl_lmhead_bwd_saved_workspace_bytes(int64_t T, int32_t H, int64_t V) {

@@ -187,4 +187,30 @@ int prl_scatter_rows_bf16(const void* src, const int32_t* slot, int64_t T, int64
   return check_launch("scatter_rows_kernel");
 }
 
+// ---- peer memory for the fused reduce-scatter (include/prl_b200.h): open a CUDA IPC handle exported by another rank of the
+// same node under THIS rank's device, with peer access enabled lazily (no context on the exporting device is created here)
+int prl_ipc_open(const void* handle, void** dev_ptr_out) {
+  PRL_REQUIRE(handle && dev_ptr_out, PRL_ERR_BAD_ARG, "ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail_cuda(e, "cudaIpcOpenMemHandle");
+  }
+  *dev_ptr_out = p;
+  return PRL_OK;
+}
+
+int prl_ipc_close(void* dev_ptr) {
+  if (!dev_ptr) return PRL_OK;
+  cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail_cuda(e, "cudaIpcCloseMemHandle");
+  }
+  return PRL_OK;
+}
+
 }  // extern "C"

@@ -60,6 +60,29 @@ def _worker(rank, world, port, ret):
         np.testing.assert_allclose(logp, wl, atol=2e-5)
         np.testing.assert_allclose(ent, we, atol=2e-5)
         np.testing.assert_allclose(lse, wlse, atol=2e-5)
+
+        # ---- config 4 as rounds (VocabShardedLMHead): every rank brings ITS OWN T tokens; a rank sweeps all world*T tokens over its
+        # vocab shard, the partials go to the token owners (all-to-all, 16 B per token and shard), owners merge; (lse, dlogp) of
+        # all tokens are gathered for the backward with the dlogp of every row's position 0 forced to 0
+        T = 24
+        rng_r = [np.random.default_rng(100 + r) for r in range(world)]
+        z_rows = [rg.standard_normal((T, V)) * 3 for rg in rng_r]          # un-shifted logits of every rank's packed row
+        ids_rows = [rg.integers(0, V, T) for rg in rng_r]
+        z_all = np.concatenate([oracle.shift_rows(zr) for zr in z_rows])    # the shift is per packed row (rl/loss.py:54-57)
+        ids_all = np.concatenate(ids_rows)
+        part_all = oracle.shard_partials(z_all[:, v0:v1], ids_all, v0).astype(np.float32).reshape(world, T, 4)
+        mine = par.partials_to_owners(torch.from_numpy(part_all))
+        assert mine.shape == (world, T, 4)
+        logp, ent, lse = oracle.merge_partials(mine.numpy())
+        wl, we, wlse = oracle.logprobs_entropy(oracle.shift_rows(z_rows[rank]), ids_rows[rank], 1.0)
+        np.testing.assert_allclose(logp, wl, atol=2e-5)
+        np.testing.assert_allclose(ent, we, atol=2e-5)
+        assert abs(logp[0] + np.log(V)) < 1e-5  # position 0 of every row: uniform over the WHOLE vocabulary after the merge
+        g_local = torch.from_numpy(rng_r[rank].standard_normal(T).astype(np.float32))
+        lse_all, g_all = par.gather_token_scalars(torch.from_numpy(lse.astype(np.float32)), g_local)
+        assert lse_all.shape == (world * T,) and torch.equal(g_all[rank * T + 1 : (rank + 1) * T], g_local[1:])
+        assert all(float(g_all[r * T]) == 0.0 for r in range(world))
+        np.testing.assert_allclose(lse_all[rank * T : (rank + 1) * T].numpy(), lse, atol=1e-6)
         ret[rank] = "ok"
     except Exception as e:  # noqa: BLE001
         ret[rank] = f"{type(e).__name__}: {e}"
