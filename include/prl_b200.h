@@ -9,7 +9,8 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
  *     stated otherwise; the caller owns all memory (inputs, outputs, workspace);
- *     the library never allocates, frees or retains device memory.
+ *     the library never allocates, frees or retains device memory (one explicit
+ *     exception: prl_ipc_alloc / prl_ipc_free, buffers shared between ranks).
  *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and
  *     the call returns without synchronising.
  *   - return value: PRL_OK (0) or a negative PRL_ERR_* code; nothing is thrown
@@ -178,9 +179,13 @@ int prl_lmhead_bwd_scatter(const void* hidden, const void* weight, const int64_t
                            void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, int32_t phase_mask,
                            void* workspace, size_t workspace_bytes, void* stream);
 
-/* Peer memory for prl_lmhead_bwd_scatter: map a buffer another rank of the same node exported with cudaIpcGetMemHandle
- * (64-byte handle) into this process under the CURRENT device, enabling peer access lazily; *dev_ptr_out is the base of the
- * exporter's allocation.  HOST pointers in, device pointer out.  prl_ipc_close unmaps it. */
+/* Peer memory for prl_lmhead_bwd_scatter (the ONLY entry points that own device memory: an accumulator that other processes
+ * map has to be a whole allocation of its own).  prl_ipc_alloc: cudaMalloc `bytes` on the current device and export it
+ * (handle_out: 64 bytes, a cudaIpcMemHandle_t to hand to the other ranks of the node); prl_ipc_free releases it.
+ * prl_ipc_open: map a buffer another rank exported into this process under the CURRENT device, enabling peer access lazily
+ * (*dev_ptr_out = the exporter's allocation); prl_ipc_close unmaps it.  HOST pointers in, device pointers out. */
+int prl_ipc_alloc(size_t bytes, void** dev_ptr_out, void* handle_out);
+int prl_ipc_free(void* dev_ptr);
 int prl_ipc_open(const void* handle, void** dev_ptr_out);
 int prl_ipc_close(void* dev_ptr);
 
@@ -287,6 +292,14 @@ int prl_pack_rollouts(const int64_t* tokens, const uint8_t* mask, const float* c
  * ---------------------------------------------------------------------------------------- */
 int prl_gemm_bf16_f32(const void* A, const void* B, float* C, int64_t M, int64_t N, int64_t K, int32_t a_mn_major,
                       int32_t b_mn_major, int32_t accumulate, void* stream);
+
+/* Tuning knobs.  Every knob has a compiled-in default; the environment variable of the same name is
+ * read once, when the library first needs a knob; prl_set_knob changes it afterwards (process-wide; meant for tests and tuning
+ * scripts, not for production use).  Names: PRL_VCHUNK, PRL_FWD_STAGES, PRL_DZ_STAGES, PRL_GROUP_M, PRL_SWEEP_GROUP_M,
+ * PRL_TILE_STAGES, PRL_K_SPLITS, PRL_L2_PROMO, PRL_EPI_TMA, PRL_HINT_<FWD|FWDS|DZ|DH|DW|GEMM>_<A|B|C>, and -- before the
+ * first compute call only -- PRL_CTA_GROUP, PRL_MSUB.  Profiling aids (PRL_DEBUG_*) exist only in -DPRL_DEBUG_KNOBS builds. */
+int prl_set_knob(const char* name, int64_t value);
+int prl_get_knob(const char* name, int64_t* value);
 
 /* Test hook (host only, no GPU): the work decomposition the GEMM engine would use for an M x N x K problem.
  * kind 0 = forward sweep, 1 = dlogits sweep, 2 / 3 = store tiles of the recompute / saved-logits backward (incl. the

@@ -62,6 +62,8 @@ _SIGNATURES = {
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_int64, c_float, c_int32, c_int32,
          c_void_p, c_int32, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int64, c_int32, c_void_p, c_size_t, c_void_p],
     ),
+    "prl_ipc_alloc": (c_int32, [c_size_t, c_void_p, c_void_p]),
+    "prl_ipc_free": (c_int32, [c_void_p]),
     "prl_ipc_open": (c_int32, [c_void_p, c_void_p]),
     "prl_ipc_close": (c_int32, [c_void_p]),
     "prl_lmhead_saved_logits_ld": (c_int64, [c_int64]),
@@ -82,6 +84,8 @@ _SIGNATURES = {
     "prl_scatter_tokens_f32": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_float,
                                          c_void_p, c_void_p, c_float, c_void_p]),
     "prl_scatter_rows_bf16": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "prl_set_knob": (c_int32, [ctypes.c_char_p, c_int64]),
+    "prl_get_knob": (c_int32, [ctypes.c_char_p, c_void_p]),
     "prl_debug_schedule": (c_int32, [c_int32, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "prl_gemm_bf16_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
 }
@@ -133,6 +137,18 @@ def require_cuda(*tensors: torch.Tensor) -> None:
     for t in tensors:
         if t is not None and not t.is_cuda:
             raise RuntimeError("prime_rl_cse_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+
+
+def set_knob(name: str, value: int) -> None:
+    """Tuning knob of the library (include/prl_b200.h "Tuning knobs"); the environment variable of the same name is only the
+    initial value, read once."""
+    check(load().prl_set_knob(name.encode(), int(value)), f"prl_set_knob({name})")
+
+
+def get_knob(name: str) -> int:
+    v = c_int64()
+    check(load().prl_get_knob(name.encode(), ctypes.byref(v)), f"prl_get_knob({name})")
+    return int(v.value)
 
 
 def launch_count(reset: bool = False) -> int:

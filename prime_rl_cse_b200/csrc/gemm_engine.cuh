@@ -41,9 +41,17 @@ constexpr int ST_STORE_F32 = 2;   // write fp32 to c_f32
 constexpr int ST_STORE_BF16 = 4;  // write bf16 to c_bf16
 constexpr int ST_LOAD_BF16 = 8;   // C += existing bf16 at c_bf16
 constexpr int ST_TMA = 16;         // epilogue writes through smem staging + TMA store / reduce-add (tma_c)
+// Profiling aids, compiled in only with -DPRL_DEBUG_KNOBS (they give WRONG results by design); in the release build the flags are
+// 0 and every branch on them folds away.
+#ifdef PRL_DEBUG_KNOBS
 constexpr int ST_WAIT_BACKOFF = 1 << 18;  // epilogue warps sleep between mbarrier probes (PRL_WAIT_BACKOFF=1)
-constexpr int ST_DEBUG_SKIPB = 1 << 17;
-constexpr int ST_DEBUG_SKIP = 1 << 16;  // profiling aid (PRL_DEBUG_NOSTORE=1): run the GEMM but skip the epilogue's global memory traffic
+constexpr int ST_DEBUG_SKIPB = 1 << 17;   // skip the B load on odd k-blocks (PRL_DEBUG_SKIPB=1): cost of the L2->SM operand traffic
+constexpr int ST_DEBUG_SKIP = 1 << 16;    // run the GEMM but skip the epilogue's global memory traffic (PRL_DEBUG_NOSTORE=1)
+#else
+constexpr int ST_WAIT_BACKOFF = 0;
+constexpr int ST_DEBUG_SKIPB = 0;
+constexpr int ST_DEBUG_SKIP = 0;
+#endif
 
 struct EpiParams {
   int64_t m_rows;  // valid rows of C

@@ -6,18 +6,77 @@
 
 namespace prl {
 
-// diagnostic knobs (PRL_*) are read from the environment at every call
-static long env_long(const char* name, long dflt) {
-  const char* s = getenv(name);
-  return s ? strtol(s, nullptr, 0) : dflt;
+// ------------------------------------------------------------------------------------------------
+// Tuning knobs.  Every knob has a compiled-in default (the measured winner); the environment variable
+// of the same name is read ONCE, the first time the library needs a knob; prl_set_knob() changes a value afterwards
+// (tests and the tuning scripts under tools/).  PRL_CTA_GROUP, PRL_MSUB and PRL_MAX_WORKERS select kernel variants whose
+// launch attributes are cached on first use: set them before the first call.  Knobs marked `debug` exist only in builds with
+// -DPRL_DEBUG_KNOBS (make debug): the profiling aids behind them (which produce WRONG results) are not compiled into the
+// release kernels.
+// ------------------------------------------------------------------------------------------------
+enum KnobId {
+  K_CTA_GROUP, K_MSUB, K_EPI_TMA, K_L2_PROMO, K_K_SPLITS, K_GROUP_M, K_TILE_STAGES, K_SWEEP_GROUP_M, K_FWD_STAGES, K_DZ_STAGES, K_VCHUNK,
+  K_HINT0,  // 18 hints: family (FWD, FWDS, DZ, DH, DW, GEMM) x operand (A, B, C); -1 = the family's compiled-in default
+  K_HINT_END = K_HINT0 + 18,
+#ifdef PRL_DEBUG_KNOBS
+  K_SPLIT_GROUP = K_HINT_END, K_MAX_WORKERS, K_WAIT_BACKOFF, K_DEBUG_NOSTORE, K_DEBUG_SKIPB, K_DEBUG_MN_LBO, K_DEBUG_MN_SBO, K_DEBUG_MN_KSTEP,
+  K_COUNT
+#else
+  K_COUNT = K_HINT_END
+#endif
+};
+static const char* const kHintFamilies[6] = {"FWD", "FWDS", "DZ", "DH", "DW", "GEMM"};
+
+struct KnobTable {
+  char names[K_COUNT][32];
+  long values[K_COUNT];
+  KnobTable() {
+    auto def = [&](int id, const char* name, long dflt) {
+      snprintf(names[id], sizeof(names[id]), "%s", name);
+      const char* e = getenv(name);
+      values[id] = e ? strtol(e, nullptr, 0) : dflt;
+    };
+    def(K_CTA_GROUP, "PRL_CTA_GROUP", 2);
+    def(K_MSUB, "PRL_MSUB", 0);
+    def(K_EPI_TMA, "PRL_EPI_TMA", 1);
+    def(K_L2_PROMO, "PRL_L2_PROMO", 256);
+    def(K_K_SPLITS, "PRL_K_SPLITS", 0);
+    def(K_GROUP_M, "PRL_GROUP_M", 0);
+    def(K_TILE_STAGES, "PRL_TILE_STAGES", 0);
+    def(K_SWEEP_GROUP_M, "PRL_SWEEP_GROUP_M", 32);
+    def(K_FWD_STAGES, "PRL_FWD_STAGES", 5);
+    def(K_DZ_STAGES, "PRL_DZ_STAGES", 5);
+    def(K_VCHUNK, "PRL_VCHUNK", 16384);
+    for (int f = 0; f < 6; ++f)
+      for (int o = 0; o < 3; ++o) {
+        char name[32];
+        snprintf(name, sizeof(name), "PRL_HINT_%s_%c", kHintFamilies[f], "ABC"[o]);
+        def(K_HINT0 + 3 * f + o, name, -1);
+      }
+#ifdef PRL_DEBUG_KNOBS
+    def(K_SPLIT_GROUP, "PRL_SPLIT_GROUP", 0);
+    def(K_MAX_WORKERS, "PRL_MAX_WORKERS", 0);
+    def(K_WAIT_BACKOFF, "PRL_WAIT_BACKOFF", 0);
+    def(K_DEBUG_NOSTORE, "PRL_DEBUG_NOSTORE", 0);
+    def(K_DEBUG_SKIPB, "PRL_DEBUG_SKIPB", 0);
+    def(K_DEBUG_MN_LBO, "PRL_DEBUG_MN_LBO", BLOCK_K * 128);
+    def(K_DEBUG_MN_SBO, "PRL_DEBUG_MN_SBO", 1024);
+    def(K_DEBUG_MN_KSTEP, "PRL_DEBUG_MN_KSTEP", UMMA_K * 128);
+#endif
+  }
+};
+static KnobTable& knobs() {
+  static KnobTable t;  // C++11: initialised once, thread-safe
+  return t;
 }
+static long knob(int id) { return knobs().values[id]; }
 
 // CTAs per cluster: 1 = one CTA per 128x256 tile; 2 = a CTA pair (cta_group::2) per 256x256 tile; 4 = two pairs per
 // 512x256 tile sharing B by TMA multicast
 static int cta_group() {
   static int cg = 0;
   if (cg == 0) {
-    const long v = env_long("PRL_CTA_GROUP", 2);
+    const long v = knob(K_CTA_GROUP);
     cg = (v == 1) ? 1 : (v == 4 ? 4 : 2);
   }
   return cg;
@@ -43,7 +102,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // L2 promotion of TMA requests (PRL_L2_PROMO = 0 none | 64 | 128 | 256; default 256)
 static CUtensorMapL2promotion l2_promotion() {
-  const long v = env_long("PRL_L2_PROMO", 256);
+  const long v = knob(K_L2_PROMO);
   return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                 : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
 }
@@ -70,7 +129,7 @@ static int make_tmap_t(CUtensorMap* map, const void* base, int64_t inner, int64_
 static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer) {
   return make_tmap_t(map, base, inner, outer, ld, box_inner, box_outer, false);
 }
-static bool epi_tma_enabled() { return env_long("PRL_EPI_TMA", 1) != 0; }
+static bool epi_tma_enabled() { return knob(K_EPI_TMA) != 0; }
 // output map of the TMA-store epilogues: [rows, cols] row-major with pitch ld; fp32 boxes 32 x 32, bf16 boxes 64 x 32 (128 B rows)
 static int make_output_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, bool f32) {
   return make_tmap_t(map, base, cols, rows, ld, f32 ? 32 : 64, 32, f32);
@@ -87,9 +146,11 @@ static void make_desc_defaults(GemmParams& p, bool a_mn, bool b_mn) {
   // K-major SW128: 8-row groups 1024 B apart (SBO), LBO unused (16 B); one UMMA_K step = +32 B.
   // MN-major SW128: 64-element MN slabs BLOCK_K*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
   //                 one UMMA_K step (16 k rows) = +2048 B.
-  const uint32_t mn_lbo = (uint32_t)env_long("PRL_DEBUG_MN_LBO", BLOCK_K * 128);
-  const uint32_t mn_sbo = (uint32_t)env_long("PRL_DEBUG_MN_SBO", 1024);
-  const uint32_t mn_kstep = (uint32_t)env_long("PRL_DEBUG_MN_KSTEP", UMMA_K * 128);
+#ifdef PRL_DEBUG_KNOBS
+  const uint32_t mn_lbo = (uint32_t)knob(K_DEBUG_MN_LBO), mn_sbo = (uint32_t)knob(K_DEBUG_MN_SBO), mn_kstep = (uint32_t)knob(K_DEBUG_MN_KSTEP);
+#else
+  constexpr uint32_t mn_lbo = BLOCK_K * 128, mn_sbo = 1024, mn_kstep = UMMA_K * 128;
+#endif
   p.a_desc_hi = a_mn ? ptx::make_smem_desc_hi_sw128(mn_lbo, mn_sbo) : ptx::make_smem_desc_hi_sw128(16, 1024);
   p.b_desc_hi = b_mn ? ptx::make_smem_desc_hi_sw128(mn_lbo, mn_sbo) : ptx::make_smem_desc_hi_sw128(16, 1024);
   p.a_kstep = a_mn ? mn_kstep : UMMA_K * 2;
@@ -103,7 +164,7 @@ static void make_desc_defaults(GemmParams& p, bool a_mn, bool b_mn) {
 // PRL_MSUB=1|2 forces one value everywhere.
 static int msub(int epi) {
   static int forced = -1;
-  if (forced < 0) forced = (int)env_long("PRL_MSUB", 0);
+  if (forced < 0) forced = (int)knob(K_MSUB);
   if (cta_group() != 2) return 1;
   if (forced == 1 || forced == 2) return forced;
   return epi == EPI_STORE ? 2 : 1;
@@ -142,25 +203,26 @@ static int resident_workers() {
       if (cudaOccupancyMaxActiveClusters(&q, kern, &cfg) == cudaSuccess && q > 0 && q < n) n = q;
       cudaGetLastError();
     }
-    const long cap = env_long("PRL_MAX_WORKERS", 0);  // diagnostic: use only the first `cap` clusters
+#ifdef PRL_DEBUG_KNOBS
+    const long cap = knob(K_MAX_WORKERS);  // diagnostic: use only the first `cap` clusters
     if (cap > 0 && cap < n) n = (int)cap;
+#endif
     cached = n > 0 ? n : 1;
   }
   return cached;
 }
 static int workers() { return cta_group() == 4 ? resident_workers<4>() : (cta_group() == 2 ? resident_workers<2>() : resident_workers<1>()); }
 
-// L2 eviction priorities per kernel family; each can be overridden for experiments with PRL_HINT_<FAMILY>_<A|B|C> =
-// 0 (no hint) | 1 (evict first) | 2 (evict last) | 3 (explicit evict-normal)
+// L2 eviction priorities per kernel family (a, b, c = the compiled-in defaults); each can be overridden for experiments with the
+// knob PRL_HINT_<FAMILY>_<A|B|C> = 0 (no hint) | 1 (evict first) | 2 (evict last) | 3 (explicit evict-normal)
 static uint64_t hint_value(long v) { return v == 1 ? ptx::kEvictFirst : (v == 2 ? ptx::kEvictLast : (v == 3 ? ptx::kEvictNormal : 0)); }
 static void set_hints(GemmParams& p, const char* family, int a, int b, int c) {
-  char name[64];
-  snprintf(name, sizeof(name), "PRL_HINT_%s_A", family);
-  p.hint_a = hint_value(env_long(name, a));
-  snprintf(name, sizeof(name), "PRL_HINT_%s_B", family);
-  p.hint_b = hint_value(env_long(name, b));
-  snprintf(name, sizeof(name), "PRL_HINT_%s_C", family);
-  p.hint_c = hint_value(env_long(name, c));
+  int f = 0;
+  while (f < 5 && strcmp(kHintFamilies[f], family) != 0) ++f;
+  const long ka = knob(K_HINT0 + 3 * f), kb = knob(K_HINT0 + 3 * f + 1), kc = knob(K_HINT0 + 3 * f + 2);
+  p.hint_a = hint_value(ka >= 0 ? ka : a);
+  p.hint_b = hint_value(kb >= 0 ? kb : b);
+  p.hint_c = hint_value(kc >= 0 ? kc : c);
 }
 
 template <int CG, int MS, bool A_MN, bool B_MN, int EPI>
@@ -176,9 +238,11 @@ static int launch_gemm_cg(GemmParams p /* by value: the profiling knobs below ed
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   if (p.num_items < 1) return PRL_OK;
-  if (env_long("PRL_DEBUG_NOSTORE", 0)) p.epi.flags |= ST_DEBUG_SKIP;
-  if (env_long("PRL_DEBUG_SKIPB", 0)) p.epi.flags |= ST_DEBUG_SKIPB;
-  if (env_long("PRL_WAIT_BACKOFF", 0)) p.epi.flags |= ST_WAIT_BACKOFF;
+#ifdef PRL_DEBUG_KNOBS
+  if (knob(K_DEBUG_NOSTORE)) p.epi.flags |= ST_DEBUG_SKIP;
+  if (knob(K_DEBUG_SKIPB)) p.epi.flags |= ST_DEBUG_SKIPB;
+  if (knob(K_WAIT_BACKOFF)) p.epi.flags |= ST_WAIT_BACKOFF;
+#endif
   int nw = resident_workers<CG>();
   if (nw > p.num_items) nw = p.num_items;
   cudaLaunchConfig_t cfg;
@@ -209,7 +273,7 @@ static void set_tiling(GemmParams& p, int64_t M, int64_t N, int64_t K, int epi) 
 // Two k-splits per output tile when that fills the machine markedly better (few output tiles, long K: d_hidden at small T x H).
 // Only 1 or 2: with two partial sums the fp32 reduce-add into a zeroed accumulator gives the same bits in either arrival order.
 static int pick_k_splits(int64_t M, int64_t N, int64_t K) {
-  const long forced = env_long("PRL_K_SPLITS", 0);
+  const long forced = knob(K_K_SPLITS);
   if (forced == 1 || forced == 2) return (int)forced;
   const int64_t bm = (int64_t)BLOCK_M * cta_group() * msub(EPI_STORE);
   const int64_t items = ((M + bm - 1) / bm) * ((N + BLOCK_N - 1) / BLOCK_N), w = workers();
@@ -230,9 +294,9 @@ static void set_k_splits(GemmParams& p, int ks) {
 static void schedule_tiles(GemmParams& p, int band = 8) {
   p.tiles_per_split = 1;
   p.n_splits = p.n_tiles;
-  p.group_m = (int)env_long("PRL_GROUP_M", band) / (cta_group() * msub(EPI_STORE));
+  p.group_m = (int)(knob(K_GROUP_M) > 0 ? knob(K_GROUP_M) : band) / (cta_group() * msub(EPI_STORE));
   if (p.group_m < 1) p.group_m = 1;
-  p.max_stages = (int)env_long("PRL_TILE_STAGES", 0);
+  p.max_stages = (int)knob(K_TILE_STAGES);
   p.num_items = p.m_tiles * p.n_splits * (p.k_splits > 1 ? p.k_splits : 1);
 }
 
@@ -254,9 +318,11 @@ static void schedule_sweeps(GemmParams& p, int max_splits, int epi) {
   }
   p.tiles_per_split = (p.n_tiles + best_ns - 1) / best_ns;
   p.n_splits = (p.n_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.group_m = (int)env_long("PRL_SWEEP_GROUP_M", 32) / (cta_group() * msub(epi));
+  p.group_m = (int)knob(K_SWEEP_GROUP_M) / (cta_group() * msub(epi));
   if (p.group_m < 1) p.group_m = 1;
-  p.split_group = (int)env_long("PRL_SPLIT_GROUP", 0);
+#ifdef PRL_DEBUG_KNOBS
+  p.split_group = (int)knob(K_SPLIT_GROUP);
+#endif
   p.num_items = p.m_tiles * p.n_splits;
 }
 
@@ -425,7 +491,7 @@ static int lmhead_fwd_impl(const void* hidden, const void* weight, const int64_t
     // Prefetch depth: 5 of the 7 stages that fit.  Measured (ncu, one forward at the Qwen3-8B shape): 7 stages 18-23 GB of DRAM
     // reads, 5 stages 11.6 GB, 4 stages 6.7 GB (3 stages starve the MMAs); sustained under the power cap 5 stages is fastest
     // (+4..6 % over 7).  The hidden band is marked evict-last.
-    p.max_stages = (int)env_long("PRL_FWD_STAGES", 5);
+    p.max_stages = (int)knob(K_FWD_STAGES);
     if (saved) {
       p.epi.dz = reinterpret_cast<__nv_bfloat16*>(saved);
       p.epi.ldz = saved_ld;
@@ -617,7 +683,7 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
 extern "C" {
 
 static int64_t pick_vchunk(int64_t V, int64_t vchunk) {
-  if (vchunk <= 0) vchunk = env_long("PRL_VCHUNK", 16384);
+  if (vchunk <= 0) vchunk = knob(K_VCHUNK);
   vchunk = round_up(vchunk, BLOCK_N);
   const int64_t vpad = round_up(V, BLOCK_N);
   return vchunk < vpad ? vchunk : vpad;
@@ -683,7 +749,7 @@ static int lmhead_bwd_impl(const void* hidden, const void* weight, const int64_t
         p.epi.flags = ST_TMA;
       }
       set_hints(p, "DZ", 2, 1, 1);  // hidden band reused across the sweep, W tiles and the dlogits block stream through
-      p.max_stages = (int)env_long("PRL_DZ_STAGES", 5);  // 5 of 6 stages: +1 % over 6, 4 is 6 % slower
+      p.max_stages = (int)knob(K_DZ_STAGES);  // 5 of 6 stages: +1 % over 6, 4 is 6 % slower
       rc = launch_gemm<false, false, EPI_DZ>(p, st, "lmhead_bwd_dz_kernel");
       if (rc) return rc;
     }
@@ -756,6 +822,28 @@ int prl_lmhead_bwd_saved(const void* hidden, const void* weight, const int64_t* 
     dh_acc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
   return lmhead_bwd_gemms(hidden, reinterpret_cast<const __nv_bfloat16*>(weight), dz, saved_ld, 0, V, T, H, d_hidden, d_hidden_f32, d_weight,
                           d_weight_dtype, accumulate_dw, phase_mask, true, true, 1, dh_acc, 4, st);
+}
+
+int prl_set_knob(const char* name, int64_t value) {
+  PRL_REQUIRE(name, PRL_ERR_BAD_ARG, "set_knob: null name");
+  KnobTable& t = knobs();
+  for (int i = 0; i < K_COUNT; ++i)
+    if (strcmp(t.names[i], name) == 0) {
+      t.values[i] = (long)value;
+      return PRL_OK;
+    }
+  return fail(PRL_ERR_BAD_ARG, "set_knob: unknown knob %s (debug knobs need a -DPRL_DEBUG_KNOBS build)", name);
+}
+
+int prl_get_knob(const char* name, int64_t* value) {
+  PRL_REQUIRE(name && value, PRL_ERR_BAD_ARG, "get_knob: null pointer");
+  KnobTable& t = knobs();
+  for (int i = 0; i < K_COUNT; ++i)
+    if (strcmp(t.names[i], name) == 0) {
+      *value = t.values[i];
+      return PRL_OK;
+    }
+  return fail(PRL_ERR_BAD_ARG, "get_knob: unknown knob %s", name);
 }
 
 int prl_debug_schedule(int32_t kind, int64_t M, int64_t N, int64_t K, int32_t* items, int64_t capacity, int32_t* dims) {

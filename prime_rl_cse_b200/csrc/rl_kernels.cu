@@ -26,6 +26,13 @@ int sm_count() {
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// torch.clamp(max=) / torch.maximum / torch.min / torch.max PROPAGATE NaN, fminf / fmaxf drop it: these keep the reference's
+// behaviour (a NaN log-prob must surface as a NaN loss, not as a silently clipped ratio)
+__device__ __forceinline__ float clamp_max_nan(float x, float hi) { return (x != x) ? x : fminf(x, hi); }
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a) ? a : ((b != b) ? b : fmaxf(a, b)); }
+__device__ __forceinline__ double min_nan(double a, double b) { return (a != a) ? a : ((b != b) ? b : fmin(a, b)); }
+__device__ __forceinline__ double max_nan(double a, double b) { return (a != a) ? a : ((b != b) ? b : fmax(a, b)); }
+
 // ------------------------------------------------------------------------------------------------
 // advantages: one warp per group.  src/prime_rl/orchestrator/advantage.py:18,32,41-43,55-57.
 // fp32 sum order ("L8"): lane accumulators acc[j] = x[j] + x[j+8] + ... (j < 8, left to right), then
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(256) advantages_small_group_kernel(const float
     for (int u = 0; u < ADV_U; ++u) {
       if (active[u]) {
         float a = __fsub_rn(r[u], __fdiv_rn(num[u], den[u]));
-        if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = fmaxf(a, 0.f);
+        if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = max_nan(a, 0.f);
         if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
         out[idx[u]] = a;
       }
@@ -188,7 +195,7 @@ __global__ void __launch_bounds__(256) advantages_kernel(const float* __restrict
     }
     for (int i = lane; i < G; i += 32) {
       float a = __fsub_rn(r[i], base);
-      if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = fmaxf(a, 0.f);
+      if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = max_nan(a, 0.f);
       if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
       out[g * G + i] = a;
     }
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(256) advantages_kernel(const float* __restrict
       for (int i = 0; i < G; ++i) {
         const int64_t idx = g * G + i;
         float a = __fsub_rn(r[i], base);
-        if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = fmaxf(a, 0.f);
+        if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = max_nan(a, 0.f);
         if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
         const int64_t t0 = tok_offsets[idx], t1 = tok_offsets[idx + 1];
         for (int64_t t = t0 + lane; t < t1; t += 32) token_out[t] = a;
@@ -299,9 +306,10 @@ __global__ void __launch_bounds__(256) loss_token_kernel(const float* __restrict
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         r[k] = expf(l[k] - o[k]);
-        c[k] = fminf(r[k], clip);
+        c[k] = clamp_max_nan(r[k], clip);
         f[k] = (r[k] > clip) ? 1.f : 0.f;
         g[k] = (m[k] && r[k] <= clip) ? (-a[k] * r[k]) * inv_scale : 0.f;
+        if (r[k] != r[k]) g[k] = r[k];  // autograd: 0 * exp'(nan) = nan, masked or not
         if (m[k]) acc += (double)(-c[k] * a[k]);
       }
       reinterpret_cast<float4*>(ratio)[q] = make_float4(r[0], r[1], r[2], r[3]);
@@ -313,12 +321,12 @@ __global__ void __launch_bounds__(256) loss_token_kernel(const float* __restrict
   }
   for (int64_t t = done + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += stride) {
     const float r = expf(logp[t] - old[t]);
-    const float c = fminf(r, clip);
+    const float c = clamp_max_nan(r, clip);
     const bool m = mask[t] != 0;
     ratio[t] = r;
     clipped[t] = c;
     is_clipped[t] = (r > clip) ? 1.f : 0.f;
-    dlogp[t] = (m && r <= clip) ? (-adv[t] * r) * inv_scale : 0.f;
+    dlogp[t] = (r != r) ? r : ((m && r <= clip) ? (-adv[t] * r) * inv_scale : 0.f);
     if (m) acc += (double)(-c * adv[t]);
   }
   const double tot = block_sum(acc, sh);
@@ -351,9 +359,9 @@ __global__ void __launch_bounds__(512) loss_seq_kernel(const float* __restrict__
     float L = (float)Sd;
     if (length_norm) L = L / n;
     const float pre = L;
-    L = fminf(L, 10.f);
+    L = clamp_max_nan(L, 10.f);
     const float r = expf(L);
-    const float c = fminf(r, clip);
+    const float c = clamp_max_nan(r, clip);
     ratio[seg] = r;
     clipped[seg] = c;
     is_clipped[seg] = (r > clip) ? 1.f : 0.f;
@@ -361,6 +369,7 @@ __global__ void __launch_bounds__(512) loss_seq_kernel(const float* __restrict__
     partial[seg] = (double)(-c * mean_a);
     float coef = -mean_a * r;
     if (!(r <= clip) || !(pre <= 10.f)) coef = 0.f;
+    if (r != r) coef = r;  // a NaN log-prob in the segment: NaN gradient for its unmasked tokens, as autograd gives
     if (length_norm) coef = coef / n;
     coef_sh = coef * inv_scale;
   }
@@ -401,6 +410,12 @@ __device__ __forceinline__ Stat stat_merge(Stat a, Stat b) {
   return r;
 }
 __device__ __forceinline__ void stat_push(Stat& st, float z) {
+  if (z == -INFINITY) {
+    // exp(-inf) = 0: nothing for the log-sum-exp (torch.logsumexp handles -inf logits), but the reference's entropy has the
+    // term softmax * z = 0 * -inf = nan (rl/loss.py:45-46)
+    st.u += __int_as_float(0x7fc00000);
+    return;
+  }
   if (z > st.m) {
     const float e = __expf(st.m - z);
     st.s = st.s * e + 1.f;
@@ -521,8 +536,8 @@ __global__ void __launch_bounds__(256) masked_moments_kernel(const float* __rest
       cnt += 1.0;
       sum += d;
       sq += d * d;
-      mn = fmin(mn, d);
-      mx = fmax(mx, d);
+      mn = min_nan(mn, d);
+      mx = max_nan(mx, d);
     }
   }
 #pragma unroll
@@ -530,8 +545,8 @@ __global__ void __launch_bounds__(256) masked_moments_kernel(const float* __rest
     cnt += __shfl_down_sync(FULL, cnt, o);
     sum += __shfl_down_sync(FULL, sum, o);
     sq += __shfl_down_sync(FULL, sq, o);
-    mn = fmin(mn, __shfl_down_sync(FULL, mn, o));
-    mx = fmax(mx, __shfl_down_sync(FULL, mx, o));
+    mn = min_nan(mn, __shfl_down_sync(FULL, mn, o));
+    mx = max_nan(mx, __shfl_down_sync(FULL, mx, o));
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) {
@@ -541,7 +556,7 @@ __global__ void __launch_bounds__(256) masked_moments_kernel(const float* __rest
   if (threadIdx.x == 0) {
     for (int w = 1; w < 8; ++w) {
       cnt += sh[0][w], sum += sh[1][w], sq += sh[2][w];
-      mn = fmin(mn, sh[3][w]), mx = fmax(mx, sh[4][w]);
+      mn = min_nan(mn, sh[3][w]), mx = max_nan(mx, sh[4][w]);
     }
     double* o = partial + (int64_t)blockIdx.x * 5;
     o[0] = cnt, o[1] = sum, o[2] = sq, o[3] = mn, o[4] = mx;
@@ -639,7 +654,7 @@ __global__ void masked_moments_finalize_kernel(const double* __restrict__ partia
     for (int b = 0; b < nblocks; ++b) {
       const double* p = partial + (int64_t)b * 5;
       cnt += p[0], sum += p[1], sq += p[2];
-      mn = fmin(mn, p[3]), mx = fmax(mx, p[4]);
+      mn = min_nan(mn, p[3]), mx = max_nan(mx, p[4]);
     }
     acc[0] = cnt, acc[1] = sum, acc[2] = sq, acc[3] = mn, acc[4] = mx;
   }

@@ -189,6 +189,36 @@ int prl_scatter_rows_bf16(const void* src, const int32_t* slot, int64_t T, int64
 
 // ---- peer memory for the fused reduce-scatter (include/prl_b200.h): open a CUDA IPC handle exported by another rank of the
 // same node under THIS rank's device, with peer access enabled lazily (no context on the exporting device is created here)
+int prl_ipc_alloc(size_t bytes, void** dev_ptr_out, void* handle_out) {
+  PRL_REQUIRE(bytes > 0 && dev_ptr_out && handle_out, PRL_ERR_BAD_ARG, "ipc_alloc: bad arguments");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail_cuda(e, "cudaMalloc (ipc_alloc)");
+  }
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(p);
+    return fail_cuda(e, "cudaIpcGetMemHandle");
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *dev_ptr_out = p;
+  return PRL_OK;
+}
+
+int prl_ipc_free(void* dev_ptr) {
+  if (!dev_ptr) return PRL_OK;
+  cudaError_t e = cudaFree(dev_ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail_cuda(e, "cudaFree (ipc_free)");
+  }
+  return PRL_OK;
+}
+
 int prl_ipc_open(const void* handle, void** dev_ptr_out) {
   PRL_REQUIRE(handle && dev_ptr_out, PRL_ERR_BAD_ARG, "ipc_open: null pointer");
   cudaIpcMemHandle_t h;

@@ -19,6 +19,8 @@ def recompute_logprobs(hidden: torch.Tensor, weight: torch.Tensor, input_ids: to
     temperature, input_ids)` and, if `old_logprobs` is given, `recomputed_logprob_error = exp(recomputed - old)`.
     hidden [..., T, H] bf16, weight [V, H] bf16, input_ids [..., T].  Returns (logprobs[..., T], error | None)."""
     _lib.require_cuda(hidden, weight, input_ids, old_logprobs)
+    if hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise ValueError("recompute_logprobs needs bf16 hidden and weight (an fp32 logprob model must be cast explicitly)")
     lead = input_ids.shape
     h2 = hidden.reshape(-1, hidden.shape[-1]).contiguous()
     i2 = input_ids.reshape(-1).contiguous().to(torch.int64)

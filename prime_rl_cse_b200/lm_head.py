@@ -24,9 +24,29 @@ def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+def _check_operands(hidden, weight, ids, what: str, **per_token) -> None:
+    """The kernels read raw pointers through TMA descriptors: anything but contiguous bf16 [T, H] / [V, H] operands and
+    contiguous int64 ids [T] would be silently reinterpreted, so every wrapper that reaches prl_lmhead_* checks them here."""
+    _lib.require_cuda(hidden, weight, ids, *per_token.values())
+    if hidden.dim() != 2 or weight.dim() != 2 or hidden.shape[1] != weight.shape[1]:
+        raise ValueError(f"{what}: hidden must be [T, H] and weight [V, H] (got {tuple(hidden.shape)} and {tuple(weight.shape)})")
+    for name, t in (("hidden", hidden), ("weight", weight)):
+        if t.dtype != torch.bfloat16:
+            raise ValueError(f"{what}: {name} must be bf16 (got {t.dtype}); cast it explicitly (FSDP param_dtype=bf16, model.py:103)")
+        if not t.is_contiguous() or t.data_ptr() % 16 != 0:
+            raise ValueError(f"{what}: {name} must be contiguous and 16-byte aligned")
+    T = hidden.shape[0]
+    if ids.dtype != torch.int64 or ids.dim() != 1 or ids.shape[0] != T or not ids.is_contiguous():
+        raise ValueError(f"{what}: ids must be a contiguous int64 [T] tensor (T = {T})")
+    for name, t in per_token.items():
+        if t is not None and (t.dtype != torch.float32 or t.numel() != T or not t.is_contiguous()):
+            raise ValueError(f"{what}: {name} must be a contiguous fp32 tensor with T = {T} elements")
+
+
 def lm_head_forward_raw(hidden, weight, ids, inv_temp, shift=True, round_bf16=True, v_offset=0, v_total=None,
                         want_partials=False, workspace=None):
     """hidden [T,H] bf16, weight [V,H] bf16, ids [T] int64 -> (logp, entropy, lse, partials|None)."""
+    _check_operands(hidden, weight, ids, "lm_head_forward_raw")
     lib = _lib.load()
     T, H = hidden.shape
     V = weight.shape[0]
@@ -88,6 +108,7 @@ def lm_head_forward_save_raw(hidden, weight, ids, inv_temp, shift=True, v_offset
                              workspace=None, saved=None):
     """`lm_head_forward_raw` (bf16-rounded logits) that also keeps the logits: returns (logp, entropy, lse,
     partials|None, saved [T, ld] bf16).  `saved` may be a preallocated [T, ld] bf16 block, ld = saved_logits_ld(V)."""
+    _check_operands(hidden, weight, ids, "lm_head_forward_save_raw")
     lib = _lib.load()
     T, H = hidden.shape
     V = weight.shape[0]
@@ -131,6 +152,7 @@ def lm_head_backward_saved_raw(hidden, weight, ids, lse, dlogp, inv_temp, saved,
                                workspace=None):
     """Backward from the logits kept by `lm_head_forward_save_raw`.  `saved` is overwritten (it holds the bf16 dlogits
     afterwards).  Returns (d_hidden, d_weight) like `lm_head_backward_raw`."""
+    _check_operands(hidden, weight, ids, "lm_head_backward_saved_raw", lse=lse, dlogp=dlogp)
     lib = _lib.load()
     T, H = hidden.shape
     V = weight.shape[0]
@@ -158,6 +180,7 @@ def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, 
                          dhidden_f32=False, phase_mask=0, workspace=None):
     """Returns (d_hidden [T,H] bf16|fp32|None, d_weight [V,H]).  `dweight` may be a preallocated bf16 or
     fp32 [V,H] buffer (with `dweight_accumulate` the kernel adds into it: fused gradient accumulation)."""
+    _check_operands(hidden, weight, ids, "lm_head_backward_raw", lse=lse, dlogp=dlogp)
     lib = _lib.load()
     T, H = hidden.shape
     V = weight.shape[0]

@@ -304,29 +304,35 @@ class VocabShardedLMHead:
     def _peer_accumulator(self, T: int, dev) -> torch.Tensor:
         if self._sym is not None and self._sym["T"] == T:
             return self._sym["acc"]
+        if self._sym is not None:
+            self.close()
         if T % 32 != 0:
             raise ValueError("fused reduce-scatter needs T % 32 == 0 (an epilogue slab must not straddle two token owners)")
         import ctypes
 
         lib = _lib.load()
-        acc = torch.zeros(T, self.H, dtype=torch.float32, device=dev)
-        # export: the CUDA IPC handle of the allocation that holds `acc` and acc's offset inside it (torch's caching allocator
-        # may place the tensor inside a larger cudaMalloc segment)
-        share = acc.untyped_storage()._share_cuda_()
-        handle, offset = bytes(share[1]), int(share[3]) + acc.storage_offset() * 4
+        # the accumulator is a cudaMalloc allocation of its own (exportable as a whole), wrapped as a torch tensor
+        base, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        _lib.check(lib.prl_ipc_alloc(T * self.H * 4, ctypes.byref(base), handle), "prl_ipc_alloc")
+
+        class _Buf:  # zero-copy view for torch (CUDA array interface v2)
+            __cuda_array_interface__ = {"shape": (T, self.H), "typestr": "<f4", "data": (int(base.value), False), "version": 2}
+
+        acc = torch.as_tensor(_Buf(), device=dev)
+        acc.zero_()
         infos = [None] * self.world
-        dist.all_gather_object(infos, (handle, offset), group=self.group)
+        dist.all_gather_object(infos, bytes(handle.raw), group=self.group)
         ptrs, opened = [], []
-        for j, (h, off) in enumerate(infos):
+        for j, h in enumerate(infos):
             if j == self.rank:
-                ptrs.append(acc.data_ptr())
+                ptrs.append(int(base.value))
                 continue
-            base = ctypes.c_void_p()
-            _lib.check(lib.prl_ipc_open(ctypes.c_char_p(h), ctypes.byref(base)), "prl_ipc_open")
-            opened.append(base.value)
-            ptrs.append(base.value + off)
+            peer = ctypes.c_void_p()
+            _lib.check(lib.prl_ipc_open(ctypes.c_char_p(h), ctypes.byref(peer)), "prl_ipc_open")
+            opened.append(peer.value)
+            ptrs.append(peer.value)
         arr = (ctypes.c_void_p * self.world)(*ptrs)
-        self._sym = dict(T=T, acc=acc, ptrs=arr, opened=opened, flag=torch.zeros(1, dtype=torch.float32, device=dev))
+        self._sym = dict(T=T, acc=acc, ptrs=arr, opened=opened, own=int(base.value), flag=torch.zeros(1, dtype=torch.float32, device=dev))
         dist.barrier(group=self.group)  # every rank has mapped every buffer before anyone uses them
         return acc
 
@@ -356,6 +362,9 @@ class VocabShardedLMHead:
             lib = _lib.load()
             for p in self._sym["opened"]:
                 lib.prl_ipc_close(p)
+            dist.barrier(group=self.group)  # nobody maps the buffer any more
+            own, self._sym["acc"] = self._sym["own"], None
+            lib.prl_ipc_free(own)
             self._sym = None
 
     def micro_step(self, hidden_local, micro_batch, loss_config, loss_scale, gathered=None):

@@ -33,17 +33,27 @@ def rollout_path(output_dir: Path | str, step: int, rank: int) -> Path:
 
 
 def save_step(output_dir: Path | str, step: int, all_data_ranks_batches: list[list[MicroBatch]]) -> list[Path]:
-    """Writer side (orchestrator.py:356-363): one file per data rank, tmp + rename."""
+    """Writer side (orchestrator.py:356-363): one file per data rank, tmp + rename.  Every tensor is made to OWN its storage
+    before it is serialised: `prepare_batch` hands out micro-batches that are slice views of one step-wide buffer per field, and
+    torch.save writes a view's whole backing storage -- without the clone every rank file would carry every rank's tokens."""
     step_path = get_rollout_dir(output_dir) / f"step_{step}"
     step_path.mkdir(parents=True, exist_ok=True)
     paths = []
     for i, batches in enumerate(all_data_ranks_batches):
         batch_path = step_path / f"rank_{i}.pt"
         tmp_path = batch_path.with_suffix(".tmp")
-        torch.save([{k: (v.cpu() if torch.is_tensor(v) else v) for k, v in mb.items()} for mb in batches], tmp_path)
+        torch.save([{k: (_owned_cpu(v) if torch.is_tensor(v) else v) for k, v in mb.items()} for mb in batches], tmp_path)
         tmp_path.rename(batch_path)
         paths.append(batch_path)
     return paths
+
+
+def _owned_cpu(t: torch.Tensor) -> torch.Tensor:
+    """CPU copy whose storage holds exactly the tensor's elements (no-op for a CPU tensor that already owns a compact storage)"""
+    c = t.detach().cpu()
+    if c.untyped_storage().nbytes() != c.numel() * c.element_size() or not c.is_contiguous():
+        c = c.clone(memory_format=torch.contiguous_format)
+    return c
 
 
 def wait_for_path(path: Path, interval: float = 1.0, timeout: float | None = None) -> None:

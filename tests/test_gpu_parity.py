@@ -168,6 +168,82 @@ def test_loss_reference_unit_test_shapes(P):
         np.testing.assert_allclose(loss.item(), want, rtol=1e-4)
 
 
+@pytest.mark.parametrize("ratio_type", ["token", "sequence"])
+def test_loss_nan_propagation_matches_torch(P, ratio_type):
+    """A NaN log-prob must surface exactly where the reference's torch ops put it (torch.clamp propagates NaN, fminf does not):
+    NaN loss when the token is unmasked, finite loss when it is masked out, NaN gradient at the token itself either way in
+    token mode (autograd: 0 * exp'(nan)).  Checked against the same torch ops under autograd (oracle/torch_port.py)."""
+    from oracle import torch_port
+
+    torch.manual_seed(3)
+    lens = [40, 57, 31]
+    T = sum(lens)
+    old, adv = torch.randn(T).cuda(), torch.randn(T).cuda()
+    for where, masked_out in ((5, False), (60, True), (T - 1, False)):
+        base = (old + 0.1 * torch.randn(T).cuda())
+        base[where] = float("nan")
+        mask = torch.rand(T).cuda() < 0.8
+        mask[where] = not masked_out
+        lp_ref = base.clone().requires_grad_(True)
+        want = torch_port.loss_cpu(lp_ref, old, adv, mask, lens, ratio_type, ratio_type == "sequence", 8.0, int(mask.sum()))
+        want.backward()
+        lp = base.clone().requires_grad_(True)
+        loss, tens = P.compute_loss(lp.split(lens), old.split(lens), adv.split(lens), mask.split(lens),
+                                    P.LossConfig(ratio_type, ratio_type == "sequence", 8.0), int(mask.sum()))
+        loss.backward()
+        assert math.isnan(loss.item()) == math.isnan(want.item()) == (not masked_out), (where, loss.item(), want.item())
+        assert torch.equal(torch.isnan(lp.grad), torch.isnan(lp_ref.grad)), (ratio_type, where)
+        ok = ~torch.isnan(lp_ref.grad)
+        np.testing.assert_allclose(lp.grad[ok].cpu().numpy(), lp_ref.grad[ok].cpu().numpy(), rtol=1e-4, atol=1e-7)
+        if masked_out:
+            np.testing.assert_allclose(loss.item(), want.item(), rtol=1e-4)
+
+
+def test_raw_wrappers_reject_operands_the_kernels_would_misread(P):
+    """an fp32 / non-contiguous / mis-shaped operand must raise instead of being reinterpreted as bf16 by the TMA descriptors"""
+    T, H, V = 64, 64, 512
+    h, w, i = torch.randn(T, H).cuda().bfloat16(), torch.randn(V, H).cuda().bfloat16(), torch.randint(0, V, (T,)).cuda()
+    lse, g = torch.zeros(T).cuda(), torch.zeros(T).cuda()
+    bad = [(h.float(), w, i), (h, w.float(), i), (h.t().contiguous().t(), w, i), (h, w[:, :32], i), (h, w, i.int()), (h, w, i[:-1]),
+           (h.cpu(), w, i)]
+    for hh, ww, ii in bad:
+        with pytest.raises((ValueError, RuntimeError)):
+            P.lm_head_forward_raw(hh, ww, ii, 1.0)
+        with pytest.raises((ValueError, RuntimeError)):
+            P.lm_head_backward_raw(hh, ww, ii, lse, g, 1.0)
+    with pytest.raises(ValueError):
+        P.lm_head_backward_raw(h, w, i, lse.double(), g, 1.0)
+    with pytest.raises(ValueError):
+        P.recompute_logprobs(h.float().unsqueeze(0), w, i.unsqueeze(0), 1.0)
+    P.lm_head_forward_raw(h, w, i, 1.0)  # the well-formed call goes through
+
+
+def test_logits_stats_nan_and_minus_inf_like_torch(P):
+    """materialised-logits helpers: -inf logits are fine for the log-prob (torch.logsumexp) and make the entropy NaN
+    (softmax * z = 0 * -inf, rl/loss.py:45-46); a NaN logit makes both NaN -- as the reference's torch ops do"""
+    torch.manual_seed(0)
+    z = torch.randn(1, 6, 300).cuda()
+    z[0, 1, 0] = float("-inf")      # the very first element a thread sees
+    z[0, 2, 17] = float("-inf")
+    z[0, 3, 100] = float("nan")
+    ids = torch.randint(1, 300, (1, 6)).cuda()
+    lp = P.selective_log_softmax(z, ids)
+    ent = P.compute_entropy(z)
+    ref_lp = torch.gather(z, -1, ids.unsqueeze(-1)).squeeze(-1) - torch.logsumexp(z, -1)
+    pd = torch.softmax(z, -1)
+    ref_ent = torch.logsumexp(z, -1) - (pd * z).sum(-1)
+    assert torch.equal(torch.isnan(lp), torch.isnan(ref_lp)) and torch.equal(torch.isnan(ent), torch.isnan(ref_ent))
+    ok = ~torch.isnan(ref_lp)
+    assert (lp[ok] - ref_lp[ok]).abs().max().item() < 1e-5
+    ok = ~torch.isnan(ref_ent)
+    assert (ent[ok] - ref_ent[ok]).abs().max().item() < 1e-5
+    # logging moments: torch.min / torch.max propagate NaN
+    st = P.TensorStats(median=False)
+    st.add("x", torch.tensor([1.0, float("nan"), 3.0]).cuda())
+    got = st.compute_stats()
+    assert math.isnan(got["x/min"]) and math.isnan(got["x/max"]) and math.isnan(got["x/mean"])
+
+
 def test_loss_all_masked_and_big(P):
     # padding micro-batches: all-False mask, zero advantages, loss_scale 0 (orchestrator/batch.py:153-161)
     T = 1000
@@ -372,7 +448,9 @@ def test_lmhead_fixtures_from_reference(P):
     (200, 1024, 151936, 0.6, "token", 0),
 ])
 def test_micro_step_vs_oracle(P, T, H, V, tau, mode, vchunk, save):
-    os.environ["PRL_VCHUNK"] = str(vchunk) if vchunk else "8192"
+    from prime_rl_cse_b200 import _lib as _lib_mod
+
+    _lib_mod.set_knob("PRL_VCHUNK", vchunk if vchunk else 8192)  # knobs are read from the environment once; tests set them directly
     try:
         hidden, weight, ids = _mk(T, H, V, T + H, peaked=True)
         rng = np.random.default_rng(T)
@@ -404,7 +482,7 @@ def test_micro_step_vs_oracle(P, T, H, V, tau, mode, vchunk, save):
         assert h.grad.dtype == torch.bfloat16 and w.grad.dtype == torch.bfloat16
         assert float(h.grad[-1].abs().max()) == 0.0  # the dropped last position gets no gradient (loss.py:54)
     finally:
-        os.environ.pop("PRL_VCHUNK", None)
+        _lib_mod.set_knob("PRL_VCHUNK", 16384)
 
 
 @pytest.mark.parametrize("cta_group,epi_tma", [(1, 1), (2, 0), (4, 1), (1, 0)])
@@ -716,6 +794,8 @@ def test_dhidden_k_split_matches_unsplit_and_is_deterministic(P):
     accumulator.  Same result as the unsplit GEMM up to fp32 summation order, and run-to-run identical (two addends commute)."""
     from prime_rl_cse_b200 import lm_head_backward_raw, lm_head_backward_saved_raw, lm_head_forward_save_raw
 
+    from prime_rl_cse_b200 import _lib as _lib_mod
+
     T, H, V, tau = 600, 256, 20000 + 64, 0.8
     hidden, weight, ids = _mk(T, H, V, 17, peaked=True)
     h, w, i = hidden.cuda(), weight.cuda(), ids.cuda()
@@ -723,7 +803,7 @@ def test_dhidden_k_split_matches_unsplit_and_is_deterministic(P):
     out = {}
     try:
         for ks in ("1", "2"):
-            os.environ["PRL_K_SPLITS"] = ks
+            _lib_mod.set_knob("PRL_K_SPLITS", int(ks))
             for f32 in (False, True):
                 lse = lm_head_forward_save_raw(h, w, i, 1 / tau)[2]
                 a = lm_head_backward_raw(h, w, i, lse, g, 1 / tau, vchunk=V, dhidden_f32=f32)[0]
@@ -735,7 +815,7 @@ def test_dhidden_k_split_matches_unsplit_and_is_deterministic(P):
                 assert torch.equal(c, c2) and torch.equal(a, c)  # deterministic; single-chunk recompute == saved
                 out[(ks, f32)] = (a.float(), b.float(), c.float())
     finally:
-        os.environ.pop("PRL_K_SPLITS", None)
+        _lib_mod.set_knob("PRL_K_SPLITS", 0)
     for f32 in (False, True):
         ref = out[("1", f32)][0]
         for t in out[("2", f32)] + out[("1", f32)][1:]:

@@ -65,6 +65,29 @@ def test_writer_round_trip_and_atomic_rename(io, tmp_path):
     assert len(ref) == len(mine) and all(set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in KEYS) for a, b in zip(ref, mine))
 
 
+def test_rank_files_hold_only_their_own_tokens(io, tmp_path):
+    """micro-batches that are slice VIEWS of one step-wide buffer (what prepare_batch(device_output=False) hands out) must not
+    drag the whole buffer into every rank file: file size is bounded by the rank's own token count"""
+    n_ranks, per_rank, T = 4, 3, 5000
+    total = n_ranks * per_rank * T
+    flat = {"input_ids": torch.arange(total), "position_ids": torch.arange(total) % T, "advantages": torch.randn(total),
+            "logprobs": torch.randn(total), "loss_mask": torch.rand(total) < 0.5}
+    ranks = []
+    for r in range(n_ranks):
+        mbs = []
+        for i in range(per_rank):
+            a = (r * per_rank + i) * T
+            mbs.append({k: v[a : a + T].unsqueeze(0) for k, v in flat.items()} | {"temperature": 1.0})
+        ranks.append(mbs)
+    paths = io.save_step(tmp_path, 0, ranks)
+    bytes_per_token = 8 + 8 + 4 + 4 + 1
+    for r, p in enumerate(paths):
+        assert os.path.getsize(p) < per_rank * T * bytes_per_token * 1.05 + 20000, os.path.getsize(p)
+        got = io.DataLoader(tmp_path, 0, rank=r).get_batch()
+        assert all(torch.equal(g[k], w[k]) for g, w in zip(got, ranks[r]) for k in KEYS)
+        assert all(g[k].untyped_storage().nbytes() == g[k].numel() * g[k].element_size() for g in got for k in KEYS)
+
+
 def test_wait_for_batch_sees_a_file_that_arrives_later(io, tmp_path):
     dl = io.DataLoader(tmp_path, 0, rank=0)
     mb = {k: torch.zeros(1, 4, dtype=dt) for k, dt in zip(KEYS, (torch.int64, torch.int64, torch.float32, torch.float32, torch.bool))}
