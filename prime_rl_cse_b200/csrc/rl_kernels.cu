@@ -368,8 +368,7 @@ __global__ void __launch_bounds__(512) loss_seq_kernel(const float* __restrict__
     const float mean_a = (float)Sa / n;
     partial[seg] = (double)(-c * mean_a);
     float coef = -mean_a * r;
-    if (!(r <= clip) || !(pre <= 10.f)) coef = 0.f;
-    if (r != r) coef = r;  // a NaN log-prob in the segment: NaN gradient for its unmasked tokens, as autograd gives
+    if (!(r <= clip) || !(pre <= 10.f)) coef = 0.f;  // also for a NaN segment: clamp's backward is where(x <= max, g, 0), not g * mask
     if (length_norm) coef = coef / n;
     coef_sh = coef * inv_scale;
   }
