@@ -155,6 +155,82 @@ __global__ void __launch_bounds__(256) advantages_small_group_kernel(const float
   }
 }
 
+// G in {8, 16, 24, 32} (every BASELINE configuration): each lane owns EIGHT consecutive rollouts (two 16-byte loads, two
+// 16-byte stores), M = G / 8 consecutive lanes own a group.  The L8 lane accumulator j of the group is
+// ((x[j] + x[j+8]) + x[j+16]) + x[j+24] = the j-th component of lanes 0..M-1 added in lane order (M shuffles per component), the
+// total is the eight accumulators added left to right: the same fp32 operations in the same order as the generic kernels
+// (and the oracle), ~5 instead of ~20 instructions per rollout, so large batches run at HBM speed.
+template <int M>
+__global__ void __launch_bounds__(256) advantages_vec8_kernel(const float* __restrict__ rewards, const int64_t* __restrict__ lengths,
+                                                              int64_t ngroups, int kind, float* __restrict__ out) {
+  constexpr int G = 8 * M;
+  constexpr int GPW = 32 / M;  // groups per warp (M = 3: 10 groups, 2 idle lanes)
+  const int lane = threadIdx.x & 31;
+  const int gl = lane / M, q = lane - gl * M;
+  const int base = gl < GPW ? gl * M : 0;  // idle lanes still take part in the shuffles
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t n_sets = (ngroups + GPW - 1) / GPW;
+  for (int64_t set = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); set < n_sets; set += warps_total) {
+    const int64_t g = set * GPW + gl;
+    const bool active = gl < GPW && g < ngroups;
+    const int64_t e0 = g * G + 8 * q;  // first of this lane's eight rollouts
+    float x[8], w[8];
+    if (active) {
+      const float4 a = *reinterpret_cast<const float4*>(rewards + e0), b = *reinterpret_cast<const float4*>(rewards + e0 + 4);
+      x[0] = a.x, x[1] = a.y, x[2] = a.z, x[3] = a.w, x[4] = b.x, x[5] = b.y, x[6] = b.z, x[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    }
+    float num, den = (float)G;
+    auto sum_l8 = [&](const float (&v)[8]) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = __shfl_sync(FULL, v[j], base);
+#pragma unroll
+        for (int m = 1; m < M; ++m) acc[j] = __fadd_rn(acc[j], __shfl_sync(FULL, v[j], base + m));
+      }
+      float t = acc[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) t = __fadd_rn(t, acc[j]);
+      return t;
+    };
+    if (kind == PRL_ADV_OPO) {
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const longlong2 l2 = *reinterpret_cast<const longlong2*>(lengths + e0 + j);
+          w[j] = (float)l2.x, w[j + 1] = (float)l2.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = 0.f;
+      }
+      float rw[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rw[j] = __fmul_rn(x[j], w[j]);
+      num = sum_l8(rw);
+      den = sum_l8(w);
+    } else {
+      num = sum_l8(x);
+    }
+    if (active) {
+      const float mean = __fdiv_rn(num, den);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = __fsub_rn(x[j], mean);
+        if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = max_nan(a, 0.f);
+        if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
+        o[j] = a;
+      }
+      *reinterpret_cast<float4*>(out + e0) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(out + e0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) advantages_kernel(const float* __restrict__ rewards, const int64_t* __restrict__ lengths,
                                                          int64_t ngroups, int G, int kind, float* __restrict__ out,
                                                          const int64_t* __restrict__ tok_offsets, float* __restrict__ token_out) {
@@ -344,13 +420,29 @@ __global__ void __launch_bounds__(512) loss_seq_kernel(const float* __restrict__
   const int seg = blockIdx.x;
   const int t0 = cu[seg], t1 = cu[seg + 1];
   double sd = 0.0, sa = 0.0, sn = 0.0;
-  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-    if (mask[t]) {
-      sd += (double)(logp[t] - old[t]);
-      sa += (double)adv[t];
+  auto take = [&](float l, float o, float a, bool m) {
+    if (m) {
+      sd += (double)(l - o);
+      sa += (double)a;
       sn += 1.0;
     }
+  };
+  // 16-byte loads over the 4-aligned body of the segment (all four arrays share the index, so one alignment test on the
+  // base pointers covers them); up to 3 scalar tokens at either end
+  const bool vec_ok = ((((uintptr_t)logp | (uintptr_t)old | (uintptr_t)adv | (uintptr_t)dlogp) & 15) == 0) && (((uintptr_t)mask & 3) == 0);
+  const int b0 = vec_ok ? min((t0 + 3) & ~3, t1) : t1;  // body = [b0, b1), both multiples of 4
+  const int b1 = vec_ok ? max(b0, t1 & ~3) : t1;
+  for (int t = t0 + threadIdx.x; t < b0; t += blockDim.x) take(logp[t], old[t], adv[t], mask[t] != 0);
+  for (int q = b0 / 4 + threadIdx.x; q < b1 / 4; q += blockDim.x) {
+    const float4 l = reinterpret_cast<const float4*>(logp)[q], o = reinterpret_cast<const float4*>(old)[q];
+    const float4 a = reinterpret_cast<const float4*>(adv)[q];
+    const uchar4 m = reinterpret_cast<const uchar4*>(mask)[q];
+    take(l.x, o.x, a.x, m.x != 0);
+    take(l.y, o.y, a.y, m.y != 0);
+    take(l.z, o.z, a.z, m.z != 0);
+    take(l.w, o.w, a.w, m.w != 0);
   }
+  for (int t = b1 + threadIdx.x; t < t1; t += blockDim.x) take(logp[t], old[t], adv[t], mask[t] != 0);
   const double Sd = block_sum(sd, sh);
   const double Sa = block_sum(sa, sh);
   const double Sn = block_sum(sn, sh);
@@ -374,7 +466,12 @@ __global__ void __launch_bounds__(512) loss_seq_kernel(const float* __restrict__
   }
   __syncthreads();
   const float coef = coef_sh;
-  for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) dlogp[t] = mask[t] ? coef : 0.f;
+  for (int t = t0 + threadIdx.x; t < b0; t += blockDim.x) dlogp[t] = mask[t] ? coef : 0.f;
+  for (int q = b0 / 4 + threadIdx.x; q < b1 / 4; q += blockDim.x) {
+    const uchar4 m = reinterpret_cast<const uchar4*>(mask)[q];
+    reinterpret_cast<float4*>(dlogp)[q] = make_float4(m.x ? coef : 0.f, m.y ? coef : 0.f, m.z ? coef : 0.f, m.w ? coef : 0.f);
+  }
+  for (int t = b1 + threadIdx.x; t < t1; t += blockDim.x) dlogp[t] = mask[t] ? coef : 0.f;
 }
 
 // sums partial[0..n) left to right (the reference adds segment losses in order, loss.py:110) and scales
@@ -726,6 +823,18 @@ int prl_advantages_f32(const float* rewards, const int64_t* lengths, int64_t n, 
   const int64_t blocks_needed = (ngroups + 7) / 8;
   const int64_t cap = (int64_t)sm_count() * 8;
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(rewards) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(lengths)) & 15) == 0;
+  if (token_out == nullptr && aligned16 && group % 8 == 0 && group <= 32) {
+    const int m = group / 8, gpw = 32 / m;
+    const int64_t need = ((ngroups + gpw - 1) / gpw + 7) / 8;  // one group-set per warp iteration, 8 warps per CTA
+    const int g3 = (int)(need < cap * 2 ? need : cap * 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m == 1) advantages_vec8_kernel<1><<<g3, 256, 0, st>>>(rewards, lengths, ngroups, kind, out);
+    if (m == 2) advantages_vec8_kernel<2><<<g3, 256, 0, st>>>(rewards, lengths, ngroups, kind, out);
+    if (m == 3) advantages_vec8_kernel<3><<<g3, 256, 0, st>>>(rewards, lengths, ngroups, kind, out);
+    if (m == 4) advantages_vec8_kernel<4><<<g3, 256, 0, st>>>(rewards, lengths, ngroups, kind, out);
+    return check_launch("advantages_vec8_kernel");
+  }
   if (group <= 32 && token_out == nullptr) {
     const int gpw = 32 / group;
     const int64_t need = (((ngroups + gpw - 1) / gpw + 3) / 4 + 7) / 8;  // 4 group-sets per warp iteration, 8 warps per CTA

@@ -74,12 +74,19 @@ def test_advantages_fixtures_bit_exact(P):
 
 def test_advantages_large_and_broadcast(P):
     rng = np.random.default_rng(5)
-    for grp, n in [(16, 1 << 16), (32, 1 << 12), (7, 7 * 100), (1, 5)]:
+    for grp, n in [(16, 1 << 16), (32, 1 << 12), (7, 7 * 100), (1, 5), (8, 8 * 1001), (24, 24 * 333), (16, 16 * 3), (32, 32)]:
         r = rng.standard_normal(n).astype(np.float32)
         ln = rng.integers(1, 5000, n)
         for k in KINDS:
             got = P.compute_advantages_tensor(cu(r), cu(ln), grp, k).cpu().numpy()
             np.testing.assert_array_equal(got, oracle.advantages(r, ln, grp, k))
+    # group sizes 8 / 16 / 24 / 32 take the 8-rollouts-per-lane kernel (16-byte loads) when the buffers are 16-byte aligned;
+    # a view that is only 4-byte aligned must give the same bits through the generic kernel
+    r = rng.standard_normal(16 * 50 + 1).astype(np.float32)
+    ln = rng.integers(1, 5000, 16 * 50 + 1)
+    for k in KINDS:
+        got = P.compute_advantages_tensor(cu(r)[1:], cu(ln)[1:], 16, k).cpu().numpy()
+        np.testing.assert_array_equal(got, oracle.advantages(r[1:], ln[1:], 16, k))
     # fused per-token broadcast (orchestrator/batch.py:44)
     n, grp = 64, 8
     r = rng.standard_normal(n).astype(np.float32)

@@ -15,8 +15,13 @@ if os.path.exists(pp):
 dev = "cuda"
 
 
+QUICK = bool(os.environ.get("HBM_QUICK"))  # under ncu: one launch per kernel is enough (ncu replays it itself)
+
+
 def ev(fn, reps=10):
-    for _ in range(3):
+    if QUICK:
+        reps = 1
+    for _ in range(0 if QUICK else 3):
         fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -56,6 +61,20 @@ nseg = 2048
 cu2 = torch.arange(0, nseg + 1, dtype=torch.int32, device=dev) * (T // nseg)
 report("loss sequence mode T=2^26, 2048 segments", 17 * T, ev(lambda: _loss_packed_raw(logp, old, adv, mask, cu2, nseg, 1, True, 8.0, nseg)), "13 B read + 4 B written per token")
 del logp, old, adv, mask
+
+# masked rows (rows.py): partition of the positions (latency-bound, one CTA), gather of hidden rows into "active first" order and
+# the scatter of d_hidden back: 2 x 2 B x T x H each
+from prime_rl_cse_b200 import rows as R_
+Tm, Hm = 16384, 4096
+hid = torch.randn(Tm, Hm, device=dev).bfloat16(); idsm = torch.randint(0, 1000, (Tm,), device=dev)
+mk = torch.rand(Tm, device=dev) < 0.75
+part = R_.partition_positions(mk, True)
+na = part.n_active
+report("partition_positions T=16384 (single CTA)", 1 * Tm + 8 * Tm, ev(lambda: R_.partition_positions(mk, True), 50), "latency-bound by design")
+report("gather_rows 16383 x 4096 bf16", 2 * 2 * (Tm - 1) * Hm, ev(lambda: R_.gather_rows(hid, idsm, part, part.rows)), "2 B read + 2 B written per element")
+hp, _ = R_.gather_rows(hid, idsm, part, na)
+report("scatter_rows (75 % active) -> 16384 x 4096", 2 * na * Hm + 2 * Tm * Hm, ev(lambda: R_.scatter_rows(hp, part, na, Hm)), "active rows read, all rows written")
+del hid, hp
 
 # segments: 8 B/token, single CTA by design (T <= 64k in the trainer)
 pos = torch.arange(32768, device=dev) % 4096
