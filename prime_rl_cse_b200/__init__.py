@@ -23,8 +23,9 @@ from .micro_step import rl_micro_step
 from .rollout_io import DataLoader, FakeDataLoader, save_step, upload_micro_batches
 from .segments import get_response_lengths, segments_from_position_ids
 from .stats import TensorStats
-from .parallel import (exchange_partials, local_loss_scale, shard_micro_batches, vocab_parallel_lm_head_logprobs_entropy,
-                       vocab_shard_bounds)
+from .parallel import (VocabShardedLMHead, exchange_partials, local_loss_scale, shard_micro_batches,
+                       vocab_parallel_lm_head_logprobs_entropy, vocab_shard_bounds)
+from .rows import partition_positions
 
 __all__ = [
     "compute_advantages", "compute_advantages_tensor", "LossConfig", "MicroBatch", "fake_micro_batch",
@@ -33,4 +34,5 @@ __all__ = [
     "shifted_logprobs_entropy", "rl_micro_step", "get_response_lengths", "segments_from_position_ids",
     "fused_linear_cross_entropy", "recompute_logprobs", "TensorStats", "prepare_batch", "first_fit_decreasing",
     "DataLoader", "FakeDataLoader", "save_step", "upload_micro_batches", "exchange_partials", "local_loss_scale", "shard_micro_batches", "vocab_parallel_lm_head_logprobs_entropy", "vocab_shard_bounds",
+    "VocabShardedLMHead", "partition_positions",
 ]

@@ -104,7 +104,12 @@ def to_ns(v, unit):
 
 
 def summarise(rep, tag, traffic):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """`rep`: an .ncu-rep, or the CSV `ncu -i <rep> --page raw --csv` printed on the GPU box (the reports themselves are 20-30 MB
+    each and do not fit gpurun's 64 MiB return channel)"""
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3:
         print(f"{rep}: no launches")
@@ -145,7 +150,8 @@ def main():
     a = ap.parse_args()
     if not a.no_sass:
         write_sass(a.tag)
-    reports = a.reports if a.reports is not None else sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"{a.tag}_*.ncu-rep")))
+    reports = a.reports if a.reports is not None else sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"{a.tag}_*__*.csv")) +
+                                                            glob.glob(os.path.join(ROOT, "gpurun_out", f"{a.tag}_*.ncu-rep")))
     traffic = {}
     for rep in reports:
         summarise(rep, a.tag, traffic)
