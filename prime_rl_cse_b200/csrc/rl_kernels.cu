@@ -474,13 +474,22 @@ __global__ void __launch_bounds__(512) loss_seq_kernel(const float* __restrict__
   for (int t = b1 + threadIdx.x; t < t1; t += blockDim.x) dlogp[t] = mask[t] ? coef : 0.f;
 }
 
-// sums partial[0..n) left to right (the reference adds segment losses in order, loss.py:110) and scales
-__global__ void loss_finalize_kernel(const double* __restrict__ partial, int n, double inv_scale, float* __restrict__ loss) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double t = 0.0;
-    for (int i = 0; i < n; ++i) t += partial[i];
-    *loss = (float)(t * inv_scale);
+// Sums partial[0..n) in fp64 in a FIXED order and scales: deterministic, and for n <= 32 (every trainer shape: one partial per
+// segment or per CTA of a 16k-token row) exactly the left-to-right order in which the reference adds the segment losses
+// (loss.py:110).  Longer lists (bench sizes: thousands of partials) are summed as 32 strided lane sums combined by a fixed
+// shuffle tree -- one dependent chain of n global loads in one thread cost 50-75 us there.
+__global__ void __launch_bounds__(32) loss_finalize_kernel(const double* __restrict__ partial, int n, double inv_scale, float* __restrict__ loss) {
+  const int lane = threadIdx.x;
+  double t = 0.0;
+  if (n <= 32) {
+    if (lane == 0)
+      for (int i = 0; i < n; ++i) t += partial[i];
+  } else {
+    for (int i = lane; i < n; i += 32) t += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(FULL, t, o);
   }
+  if (lane == 0) *loss = (float)(t * inv_scale);
 }
 
 __global__ void scale_kernel(const float* __restrict__ a, const float* __restrict__ scale, float* __restrict__ out, int64_t n) {

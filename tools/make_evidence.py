@@ -29,7 +29,7 @@ GEMM_NAMES = {
     (2, 2, 0, 1, 2): "lmhead_bwd_dhidden_kernel",
     (2, 2, 1, 1, 2): "lmhead_bwd_dweight_kernel",
 }
-HOT_PLAIN = ["dz_from_saved_logits_kernel", "merge_partials_kernel", "f32_to_bf16_kernel", "loss_token_kernel", "loss_seq_kernel",
+HOT_PLAIN = ["advantages_vec8_kernel", "dz_from_saved_logits_kernel", "merge_partials_kernel", "f32_to_bf16_kernel", "loss_token_kernel", "loss_seq_kernel",
              "loss_finalize_kernel", "advantages_small_group_kernel", "advantages_kernel", "segments_kernel", "partition_positions_kernel",
              "gather_rows_kernel", "scatter_rows_kernel", "gather_tokens_kernel", "scatter_tokens_kernel", "logits_stats_kernel",
              "logits_logsoftmax_bwd_kernel", "masked_moments_kernel", "pack_rollouts_kernel"]
@@ -72,7 +72,8 @@ def write_sass(tag):
             base = friendly(mangled)
             if base not in HOT_PLAIN:
                 continue
-            short = base
+            t = re.search(r"_kernelILi(\d+)E", mangled)  # a template instantiation: keep its argument in the file name
+            short = base + (f"_{t.group(1)}" if t else "")
         # keep address + instruction, drop the hex encodings (they double the size and carry nothing a reader needs)
         body = [re.sub(r"\s*/\* 0x[0-9a-f]{16} \*/\s*$", "", ln) for ln in ch.splitlines()]
         body = [ln for ln in body if ln.strip()]
