@@ -40,6 +40,10 @@ extern "C" {
 #define PRL_ADV_DRGRPO_NEGCLIPPED 1
 #define PRL_ADV_RLOO 2
 #define PRL_ADV_OPO 3
+/* extension, NOT in the reference's registry (which is Dr.GRPO: mean only): GRPO's std-normalised advantage
+ * (r - mean) / (std + PRL_ADV_GRPO_EPS), std unbiased (torch.std); BASELINE.json north_star names "per-group reward mean/std" */
+#define PRL_ADV_GRPO 4
+#define PRL_ADV_GRPO_EPS 1e-6f
 
 /* ratio types: LossConfig.ratio_type, src/prime_rl/trainer/rl/config.py:22 */
 #define PRL_RATIO_TOKEN 0

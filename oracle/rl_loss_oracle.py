@@ -19,6 +19,7 @@ import numpy as np
 __all__ = [
     "LossCfg",
     "ADVANTAGE_KINDS",
+    "EXTENSION_ADVANTAGE_KINDS",
     "sum_l8",
     "advantages",
     "response_lengths",
@@ -35,6 +36,11 @@ __all__ = [
 ]
 
 ADVANTAGE_KINDS = ("drgrpo", "drgrpo-negclipped", "rloo", "opo")
+# NOT in the reference's registry (advantage.py:63-68 is Dr.GRPO: mean only).  BASELINE.json's north_star names "per-group
+# reward mean/std", so the product also offers GRPO's std-normalised form; this is its definition:
+#   a_i = (r_i - mean) / (std + 1e-6), std = sqrt(sum (r_i - mean)^2 / (G - 1))  (unbiased, as torch.std), L8-ordered sums.
+EXTENSION_ADVANTAGE_KINDS = ("grpo",)
+GRPO_EPS = np.float32(1e-6)
 
 
 @dataclass
@@ -80,7 +86,7 @@ def advantages(rewards: Sequence[float], lengths: Sequence[int], group: int, kin
     rloo :41-43 (left-to-right `adv * G / (G - 1)`; G == 1 gives nan like the
     reference), opo :55-57.
     """
-    if kind not in ADVANTAGE_KINDS:
+    if kind not in ADVANTAGE_KINDS + EXTENSION_ADVANTAGE_KINDS:
         raise KeyError(kind)
     r = np.asarray(rewards, dtype=np.float32)
     ln = np.asarray(lengths, dtype=np.int64)
@@ -103,6 +109,10 @@ def advantages(rewards: Sequence[float], lengths: Sequence[int], group: int, kin
             elif kind == "rloo":
                 with np.errstate(divide="ignore", invalid="ignore"):
                     a = ((a * f(group)).astype(np.float32) / f(group - 1)).astype(np.float32)
+            elif kind == "grpo":
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    std = np.sqrt(f(sum_l8((a * a).astype(np.float32)) / f(group - 1)), dtype=np.float32)
+                    a = (a / f(std + GRPO_EPS)).astype(np.float32)
         out[g0 : g0 + group] = a
     return out
 

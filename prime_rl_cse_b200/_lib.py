@@ -15,7 +15,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PRL_LIB_PATH") or os.path.join(_HERE, "libprl_b200.so")
 
-PRL_ADV_KINDS = {"drgrpo": 0, "drgrpo-negclipped": 1, "rloo": 2, "opo": 3}
+PRL_ADV_KINDS = {"drgrpo": 0, "drgrpo-negclipped": 1, "rloo": 2, "opo": 3,
+                 "grpo": 4}  # "grpo" (std-normalised) is an extension: not in the reference's registry (advantage.py:63-68)
 PRL_RATIO = {"token": 0, "sequence": 1}
 PRL_DT_BF16, PRL_DT_F32 = 0, 1
 

@@ -9,8 +9,8 @@ import torch
 
 from . import _lib
 
-AdvantageType = Literal["drgrpo", "drgrpo-negclipped", "rloo", "opo"]
-REGISTRY = tuple(_lib.PRL_ADV_KINDS)  # same keys as advantage.py:63-68
+AdvantageType = Literal["drgrpo", "drgrpo-negclipped", "rloo", "opo", "grpo"]
+REGISTRY = tuple(_lib.PRL_ADV_KINDS)  # the reference's keys (advantage.py:63-68) + "grpo" = (r - mean) / (std + 1e-6), an extension
 
 
 def compute_advantages_tensor(

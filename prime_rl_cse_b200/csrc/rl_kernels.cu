@@ -40,7 +40,7 @@ __device__ __forceinline__ double max_nan(double a, double b) { return (a != a) 
 // __fdiv_rn keep nvcc from contracting into FMAs, so the result is bit-identical to the oracle.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum_l8(const float* __restrict__ x, int G, int lane, bool weighted,
-                                             const int64_t* __restrict__ w) {
+                                             const int64_t* __restrict__ w, bool squared_dev = false, float center = 0.f) {
   const int n8 = (G / 8) * 8;
   float acc = 0.f;
   bool first = true;
@@ -50,6 +50,10 @@ __device__ __forceinline__ float warp_sum_l8(const float* __restrict__ x, int G,
     if (i < n8) {
       v = x[i];
       if (weighted) v = __fmul_rn(v, (float)w[i]);
+      if (squared_dev) {
+        const float d = __fsub_rn(v, center);
+        v = __fmul_rn(d, d);
+      }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -71,9 +75,21 @@ __device__ __forceinline__ float warp_sum_l8(const float* __restrict__ x, int G,
   for (int i = n8; i < G; ++i) {
     float v = x[i];
     if (weighted) v = __fmul_rn(v, (float)w[i]);
+    if (squared_dev) {
+      const float d = __fsub_rn(v, center);
+      v = __fmul_rn(d, d);
+    }
     s = __fadd_rn(s, v);
   }
   return s;
+}
+
+// GRPO's std-normalised advantage (NOT in the reference's registry, which is Dr.GRPO = mean only; north_star names "mean/std"):
+//   a_i = (r_i - mean) / (std + PRL_ADV_GRPO_EPS),  std = sqrt(sum (r_i - mean)^2 / (G - 1))   (unbiased, as torch.std)
+// with both sums in the same L8 order as the mean.  G == 1 gives nan, as torch.std of one element does.
+__device__ __forceinline__ float grpo_scale(float ssq, int G) {
+  const float std = __fsqrt_rn(__fdiv_rn(ssq, (float)(G - 1)));
+  return __fadd_rn(std, PRL_ADV_GRPO_EPS);
 }
 
 // G <= 32: floor(32 / G) groups per warp, one rollout per lane, fully coalesced loads and stores.  Every lane of a
@@ -143,12 +159,25 @@ __global__ void __launch_bounds__(256) advantages_small_group_kernel(const float
 #pragma unroll
       for (int u = 0; u < ADV_U; ++u) den[u] = (float)G;
     }
+    float scale[ADV_U];
+    if (kind == PRL_ADV_GRPO) {
+      float sq[ADV_U], ssq[ADV_U];
+#pragma unroll
+      for (int u = 0; u < ADV_U; ++u) {
+        const float d = __fsub_rn(r[u], __fdiv_rn(num[u], den[u]));
+        sq[u] = __fmul_rn(d, d);
+      }
+      subwarp_sum_l8(sq, G, base, ssq);
+#pragma unroll
+      for (int u = 0; u < ADV_U; ++u) scale[u] = grpo_scale(ssq[u], G);
+    }
 #pragma unroll
     for (int u = 0; u < ADV_U; ++u) {
       if (active[u]) {
         float a = __fsub_rn(r[u], __fdiv_rn(num[u], den[u]));
         if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = max_nan(a, 0.f);
         if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
+        if (kind == PRL_ADV_GRPO) a = __fdiv_rn(a, scale[u]);
         out[idx[u]] = a;
       }
     }
@@ -215,14 +244,25 @@ __global__ void __launch_bounds__(256) advantages_vec8_kernel(const float* __res
     } else {
       num = sum_l8(x);
     }
+    const float mean = __fdiv_rn(num, den);
+    float scale = 1.f;
+    if (kind == PRL_ADV_GRPO) {  // every lane takes part in the shuffles of the second sum
+      float sq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = __fsub_rn(x[j], mean);
+        sq[j] = __fmul_rn(d, d);
+      }
+      scale = grpo_scale(sum_l8(sq), G);
+    }
     if (active) {
-      const float mean = __fdiv_rn(num, den);
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float a = __fsub_rn(x[j], mean);
         if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = max_nan(a, 0.f);
         if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
+        if (kind == PRL_ADV_GRPO) a = __fdiv_rn(a, scale);
         o[j] = a;
       }
       *reinterpret_cast<float4*>(out + e0) = make_float4(o[0], o[1], o[2], o[3]);
@@ -269,10 +309,13 @@ __global__ void __launch_bounds__(256) advantages_kernel(const float* __restrict
     } else {
       base = __fdiv_rn(warp_sum_l8(r, G, lane, false, nullptr), (float)G);
     }
+    float scale = 1.f;
+    if (kind == PRL_ADV_GRPO) scale = grpo_scale(warp_sum_l8(r, G, lane, false, nullptr, true, base), G);
     for (int i = lane; i < G; i += 32) {
       float a = __fsub_rn(r[i], base);
       if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = max_nan(a, 0.f);
       if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
+      if (kind == PRL_ADV_GRPO) a = __fdiv_rn(a, scale);
       out[g * G + i] = a;
     }
     if (token_out != nullptr) {
@@ -282,6 +325,7 @@ __global__ void __launch_bounds__(256) advantages_kernel(const float* __restrict
         float a = __fsub_rn(r[i], base);
         if (kind == PRL_ADV_DRGRPO_NEGCLIPPED) a = max_nan(a, 0.f);
         if (kind == PRL_ADV_RLOO) a = __fdiv_rn(__fmul_rn(a, (float)G), (float)(G - 1));
+        if (kind == PRL_ADV_GRPO) a = __fdiv_rn(a, scale);
         const int64_t t0 = tok_offsets[idx], t1 = tok_offsets[idx + 1];
         for (int64_t t = t0 + lane; t < t1; t += 32) token_out[t] = a;
       }
@@ -823,7 +867,7 @@ int prl_advantages_f32(const float* rewards, const int64_t* lengths, int64_t n, 
                        const int64_t* tok_offsets, float* token_out, void* stream) {
   PRL_REQUIRE(n >= 0 && group >= 1, PRL_ERR_BAD_ARG, "advantages: n >= 0 and group >= 1 required");
   PRL_REQUIRE(n % group == 0, PRL_ERR_BAD_ARG, "advantages: len(rewards) % samples_per_problem != 0");
-  PRL_REQUIRE(kind >= 0 && kind <= 3, PRL_ERR_BAD_ARG, "advantages: unknown advantage kind");
+  PRL_REQUIRE(kind >= 0 && kind <= 4, PRL_ERR_BAD_ARG, "advantages: unknown advantage kind");
   if (n == 0) return PRL_OK;
   PRL_REQUIRE(rewards && out, PRL_ERR_BAD_ARG, "advantages: null pointer");
   PRL_REQUIRE(kind != PRL_ADV_OPO || lengths, PRL_ERR_BAD_ARG, "advantages: opo needs completion lengths");

@@ -348,14 +348,15 @@ class FusedLMHead(nn.Module):
     """Drop-in replacement MODULE for `model.lm_head` (SURVEY §7 "FSDP integration"): it owns the same
     `weight` Parameter, so FSDP2's `[lm_head, norm]` group hooks (model.py:126-131) keep firing, and its
     `forward(hidden)` returns a `[..., T, 2]` tensor (logprob, entropy) where the reference returns
-    logits.  Call `set_context(input_ids, temperature)` right before the model forward."""
+    logits.  Call `set_context(input_ids, temperature)` right before the model forward; with the micro-batch's `loss_mask` as
+    third argument the backward skips the masked (prompt / environment) positions, whose gradient is zero anyway."""
 
     def __init__(self, weight: nn.Parameter, main_grad: torch.Tensor | None = None, save_logits: bool | None = None):
         super().__init__()
         self.weight = weight
         self.main_grad = main_grad
         self.save_logits = save_logits  # None: recompute unless PRL_SAVE_LOGITS says otherwise (saved_logits_policy)
-        self._ctx: tuple[torch.Tensor, float] | None = None
+        self._ctx: tuple | None = None
 
     @classmethod
     def from_linear(cls, linear: nn.Linear) -> "FusedLMHead":
@@ -363,14 +364,14 @@ class FusedLMHead(nn.Module):
             raise ValueError("lm_head with bias is not supported (Qwen3/Llama heads are bias-free)")
         return cls(linear.weight)
 
-    def set_context(self, input_ids: torch.Tensor, temperature: float) -> None:
-        self._ctx = (input_ids, float(temperature))
+    def set_context(self, input_ids: torch.Tensor, temperature: float, loss_mask: torch.Tensor | None = None) -> None:
+        self._ctx = (input_ids, float(temperature), loss_mask)
 
     def forward(self, hidden: torch.Tensor) -> torch.Tensor:
         if self._ctx is None:
             raise RuntimeError("FusedLMHead.set_context(input_ids, temperature) must be called before forward")
-        ids, temp = self._ctx
+        ids, temp, mask = self._ctx
         self._ctx = None
-        logp, ent = fused_lm_head_logprobs_entropy(hidden, self.weight, ids, temp, main_grad=self.main_grad,
+        logp, ent = fused_lm_head_logprobs_entropy(hidden, self.weight, ids, temp, main_grad=self.main_grad, loss_mask=mask,
                                                    save_logits=self.save_logits)
         return torch.stack([logp, ent], dim=-1)

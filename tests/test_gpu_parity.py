@@ -96,6 +96,28 @@ def test_advantages_large_and_broadcast(P):
     np.testing.assert_array_equal(tok.cpu().numpy(), np.repeat(adv.cpu().numpy(), ln))
 
 
+def test_advantages_grpo_std_extension(P):
+    """the std-normalised extension (not in the reference): bit-exact against the oracle's definition through all three
+    kernels (8-rollouts-per-lane, small groups, one warp per group), close to torch's expression, per-token broadcast included"""
+    rng = np.random.default_rng(11)
+    for grp, n in [(8, 8 * 300), (16, 16 * 1000), (24, 24 * 50), (32, 32 * 64), (5, 5 * 77), (12, 12 * 40), (40, 40 * 30), (2, 2 * 9)]:
+        r = rng.standard_normal(n).astype(np.float32)
+        ln = rng.integers(1, 100, n)
+        got = P.compute_advantages_tensor(cu(r), cu(ln), grp, "grpo").cpu().numpy()
+        np.testing.assert_array_equal(got, oracle.advantages(r, ln, grp, "grpo"))
+        t = torch.from_numpy(r).view(-1, grp)
+        want = ((t - t.mean(1, keepdim=True)) / (t.std(1, keepdim=True) + 1e-6)).reshape(-1).numpy()
+        np.testing.assert_allclose(got, want, rtol=5e-6, atol=2e-6)
+    n, grp = 48, 16
+    r = rng.standard_normal(n).astype(np.float32)
+    ln = rng.integers(1, 30, n)
+    offs = np.concatenate([[0], np.cumsum(ln)])
+    adv, tok = P.compute_advantages_tensor(cu(r), cu(ln), grp, "grpo", token_offsets=cu(offs))
+    np.testing.assert_array_equal(adv.cpu().numpy(), oracle.advantages(r, ln, grp, "grpo"))
+    np.testing.assert_array_equal(tok.cpu().numpy(), np.repeat(adv.cpu().numpy(), ln))
+    assert P.compute_advantages([1.0, 1.0, 1.0, 1.0], [1, 2, 3, 4], 4, "grpo") == [0.0, 0.0, 0.0, 0.0]
+
+
 def test_advantages_errors(P):
     with pytest.raises(AssertionError):
         P.compute_advantages([1.0, 2.0, 3.0], [1, 1, 1], 2, "drgrpo")
@@ -543,6 +565,17 @@ def test_fused_lm_head_module_in_hf_qwen3(P):
     assert ((ge - ref_ge).norm() / ref_ge.norm()).item() < 2e-2  # through the whole (bf16) transformer body
     with pytest.raises(RuntimeError):
         model(input_ids=ids, position_ids=pos)  # context must be set before every forward
+    # with the micro-batch's loss_mask the backward skips masked positions: same gradients for a loss that ignores them
+    mask = torch.rand(1, T, device="cuda") < 0.6
+    grads = []
+    for m in (None, mask):
+        model.zero_grad()
+        head.set_context(ids, tau, m)
+        lp_m = model(input_ids=ids, position_ids=pos).logits[..., 0]
+        (lp_m * mask * 0.01).sum().backward()
+        grads.append((model.lm_head.weight.grad.float().clone(), model.model.embed_tokens.weight.grad.float().clone()))
+    assert ((grads[1][0] - grads[0][0]).norm() / grads[0][0].norm()).item() < 5e-3
+    assert ((grads[1][1] - grads[0][1]).norm() / grads[0][1].norm()).item() < 2e-2
 
 
 def test_next_rows_sft_cross_entropy_and_logprob_recompute(P):

@@ -206,6 +206,24 @@ def test_first_fit_decreasing_matches_reference_bins():
     assert got == want
 
 
+def test_grpo_std_extension_matches_its_torch_definition():
+    """"grpo" is NOT in the reference (its registry is Dr.GRPO: mean only); the product offers it because north_star names
+    "mean/std".  Its definition -- (r - mean) / (std + 1e-6), unbiased std -- is pinned here against plain torch."""
+    import torch
+
+    assert "grpo" not in oracle.ADVANTAGE_KINDS and oracle.EXTENSION_ADVANTAGE_KINDS == ("grpo",)
+    rng = np.random.default_rng(0)
+    for G in (2, 5, 8, 16, 24, 32, 40):
+        r = rng.standard_normal(G * 9).astype(np.float32)
+        t = torch.from_numpy(r).view(-1, G)
+        want = ((t - t.mean(1, keepdim=True)) / (t.std(1, keepdim=True) + 1e-6)).reshape(-1).numpy()
+        np.testing.assert_allclose(oracle.advantages(r, np.ones(len(r), dtype=np.int64), G, "grpo"), want, rtol=2e-6, atol=1e-6)
+    np.testing.assert_array_equal(oracle.advantages([1.0] * 4, [1] * 4, 4, "grpo"), np.zeros(4, dtype=np.float32))  # zero variance
+    assert np.isnan(oracle.advantages([3.0], [1], 1, "grpo")).all()  # torch.std of one element is nan
+    with pytest.raises(KeyError):
+        oracle.advantages([1.0, 2.0], [1, 1], 2, "gae")
+
+
 # ----------------------------------------------------------------- same-logits checker (tests/same_logits.py)
 def test_torch_checker_matches_numpy_oracle():
     """the torch fp64 restatement used for device-side checks at the BASELINE shapes == the numpy oracle"""
