@@ -627,6 +627,13 @@ def run_b200(args):
         if k in head:
             result[k] = head[k]
     result["modes"] = {("saved_logits" if m == "saved" else m): recs[m] for m in modes}
+    if dist is not None and not args.no_vocab_check:
+        import prime_rl_cse_b200 as P_
+
+        try:
+            result["vocab_sharded_check"] = vocab_sharded_check(P_, dist, rn, world, rank, dev)
+        except Exception as e:  # noqa: BLE001  a context record: never fatal for the headline (every rank takes the same path)
+            result["vocab_sharded_check"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     del rn
     torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_regimes and args.workload == "qwen3-8b-hendrycks":
@@ -683,37 +690,7 @@ def run_vocab_sharded(args, rank, world, dev, dist):
     copy_stream = torch.cuda.Stream(device=dev)
     loss_host = torch.empty(n_mb, dtype=torch.float32).pin_memory()
 
-    # ---- parity: one round from a zeroed accumulator against the UNSHARDED fused path on this GPU (same kernels, full W)
-    out = head.micro_step(mbs[0]["hidden"], mbs[0], cfg, T)
-    gathered = head.gather_inputs(mbs[0]["hidden"], mbs[0]["input_ids"])
-    torch.cuda.current_stream().wait_event(gathered["ready"])
-    lp_u, ent_u, lse_u, _ = P.lm_head_forward_raw(mbs[0]["hidden"][0], W_full, mbs[0]["input_ids"][0], 1.0)
-    from prime_rl_cse_b200.loss import _loss_packed_raw
-
-    cu = torch.tensor([0] + list(torch.tensor(seg).cumsum(0)), dtype=torch.int32, device=dev)
-    _, _, _, _, g_u = _loss_packed_raw(lp_u, mbs[0]["logprobs"][0], mbs[0]["advantages"][0], mbs[0]["loss_mask"][0].view(torch.uint8), cu, nseg, 0,
-                                       False, 8.0, T)
-    dh_u, _ = P.lm_head_backward_raw(mbs[0]["hidden"][0], W_full, mbs[0]["input_ids"][0], lse_u, g_u, 1.0, want_dweight=False)
-    # unsharded d_W needs every rank's tokens: gather (lse, dlogp) of all ranks, run the unsharded backward over world*T tokens
-    pair = torch.stack([lse_u, g_u], dim=1).contiguous()
-    pair[0, 1] = 0.0
-    pair_all = torch.empty(world * T, 2, device=dev)
-    dist.all_gather_into_tensor(pair_all, pair)
-    dw_u = torch.zeros(V, H, dtype=torch.float32, device=dev)
-    fix = pair_all[:, 1].contiguous()
-    P.lm_head_backward_raw(gathered["h_all"], W_full, gathered["i_all"], pair_all[:, 0].contiguous(), fix, 1.0, want_dhidden=False, dweight=dw_u,
-                           dweight_accumulate=True)
-
-    def rel(a, b):
-        return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
-
-    par = torch.tensor([float((out["logprobs"] - lp_u).abs().max()), float((out["entropy"] - ent_u).abs().max()), rel(out["d_hidden"], dh_u),
-                        rel(main_grad, dw_u[v0:v1])], dtype=torch.float64, device=dev)
-    dist.all_reduce(par, op=dist.ReduceOp.MAX)
-    parity = {"max_abs_dlogp": float(par[0]), "max_abs_dentropy": float(par[1]), "rel_l2_d_hidden": float(par[2]), "rel_l2_d_weight_shard": float(par[3]),
-              "ok": bool(par[0] < 1e-3 and par[1] < 1e-3 and par[2] < 1e-2 and par[3] < 1e-2),
-              "what": f"{world}-rank vocab-sharded round vs the unsharded fused path on each rank's own tokens (max over ranks)"}
-    del dw_u, dh_u, pair_all, gathered, out
+    parity = vocab_sharded_parity(P, dist, head, mbs[0], W_full, seg, world, dev)
     main_grad.zero_()
     torch.cuda.empty_cache()
 
@@ -801,6 +778,85 @@ def run_vocab_sharded(args, rank, world, dev, dist):
                      "achieved": alg * 8.0 / 6.0, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": alg * 8.0 / 6.0 / peaks["sustained"],
                      "traffic": None, "note": "executed flops (8 H V per token) / step time, exchanges included"},
     }
+
+
+def vocab_sharded_parity(P, dist, head, mb, W_full, seg, world, dev):
+    """One round of the vocab-sharded head from a zeroed d_W accumulator against the UNSHARDED fused path on this GPU (same
+    kernels, full W): every rank checks its own tokens' log-probs / entropy / d_hidden and its d_W shard; max over ranks."""
+    from prime_rl_cse_b200.loss import _loss_packed_raw
+
+    T, V, H = mb["input_ids"].shape[1], W_full.shape[0], W_full.shape[1]
+    tau = float(mb["temperature"])
+    head.main_grad.zero_()
+    cfg = P.LossConfig(ratio_type="token", ratio_length_norm=False, clip_ratio=8.0)
+    out = head.micro_step(mb["hidden"], mb, cfg, T)
+    gathered = head.gather_inputs(mb["hidden"], mb["input_ids"])
+    torch.cuda.current_stream().wait_event(gathered["ready"])
+    lp_u, ent_u, lse_u, _ = P.lm_head_forward_raw(mb["hidden"][0], W_full, mb["input_ids"][0], 1.0 / tau)
+    cu = torch.tensor([0] + list(torch.tensor(seg).cumsum(0)), dtype=torch.int32, device=dev)
+    _, _, _, _, g_u = _loss_packed_raw(lp_u, mb["logprobs"][0], mb["advantages"][0], mb["loss_mask"][0].view(torch.uint8), cu, len(seg), 0,
+                                       False, 8.0, T)
+    dh_u, _ = P.lm_head_backward_raw(mb["hidden"][0], W_full, mb["input_ids"][0], lse_u, g_u, 1.0 / tau, want_dweight=False)
+    # unsharded d_W needs every rank's tokens: gather (lse, dlogp) of all ranks, run the unsharded backward over world*T tokens
+    pair = torch.stack([lse_u, g_u], dim=1).contiguous()
+    pair[0, 1] = 0.0
+    pair_all = torch.empty(world * T, 2, device=dev)
+    dist.all_gather_into_tensor(pair_all, pair)
+    dw_u = torch.zeros(V, H, dtype=torch.float32, device=dev)
+    P.lm_head_backward_raw(gathered["h_all"], W_full, gathered["i_all"], pair_all[:, 0].contiguous(), pair_all[:, 1].contiguous(), 1.0 / tau,
+                           want_dhidden=False, dweight=dw_u, dweight_accumulate=True)
+
+    def rel(a, b):
+        return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30))
+
+    par = torch.tensor([float((out["logprobs"] - lp_u).abs().max()), float((out["entropy"] - ent_u).abs().max()), rel(out["d_hidden"], dh_u),
+                        rel(head.main_grad, dw_u[head.v0:head.v1])], dtype=torch.float64, device=dev)
+    dist.all_reduce(par, op=dist.ReduceOp.MAX)
+    return {"max_abs_dlogp": float(par[0]), "max_abs_dentropy": float(par[1]), "rel_l2_d_hidden": float(par[2]), "rel_l2_d_weight_shard": float(par[3]),
+            "ok": bool(par[0] < 1e-3 and par[1] < 1e-3 and par[2] < 1e-2 and par[3] < 1e-2),
+            "what": f"{world}-rank vocab-sharded round vs the unsharded fused path on each rank's own tokens (max over ranks)"}
+
+
+def vocab_sharded_check(P, dist, rn, world, rank, dev, T=2048):
+    """Every N > 1 line of the default (token-sharded) workload also carries a SMALL vocab-sharded round at the same H and V
+    (T tokens per rank), so that config 4's exchange steps and the fused epilogue reduce-scatter are in the driver's own
+    multi-GPU record: parity against the unsharded path and the round time, NCCL and fused."""
+    from prime_rl_cse_b200.parallel import VocabShardedLMHead
+
+    W_full = rn.Wd.clone()
+    dist.broadcast(W_full, src=0)  # the token-sharded workload seeds W per rank; the vocab-sharded head needs ONE W
+    H, V = W_full.shape[1], W_full.shape[0]
+    v0, v1 = P.vocab_shard_bounds(V, world, rank)
+    g = torch.Generator(device=dev).manual_seed(777 + rank)
+    seg = [T // 4] * 4
+    hidden = torch.randn(T, H, generator=g, device=dev).to(torch.bfloat16)
+    ids = torch.randint(0, V, (T,), generator=g, device=dev)
+    lp, _, _, _ = P.lm_head_forward_raw(hidden, W_full, ids, 1.0)
+    mb = dict(hidden=hidden.unsqueeze(0), input_ids=ids.unsqueeze(0), position_ids=torch.cat([torch.arange(n) for n in seg]).unsqueeze(0).to(dev),
+              advantages=torch.cat([torch.full((n,), a) for n, a in zip(seg, (0.5, -0.25, 1.0, -0.5))]).unsqueeze(0).to(dev),
+              logprobs=(lp + 0.15 * torch.randn(T, generator=g, device=dev)).unsqueeze(0), loss_mask=torch.ones(1, T, dtype=torch.bool, device=dev),
+              temperature=1.0)
+    out = {}
+    for fused in (False, True):
+        head = VocabShardedLMHead(W_full[v0:v1].clone(), V, main_grad=torch.zeros(v1 - v0, H, dtype=torch.float32, device=dev), fused_rs=fused)
+        rec = vocab_sharded_parity(P, dist, head, mb, W_full, seg, world, dev)
+        cfg = P.LossConfig()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            head.micro_step(mb["hidden"], mb, cfg, T)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rec["ms_per_round"] = float(t[0])
+        rec["tokens_per_rank_per_round"] = T
+        out["fused_epilogue_reduce_scatter" if fused else "nccl_reduce_scatter"] = rec
+        head.close()
+        del head
+    return out
 
 
 def torch_gpu_reference(wl, dev, T_s=4096, reps=3):
@@ -955,6 +1011,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
     ap.add_argument("--no-regimes", action="store_true", help="skip the short runs of the other measurement regimes (N=1 only)")
+    ap.add_argument("--no-vocab-check", action="store_true", help="N>1: skip the small vocab-sharded round (config 4 parity + round time)")
     ap.add_argument("--forward-skips-masked", action="store_true", help="e2e arm: also restrict the forward to unmasked positions")
     ap.add_argument("--prompt-frac", type=float, default=0.0, help="mask the first fraction of every rollout (default 0 = all-ones mask)")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the torch-on-GPU reference-chain timing")

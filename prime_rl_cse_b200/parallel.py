@@ -311,9 +311,19 @@ class VocabShardedLMHead:
         import ctypes
 
         lib = _lib.load()
-        # the accumulator is a cudaMalloc allocation of its own (exportable as a whole), wrapped as a torch tensor
+        # the accumulator is a cudaMalloc allocation of its own (exportable as a whole), wrapped as a torch tensor.  Every step
+        # that can fail on one rank only is followed by an agreement (all-reduce of a flag), so that ALL ranks raise together
+        # instead of leaving the others inside a collective.
         base, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-        _lib.check(lib.prl_ipc_alloc(T * self.H * 4, ctypes.byref(base), handle), "prl_ipc_alloc")
+        err = None
+        try:
+            _lib.check(lib.prl_ipc_alloc(T * self.H * 4, ctypes.byref(base), handle), "prl_ipc_alloc")
+        except Exception as e:  # noqa: BLE001
+            err = e
+        if not self._agree(err is None, dev, None):
+            if base.value:
+                lib.prl_ipc_free(base)
+            raise RuntimeError(f"fused reduce-scatter unavailable: prl_ipc_alloc failed on a rank ({err}); use fused_rs=False")
 
         class _Buf:  # zero-copy view for torch (CUDA array interface v2)
             __cuda_array_interface__ = {"shape": (T, self.H), "typestr": "<f4", "data": (int(base.value), False), "version": 2}
@@ -323,18 +333,37 @@ class VocabShardedLMHead:
         infos = [None] * self.world
         dist.all_gather_object(infos, bytes(handle.raw), group=self.group)
         ptrs, opened = [], []
-        for j, h in enumerate(infos):
-            if j == self.rank:
-                ptrs.append(int(base.value))
-                continue
-            peer = ctypes.c_void_p()
-            _lib.check(lib.prl_ipc_open(ctypes.c_char_p(h), ctypes.byref(peer)), "prl_ipc_open")
-            opened.append(peer.value)
-            ptrs.append(peer.value)
+        try:
+            for j, h in enumerate(infos):
+                if j == self.rank:
+                    ptrs.append(int(base.value))
+                    continue
+                peer = ctypes.c_void_p()
+                _lib.check(lib.prl_ipc_open(ctypes.c_char_p(h), ctypes.byref(peer)), "prl_ipc_open")
+                opened.append(peer.value)
+                ptrs.append(peer.value)
+        except Exception as e:  # noqa: BLE001
+            err = e
+        if not self._agree(err is None, dev, None):
+            for p_ in opened:
+                lib.prl_ipc_close(p_)
+            dist.barrier(group=self.group)
+            del acc
+            lib.prl_ipc_free(base)
+            raise RuntimeError(f"fused reduce-scatter unavailable: mapping a peer's accumulator failed on a rank ({err}); use fused_rs=False")
         arr = (ctypes.c_void_p * self.world)(*ptrs)
         self._sym = dict(T=T, acc=acc, ptrs=arr, opened=opened, own=int(base.value), flag=torch.zeros(1, dtype=torch.float32, device=dev))
         dist.barrier(group=self.group)  # every rank has mapped every buffer before anyone uses them
         return acc
+
+    def _agree(self, ok: bool, dev, message):
+        """True iff `ok` on every rank; with a `message`, raises it on ALL ranks otherwise"""
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        good = bool(flag.item())
+        if not good and message is not None:
+            raise RuntimeError(message)
+        return good
 
     def _backward_fused(self, gathered, inv, lse_all, g_all, vchunk, ws):
         lib = _lib.load()
