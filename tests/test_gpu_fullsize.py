@@ -169,6 +169,43 @@ def test_vocab_sharded_backward_emulated_on_one_gpu(P, mode):
     assert ((dh_sum - dh_full).norm() / dh_full.norm()).item() < 1e-3
 
 
+@pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
+def test_masked_micro_step_full_size(P, save):
+    """Qwen3-8B shape, 16384 tokens, prompt + multi-turn masks (52 % of the positions masked): the partitioned backward (rows.py
+    kernels) gives the same gradients as the one that visits every row, exact zeros at masked rows, the same log-probs / loss."""
+    T, H, V, tau = 16384, 4096, 151936, 1.0
+    hidden, W, ids = make(T, H, V, seed=21, peaked=False)
+    seg = [4096] * 4
+    mask = torch.ones(T, dtype=torch.bool, device="cuda")
+    o = 0
+    for n in seg:
+        p = n // 4
+        mask[o : o + p] = False  # prompt
+        k = o + p + 256
+        while k < o + n:  # environment turns
+            mask[k : min(k + 128, o + n)] = False
+            k += 512
+        o += n
+    mb = dict(input_ids=ids.unsqueeze(0), position_ids=torch.cat([torch.arange(n) for n in seg]).unsqueeze(0).cuda(),
+              advantages=torch.cat([torch.full((n,), a) for n, a in zip(seg, (0.5, -0.25, 1.0, -0.75))]).unsqueeze(0).cuda(),
+              logprobs=torch.zeros(1, T, device="cuda"), loss_mask=mask.unsqueeze(0), temperature=tau)
+    with torch.no_grad():
+        lp0, _ = P.fused_lm_head_logprobs_entropy(hidden.unsqueeze(0), W, ids.unsqueeze(0), tau)
+    mb["logprobs"] = (lp0 + 0.15 * torch.randn(1, T, device="cuda")) * mask
+    res = []
+    for skip in (False, True):
+        h = hidden.clone().requires_grad_(True)
+        w = W.clone().requires_grad_(True)
+        out = P.rl_micro_step(h.unsqueeze(0), w, mb, P.LossConfig(), int(mask.sum()), skip_masked=skip, save_logits=save)
+        res.append((out, h.grad, w.grad))
+    (o0, dh0, dw0), (o1, dh1, dw1) = res
+    assert torch.equal(o0["logprobs"], o1["logprobs"]) and torch.equal(o0["entropy"], o1["entropy"]) and o0["loss"].item() == o1["loss"].item()
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()  # noqa: E731
+    assert rel(dh1, dh0) < 2e-3 and rel(dw1, dw0) < 2e-3
+    masked_rows = (~mask[1:]).nonzero().reshape(-1)
+    assert float(dh1[masked_rows].abs().max()) == 0.0 and float(dh1[-1].abs().max()) == 0.0
+
+
 def test_sequence_mode_long_context_micro_step(P):
     """BASELINE configs[4]: one 32k-token sequence, sequence-level ratio with length normalisation."""
     T, H, V = 32768, 1024, 151936
