@@ -347,6 +347,10 @@ class Runner:
                 out = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in src.items()}
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
+            # what a loader knows from the host copy (rollout_io.upload_micro_batches does the same): the micro-step then needs
+            # no device-to-host synchronisation for the segment lengths (train.py:291) or the active-position count
+            out["response_lengths"] = P.response_lengths_host(src["position_ids"])
+            out["n_active"] = int(src["loss_mask"].reshape(-1)[1:].sum())
             return out, ev
 
         nxt = upload(0)

@@ -311,6 +311,12 @@ int prl_get_knob(const char* name, int64_t* value);
  * items; may be NULL); dims[8] = (m_tiles, n_tiles, k_blocks, num_items, workers, k_splits, n_splits, rows per m-tile). */
 int prl_debug_schedule(int32_t kind, int64_t M, int64_t N, int64_t K, int32_t* items, int64_t capacity, int32_t* dims);
 
+/* Test hook (host only): the tile order of the fused reduce-scatter d_hidden GEMM (prl_lmhead_bwd_scatter) for rank `self_index`
+ * of `n_peers`, M = n_peers * rows_per_peer output rows.  items as in prl_debug_schedule; dims[8] = (m_tiles, n_tiles, k_blocks,
+ * num_items, workers, m_rot = m-tile rotation, rows_per_peer, rows per m-tile). */
+int prl_debug_schedule_scatter(int64_t M, int64_t N, int64_t K, int32_t n_peers, int32_t self_index, int32_t* items,
+                               int64_t capacity, int32_t* dims);
+
 /* number of kernel launches issued by this library on this host thread since the last reset
  * (bench.py's `gpu_launches`) */
 int64_t prl_launch_count(int32_t reset);

@@ -21,7 +21,7 @@ from .loss import compute_entropy, compute_loss, selective_log_softmax, shift_lo
 from .extras import fused_linear_cross_entropy, recompute_logprobs
 from .micro_step import rl_micro_step
 from .rollout_io import DataLoader, FakeDataLoader, save_step, upload_micro_batches
-from .segments import get_response_lengths, segments_from_position_ids
+from .segments import get_response_lengths, response_lengths_host, segments_from_position_ids
 from .stats import TensorStats
 from .parallel import (VocabShardedLMHead, exchange_partials, local_loss_scale, shard_micro_batches,
                        vocab_parallel_lm_head_logprobs_entropy, vocab_shard_bounds)
@@ -34,5 +34,5 @@ __all__ = [
     "shifted_logprobs_entropy", "rl_micro_step", "get_response_lengths", "segments_from_position_ids",
     "fused_linear_cross_entropy", "recompute_logprobs", "TensorStats", "prepare_batch", "first_fit_decreasing",
     "DataLoader", "FakeDataLoader", "save_step", "upload_micro_batches", "exchange_partials", "local_loss_scale", "shard_micro_batches", "vocab_parallel_lm_head_logprobs_entropy", "vocab_shard_bounds",
-    "VocabShardedLMHead", "partition_positions",
+    "VocabShardedLMHead", "partition_positions", "response_lengths_host",
 ]

@@ -88,6 +88,7 @@ _SIGNATURES = {
     "prl_set_knob": (c_int32, [ctypes.c_char_p, c_int64]),
     "prl_get_knob": (c_int32, [ctypes.c_char_p, c_void_p]),
     "prl_debug_schedule": (c_int32, [c_int32, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "prl_debug_schedule_scatter": (c_int32, [c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "prl_gemm_bf16_f32": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
 }
 

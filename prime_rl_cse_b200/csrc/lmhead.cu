@@ -551,6 +551,15 @@ struct PeerScatter {
   int32_t self;           // this rank's index (sets the m-tile rotation)
 };
 
+// Fused reduce-scatter: rows [j * rows_per_peer, ..) of the output belong to peer j; rank `self` starts at the tiles of the NEXT
+// rank's tokens, so that at any time the ranks (which walk their tile lists at the same pace) write to different owners.
+static void set_scatter_rotation(GemmParams& p, int n_peers, int64_t rows_per_peer, int self) {
+  p.n_peers = n_peers;
+  p.peer_rows = (int32_t)rows_per_peer;
+  const int64_t rows_per_tile = (int64_t)BLOCK_M * cta_group() * msub(EPI_STORE);
+  p.m_rot = (int32_t)(((((int64_t)self + 1) % n_peers) * rows_per_peer / rows_per_tile) % p.m_tiles);
+}
+
 // d_hidden and d_weight GEMMs over one block of dlogits: dz[T][ldz] holds vocab columns [c0, c0 + vce) of this shard
 static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __nv_bfloat16* dz, int64_t vc, int64_t c0, int64_t vce,
                             int64_t T, int32_t H, void* d_hidden, int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype,
@@ -573,15 +582,11 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
     p.epi.n_cols = H;
     p.epi.ldc = H;
     p.epi.flags = ST_STORE_F32 | ST_LOAD_F32 | ST_TMA;
-    p.n_peers = peers->n;
-    p.peer_rows = (int32_t)peers->rows_per_peer;
     for (int j = 0; j < peers->n; ++j) {
       rc = make_output_map(&p.tma_c_peer[j], peers->ptrs[j], peers->rows_per_peer, H, H, true);
       if (rc) return rc;
     }
-    // start at the tiles of the NEXT rank's tokens: at any time the ranks write to different owners
-    const int64_t rows_per_tile = (int64_t)BLOCK_M * cta_group() * msub(EPI_STORE);
-    p.m_rot = (int32_t)((((int64_t)(peers->self + 1) % peers->n) * peers->rows_per_peer) / rows_per_tile) % p.m_tiles;
+    set_scatter_rotation(p, peers->n, peers->rows_per_peer, peers->self);
     set_hints(p, "DH", 0, 0, 0);
     rc = launch_gemm<false, true, EPI_STORE>(p, st, "lmhead_bwd_dhidden_rs_kernel");
     if (rc) return rc;
@@ -860,6 +865,27 @@ int prl_debug_schedule(int32_t kind, int64_t M, int64_t N, int64_t K, int32_t* i
   }
   dims[0] = p.m_tiles, dims[1] = p.n_tiles, dims[2] = p.k_blocks, dims[3] = p.num_items;
   dims[4] = workers(), dims[5] = p.k_splits, dims[6] = p.n_splits, dims[7] = BLOCK_M * cta_group() * msub(epi);
+  if (items) {
+    for (int i = 0; i < p.num_items && i < capacity; ++i) {
+      const Item it = decode_item(p, i);
+      int32_t* o = items + 6 * (int64_t)i;
+      o[0] = it.m_tile, o[1] = it.n_begin, o[2] = it.n_count, o[3] = it.k_begin, o[4] = it.k_count, o[5] = it.split;
+    }
+  }
+  return PRL_OK;
+}
+
+int prl_debug_schedule_scatter(int64_t M, int64_t N, int64_t K, int32_t n_peers, int32_t self_index, int32_t* items, int64_t capacity,
+                               int32_t* dims) {
+  PRL_REQUIRE(M >= 1 && N >= 1 && K >= 1 && dims && n_peers >= 1 && n_peers <= 8 && self_index >= 0 && self_index < n_peers && M % n_peers == 0,
+              PRL_ERR_BAD_ARG, "debug_schedule_scatter: bad arguments");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  set_tiling(p, M, N, K, EPI_STORE);
+  schedule_tiles(p, 8);
+  set_scatter_rotation(p, n_peers, M / n_peers, self_index);
+  dims[0] = p.m_tiles, dims[1] = p.n_tiles, dims[2] = p.k_blocks, dims[3] = p.num_items;
+  dims[4] = workers(), dims[5] = p.m_rot, dims[6] = p.peer_rows, dims[7] = BLOCK_M * cta_group() * msub(EPI_STORE);
   if (items) {
     for (int i = 0; i < p.num_items && i < capacity; ++i) {
       const Item it = decode_item(p, i);

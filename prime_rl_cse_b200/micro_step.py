@@ -36,7 +36,9 @@ def rl_micro_step(
     partitioned "active first" on the device, rows.py); a no-op when every token is unmasked.  `forward_skips_masked` (opt-in) also restricts the FORWARD to the
     unmasked positions: log-probs / entropy come back as 0 at masked positions (the reference computes values there that
     nothing reads: the loss multiplies by the mask and the trainer logs `[loss_mask]` slices, train.py:313-333).
-    `save_logits`: see `fused_lm_head_logprobs_entropy` (None = keep the bf16 logits for the backward when they fit)."""
+    `save_logits`: see `fused_lm_head_logprobs_entropy` (None / False = recompute backward, True = keep the bf16 logits).
+    Optional micro-batch keys `response_lengths` (list[int]) and `n_active` (int: unmasked positions from position 1 on), as
+    `rollout_io.upload_micro_batches` attaches them from the host copy, remove the step's two device-to-host syncs."""
     input_ids = micro_batch["input_ids"]
     position_ids = micro_batch["position_ids"]
     advantages = micro_batch["advantages"]
@@ -45,10 +47,15 @@ def rl_micro_step(
     temperature = micro_batch["temperature"]
 
     # the partition kernel is queued before the segment lengths are fetched, so the one D2H sync of train.py:291 also
-    # covers its 4-byte active-position count
-    partition = rows.partition_positions(loss_mask, shift=True) if ((skip_masked and backward) or forward_skips_masked) else None
+    # covers its 4-byte active-position count.  A loader that saw the micro-batch on the host (rollout_io.upload_micro_batches)
+    # attaches "response_lengths" and "n_active": then the whole micro-step runs without a device-to-host synchronisation.
+    partition = None
+    if (skip_masked and backward) or forward_skips_masked:
+        partition = rows.partition_positions(loss_mask, shift=True, n_active=micro_batch.get("n_active"))
 
     # train.py:291 -- done first so its single D2H sync happens before the heavy kernels are queued
+    if response_lengths is None:
+        response_lengths = micro_batch.get("response_lengths")
     if response_lengths is None:
         response_lengths = get_response_lengths(position_ids)
 

@@ -19,6 +19,7 @@ from typing import Iterator
 import torch
 
 from .data import MicroBatch, fake_micro_batch
+from .segments import response_lengths_host
 
 _TENSOR_KEYS = ("input_ids", "position_ids", "advantages", "logprobs", "loss_mask")
 
@@ -167,14 +168,21 @@ def upload_micro_batches(batches: list[MicroBatch], device, stream: "torch.cuda.
             dev = host.to(device, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return dev, host, ev, B, S, float(mb["temperature"])
+        # host-side facts the micro-step would otherwise fetch from the device with a synchronisation (train.py:291 does O(T)
+        # of them): segment lengths of the packed row, and how many positions can receive a gradient
+        extra = {}
+        if B == 1:
+            extra = {"response_lengths": response_lengths_host(mb["position_ids"].cpu()), "n_active": int(mb["loss_mask"].reshape(-1)[1:].sum())}
+        return dev, host, ev, B, S, float(mb["temperature"]), extra
 
     nxt = start(batches[0]) if batches else None
     for i in range(len(batches)):
-        dev, host, ev, B, S, temp = nxt
+        dev, host, ev, B, S, temp, extra = nxt
         nxt = start(batches[i + 1]) if i + 1 < len(batches) else None
         cur = torch.cuda.current_stream(device)
         cur.wait_event(ev)
         dev.record_stream(cur)
-        yield unpack_device(dev, B, S, temp)
+        out = unpack_device(dev, B, S, temp)
+        out.update(extra)
+        yield out
         del host  # the pinned buffer may be recycled only after its copy was consumed

@@ -20,8 +20,8 @@ class Partition:
 
     __slots__ = ("order", "slot", "_n_dev", "_n", "T", "shift")
 
-    def __init__(self, order, slot, n_dev, T, shift):
-        self.order, self.slot, self._n_dev, self._n, self.T, self.shift = order, slot, n_dev, None, T, shift
+    def __init__(self, order, slot, n_dev, T, shift, n_active=None):
+        self.order, self.slot, self._n_dev, self._n, self.T, self.shift = order, slot, n_dev, n_active, T, shift
 
     @property
     def n_active(self) -> int:
@@ -35,8 +35,9 @@ class Partition:
         return max(self.T - self.shift, 0)
 
 
-def partition_positions(loss_mask: torch.Tensor, shift: bool = True) -> Partition:
-    """Launches the partition kernel on the current stream and returns without synchronising (`n_active` syncs when read)."""
+def partition_positions(loss_mask: torch.Tensor, shift: bool = True, n_active: int | None = None) -> Partition:
+    """Launches the partition kernel on the current stream and returns without synchronising (`n_active` syncs when read,
+    unless the caller already knows it -- e.g. a data loader that counted `loss_mask[shift:]` on the host copy)."""
     _lib.require_cuda(loss_mask)
     m = loss_mask.detach().reshape(-1)
     if m.dtype == torch.bool:
@@ -52,7 +53,7 @@ def partition_positions(loss_mask: torch.Tensor, shift: bool = True) -> Partitio
     rc = _lib.load().prl_partition_positions(_lib.ptr(m), T, 1 if shift else 0, _lib.ptr(order), _lib.ptr(slot), _lib.ptr(n_dev),
                                              _lib.stream())
     _lib.check(rc, "prl_partition_positions")
-    return Partition(order, slot, n_dev, T, 1 if shift else 0)
+    return Partition(order, slot, n_dev, T, 1 if shift else 0, None if n_active is None else int(n_active))
 
 
 def gather_rows(hidden: torch.Tensor, ids: torch.Tensor | None, part: Partition, n: int):

@@ -33,3 +33,20 @@ def get_response_lengths(position_ids: torch.Tensor) -> list[int]:
         raise RuntimeError("segment table overflow")
     b = cu[: n + 1].cpu().tolist()
     return [b[i + 1] - b[i] for i in range(n)]
+
+
+def response_lengths_host(position_ids: torch.Tensor) -> list[int]:
+    """The same segment lengths from a HOST copy of position_ids (a data loader has one before it uploads the micro-batch):
+    boundary at i iff pos[i] == 0 and pos[i-1] != 0 and i + 1 < T and pos[i+1] == 1 (trainer/utils.py:54-60), vectorised.
+    Lets `rl_micro_step` run without any device-to-host synchronisation (`micro_batch["response_lengths"]`)."""
+    if position_ids.is_cuda:
+        raise ValueError("response_lengths_host works on a CPU tensor; use get_response_lengths for device tensors")
+    p = position_ids.reshape(-1)
+    T = p.numel()
+    if T == 0:
+        return [0]
+    if T < 3:
+        return [T]
+    is_b = (p[1:-1] == 0) & (p[:-2] != 0) & (p[2:] == 1)
+    b = [0] + (is_b.nonzero().reshape(-1) + 1).tolist() + [T]
+    return [b[k + 1] - b[k] for k in range(len(b) - 1)]

@@ -1079,6 +1079,16 @@ def test_loader_uploads_one_buffer_per_micro_batch(P):
         ref = P.rl_micro_step(h, w, P.to_device(b, "cuda"), P.LossConfig(), 7, backward=False)
         out = P.rl_micro_step(h, w, a, P.LossConfig(), 7, backward=False)
         assert torch.equal(out["logprobs"], ref["logprobs"]) and torch.equal(out["loss"], ref["loss"])
+        # the loader attached what it saw on the host, so that the micro-step needs no device-to-host sync: same values as the
+        # device kernels give, and the same gradients with the backward over the active positions only
+        assert a["response_lengths"] == P.get_response_lengths(a["position_ids"]) and a["n_active"] == int(b["loss_mask"][0, 1:].sum())
+        g = []
+        for mb in (a, P.to_device(b, "cuda")):
+            h2 = h.detach().clone().requires_grad_(True)
+            w2 = w.detach().clone().requires_grad_(True)
+            P.rl_micro_step(h2, w2, mb, P.LossConfig(), 7)
+            g.append((h2.grad, w2.grad))
+        assert torch.equal(g[0][0], g[1][0]) and torch.equal(g[0][1], g[1][1])
 
 
 def test_next_row_prepare_batch_on_device(P):

@@ -65,6 +65,24 @@ def test_writer_round_trip_and_atomic_rename(io, tmp_path):
     assert len(ref) == len(mine) and all(set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in KEYS) for a, b in zip(ref, mine))
 
 
+def test_host_side_segment_lengths_match_the_oracle():
+    """response_lengths_host (what the loader attaches so that the micro-step needs no device sync) == the oracle's restatement of
+    get_response_lengths (trainer/utils.py:36-69) on the reference's fixtures and on random packed rows"""
+    sys.path.insert(0, ROOT)
+    import oracle
+    from prime_rl_cse_b200.segments import response_lengths_host
+
+    d = np.load(os.path.join(GOLDEN, "segments.npz"))
+    for name in d["names"]:
+        assert response_lengths_host(torch.from_numpy(d[f"{name}/position_ids"])) == d[f"{name}/lengths"].tolist(), name
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        lens = rng.integers(1, 40, rng.integers(1, 12)).tolist()
+        pos = np.concatenate([np.arange(n) for n in lens] + [np.zeros(rng.integers(0, 4), dtype=np.int64)])
+        assert response_lengths_host(torch.from_numpy(pos).unsqueeze(0)) == oracle.response_lengths(pos)
+    assert response_lengths_host(torch.zeros(0, dtype=torch.int64)) == [0] and response_lengths_host(torch.zeros(2, dtype=torch.int64)) == [2]
+
+
 def test_rank_files_hold_only_their_own_tokens(io, tmp_path):
     """micro-batches that are slice VIEWS of one step-wide buffer (what prepare_batch(device_output=False) hands out) must not
     drag the whole buffer into every rank file: file size is bounded by the rank's own token count"""

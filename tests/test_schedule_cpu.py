@@ -83,3 +83,35 @@ def test_headline_shapes_are_not_k_split_and_small_ones_are(L):
     assert schedule(L, 3, 16384, 2048, 151936)[1]["k_splits"] == 2   # Qwen3-1.7B: 256 tiles = 3.5 waves
     assert schedule(L, 3, 4096, 1024, 151936)[1]["k_splits"] == 2    # Qwen3-0.6B: 32 tiles < 74 workers
     assert L.prl_debug_schedule(9, 1, 1, 1, None, 0, (ctypes.c_int32 * 8)()) == -1
+
+
+@pytest.mark.parametrize("peers,T_local,H,K", [(8, 16384, 5120, 18992), (2, 16384, 5120, 75968), (4, 2048, 4096, 37984), (8, 2048, 4096, 18992),
+                                              (2, 512, 256, 1000), (8, 32, 64, 128)])
+def test_fused_reduce_scatter_tile_order(L, peers, T_local, H, K):
+    """prl_lmhead_bwd_scatter: every rank covers every output tile exactly once, starts at the NEXT rank's tokens, and -- when the
+    token ranges are whole tiles -- at every position of the tile list the ranks target pairwise different owners (no rank's
+    NVLink inbound is hit by all the others at once)."""
+    M = peers * T_local
+    orders = []
+    for r in range(peers):
+        dims = (ctypes.c_int32 * 8)()
+        assert L.prl_debug_schedule_scatter(M, H, K, peers, r, None, 0, dims) == 0
+        n = dims[3]
+        items = (ctypes.c_int32 * (6 * n))()
+        assert L.prl_debug_schedule_scatter(M, H, K, peers, r, items, n, dims) == 0
+        it = np.ctypeslib.as_array(items).reshape(-1, 6).copy()
+        m_tiles, n_tiles, rows_per_tile = dims[0], dims[1], dims[7]
+        cover = np.zeros((m_tiles, n_tiles), dtype=np.int32)
+        for m, nb, nc, kb, kc, split in it:
+            assert nc == 1 and kb == 0 and kc == dims[2]
+            cover[m, nb] += 1
+        assert (cover == 1).all()
+        assert dims[6] == T_local
+        owner_of_first = min(it[0, 0] * rows_per_tile // T_local, peers - 1)
+        if T_local % rows_per_tile == 0:
+            assert owner_of_first == (r + 1) % peers
+        orders.append(it[:, 0] * rows_per_tile // T_local)
+    if T_local % rows_per_tile == 0:
+        owners = np.stack(orders)  # [rank, item] -> owner of the tile that rank writes at that position
+        assert all(len(set(owners[:, i])) == peers for i in range(owners.shape[1]))
+    assert L.prl_debug_schedule_scatter(1000, 64, 64, 3, 0, None, 0, (ctypes.c_int32 * 8)()) == -1  # M % n_peers != 0
