@@ -60,3 +60,33 @@ def test_b200_arm_json_contract():
     assert rec["frac_of_peak"]["executed_over_algorithmic"] > sav["frac_of_peak"]["executed_over_algorithmic"] == 1.0
     r = run(["--workload", "tiny", "--steps", "3", "--warmup", "3", "--lm-head-backward", "saved", "--no-cpu-baseline", "--no-torch-baseline"])
     assert r["config"]["lm_head_backward"].startswith("saved-logits") and r["value"] > 0 and set(r["modes"]) == {"saved_logits"}
+
+
+def test_evidence_tool_names_kernels_like_the_host_code():
+    """tools/make_evidence.py maps mangled (cuobjdump) and demangled (ncu) kernel names to the launch names bench.py uses as keys of
+    profiles/*traffic.json, and bench.py finds the committed capture of the headline kernels."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_evidence", os.path.join(ROOT, "tools", "make_evidence.py"))
+    me = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(me)
+    assert me.friendly("_ZN3prl11gemm_kernelILi2ELi1ELb0ELb0ELi0EEEvNS_10GemmParamsE") == "lmhead_fwd_kernel"
+    assert me.friendly("void gemm_kernel<2, 1, 0, 0, 1>(GemmParams)") == "lmhead_bwd_dz_kernel"
+    assert me.friendly("void prl::gemm_kernel<(int)2, (int)2, (bool)0, (bool)1, (int)2>(prl::GemmParams)") == "lmhead_bwd_dhidden_kernel"
+    assert me.friendly("void gemm_kernel<2, 2, 1, 1, 2>(GemmParams)") == "lmhead_bwd_dweight_kernel"
+    assert me.friendly("void gemm_kernel<1, 1, 0, 0, 2>(GemmParams)") == "gemm_kernel<1,1,0,0,2>"
+    assert me.friendly("dz_from_saved_logits_kernel(__nv_bfloat16 *, long, long)") == "dz_from_saved_logits_kernel"
+    assert me.friendly("_ZN3prl15loss_seq_kernelEPKfS1_S1_PKhPKiiffPfS6_S6_S6_Pd") == "loss_seq_kernel"
+    assert me.to_bytes("1.5", "Gbyte") == 1.5e9 and me.to_ns("2", "ms") == 2e6
+    sys.path.insert(0, ROOT)
+    saved_stdout = os.dup(1)  # importing bench.py points fd 1 at stderr (its stdout carries exactly one JSON line): undo that here
+    try:
+        import bench
+    finally:
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+
+    for mode, kernel in (("recompute", "lmhead_bwd_dz_kernel"), ("recompute", "lmhead_fwd_kernel"), ("saved", "lmhead_bwd_dweight_kernel")):
+        rec = bench.ncu_traffic(mode, kernel, "qwen3-8b-hendrycks")
+        assert rec and rec["bytes"] > bench.algorithmic_bytes(kernel, 16384, 4096, 151936, 16384 if mode == "recompute" else 151936) * 0.9
+    assert bench.ncu_traffic("recompute", "lmhead_fwd_kernel", "tiny") is None
