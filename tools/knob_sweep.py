@@ -20,6 +20,7 @@ ap.add_argument("--shape", default="8b")
 ap.add_argument("--msub", type=int, default=0)
 ap.add_argument("--only", default="fwd,dz,dh,dw")
 ap.add_argument("--secs", type=float, default=1.0)
+ap.add_argument("--hints", action="store_true", help="sweep the L2 eviction hints of the dz / fwd sweeps instead of the scheduling knobs")
 a = ap.parse_args()
 if a.msub:
     _lib.set_knob("PRL_MSUB", a.msub)
@@ -81,6 +82,21 @@ SETTINGS = [
     ("PRL_TILE_STAGES=2", {"PRL_TILE_STAGES": 2}, ["dh", "dw"]),
     ("defaults (end)", {}, only),
 ]
+if os.environ.get("PRL_LIB_PATH", "").endswith("_debug.so"):
+    # profiling aids of the -DPRL_DEBUG_KNOBS build (make -C prime_rl_cse_b200/csrc debug; PRL_LIB_PATH=.../libprl_b200_debug.so):
+    # how much of each kernel is its epilogue's global-memory traffic (results are WRONG by design)
+    DEFAULTS["PRL_DEBUG_NOSTORE"] = 0
+    SETTINGS = [("defaults", {}, only), ("PRL_DEBUG_NOSTORE=1", {"PRL_DEBUG_NOSTORE": 1}, only), ("defaults (end)", {}, only)]
+if a.hints:
+    H3 = [(-1, -1, -1), (0, 0, 0), (2, 0, 0), (2, 1, 0), (2, 0, 1), (2, 1, 1), (0, 1, 1), (2, 2, 1), (0, 0, 1)]
+    SETTINGS = [("defaults", {}, only)]
+    for fam, f in (("DZ", "dz"), ("FWD", "fwd"), ("DH", "dh"), ("DW", "dw")):
+        if f in only:
+            SETTINGS += [(f"PRL_HINT_{fam}_A/B/C={x}", {f"PRL_HINT_{fam}_A": x[0], f"PRL_HINT_{fam}_B": x[1], f"PRL_HINT_{fam}_C": x[2]}, [f]) for x in H3[1:]]
+    SETTINGS += [("defaults (end)", {}, only)]
+    for fam in ("DZ", "FWD", "DH", "DW"):
+        for o in "ABC":
+            DEFAULTS[f"PRL_HINT_{fam}_{o}"] = -1
 print(f"shape {a.shape}: T={T} H={H} V={V}  PRL_MSUB={a.msub or 'default (sweeps 1, store GEMMs 2)'}   ms per micro-batch", flush=True)
 for name, kn, fams in SETTINGS:
     for k, v in DEFAULTS.items():
