@@ -287,14 +287,34 @@ class Runner:
         self.loss_host = torch.empty(self.n_mb, dtype=torch.float32).pin_memory()
         self.rs_events = None  # (start, end) CUDA events around the last step's d_W_lm reduce-scatter
         self.compute_end = None
+        # N > 1, recompute mode: d_W_lm is accumulated straight into the reduce-scattered layout by the d_weight GEMM's epilogue
+        # (peer memory over NVLink; prime_rl_cse_b200.peer.ShardedGradAccumulator) -- no step-end collective.  Falls back to the
+        # local fp32 accumulator + ncclReduceScatter when peer buffers cannot be had (all ranks agree on that together).
+        self.acc, self.acc_note = None, "local fp32 accumulator + ncclReduceScatter once per step"
+        if dist is not None and world <= 8 and getattr(args, "fused_dw_sync", 1):
+            try:
+                self.acc = P.ShardedGradAccumulator(V, H, dev)
+                self.acc_note = "accumulated in the reduce-scattered layout inside the d_weight GEMM epilogue (TMA reduce-add into the owner's shard over NVLink), barrier at step end"
+            except RuntimeError as e:
+                self.acc_note += f" (fused accumulation unavailable: {e})"[:200]
 
     def ensure_saved_block(self):
         if self.saved_blk is None:
             lib = self._lib.load()
             self.saved_blk = torch.empty(self.wl["T"], int(lib.prl_lmhead_saved_logits_ld(self.wl["V"])), dtype=torch.bfloat16, device=self.dev)
 
-    def _grad_sync(self):
-        """FSDP2's gradient sync of the [lm_head, norm] group (model.py:126-131): fp32 reduce-scatter of d_W_lm, once per step"""
+    def _grad_sync(self, fused: bool = False):
+        """FSDP2's gradient sync of the [lm_head, norm] group (model.py:126-131): fp32 reduce-scatter of d_W_lm, once per step;
+        `fused`: the shards were accumulated in place by the GEMM epilogues, what is left is the barrier"""
+        if fused:
+            self.compute_end = torch.cuda.Event(enable_timing=True)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.compute_end.record()
+            a.record()
+            self.acc.finish_step()
+            b.record()
+            self.rs_events = (a, b)
+            return
         if self.dist is not None and self.rs_out is not None:
             self.compute_end = torch.cuda.Event(enable_timing=True)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -309,6 +329,9 @@ class Runner:
         P, wl = self.P, self.wl
         P.compute_advantages_tensor(self.rewards_d, self.lengths_d, wl["group"], "drgrpo")
         last = None
+        fused = self.acc is not None and not save
+        if fused:
+            self.acc.begin_step()
         if save:
             self.ensure_saved_block()
         for i in range(self.n_mb):
@@ -326,11 +349,13 @@ class Runner:
             if save:
                 P.lm_head_backward_saved_raw(hid, self.Wd, ids, lse, dlogp, inv, self.saved_blk, dweight=self.main_grad,
                                              dweight_accumulate=True, workspace=self.ws_bs)
+            elif fused:
+                P.lm_head_backward_dw_scatter_raw(hid, self.Wd, ids, lse, dlogp, inv, self.acc, workspace=self.ws_b)
             else:
                 P.lm_head_backward_raw(hid, self.Wd, ids, lse, dlogp, inv, dweight=self.main_grad, dweight_accumulate=True,
                                        workspace=self.ws_b)
             last = loss
-        self._grad_sync()
+        self._grad_sync(fused)
         return last
 
     def step_e2e(self, save: bool, forward_skips_masked: bool = False):
@@ -340,6 +365,9 @@ class Runner:
         adv = P.compute_advantages(wl["rewards"].tolist(), wl["lengths"].tolist(), wl["group"], "drgrpo")  # host lists in/out
         del adv
         cur = torch.cuda.current_stream()
+        fused = self.acc is not None and not save
+        if fused:
+            self.acc.begin_step()
 
         def upload(i):
             src = wl["mbs"][i % len(wl["mbs"])]
@@ -363,10 +391,10 @@ class Runner:
                 if torch.is_tensor(v):
                     v.record_stream(cur)
             hid = mb["hidden"].requires_grad_(True)
-            out = P.rl_micro_step(hid, self.W, mb, self.cfg, self.loss_scale, main_grad=self.main_grad, response_lengths=None,
-                                  forward_skips_masked=forward_skips_masked, save_logits=save)
+            out = P.rl_micro_step(hid, self.W, mb, self.cfg, self.loss_scale, main_grad=self.acc if fused else self.main_grad,
+                                  response_lengths=None, forward_skips_masked=forward_skips_masked, save_logits=save)
             self.loss_host[i].copy_(out["loss"], non_blocking=True)
-        self._grad_sync()
+        self._grad_sync(fused)
         torch.cuda.current_stream().synchronize()
         return float(self.loss_host[-1])
 
@@ -394,6 +422,32 @@ class Runner:
         if self.dist is not None:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t[0]), ms, rs_ms
+
+    def dw_sync_check(self):
+        """the fused accumulation against the classic path on the same micro-batches: one step each from zeroed accumulators;
+        every rank compares its shard (sum over ranks) -- rel-L2 and the largest element-wise deviation relative to the largest
+        element (the ranks' addends reach a shard in no fixed order: fp32 rounding, not bits)"""
+        if self.acc is None or self.rs_out is None:
+            return None
+        self.main_grad.zero_()
+        self.step_resident_classic()
+        torch.cuda.synchronize()
+        ref = self.rs_out.view(-1, self.wl["H"]).clone()
+        self.step_resident(False)
+        torch.cuda.synchronize()
+        got = self.acc.shard
+        t = torch.stack([(got - ref).norm() / ref.norm().clamp_min(1e-30), (got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)]).double()
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return {"rel_l2": float(t[0]), "max_abs_over_max": float(t[1]), "ok": bool(float(t[0]) < 1e-5 and float(t[1]) < 1e-5),
+                "what": "every rank's shard after one step of the fused accumulation vs local fp32 accumulator + ncclReduceScatter on the same micro-batches (max over ranks)"}
+
+    def step_resident_classic(self):
+        """one step with the local fp32 accumulator and the NCCL reduce-scatter (reference for dw_sync_check)"""
+        acc, self.acc = self.acc, None
+        try:
+            self.step_resident(False)
+        finally:
+            self.acc = acc
 
     def rs_check(self):
         """multi-GPU correctness in the record: the reduce-scattered d_W_lm shard of every rank equals the sum over ranks of
@@ -508,9 +562,16 @@ def measure_mode(rn: Runner, save: bool, steps: int, warmup: int, sampler, rank:
         tab = torch.stack(allr).cpu()
         rec["per_rank"] = {"ms_per_step": [round(float(x), 3) for x in tab[:, 0]], "dw_reduce_scatter_ms": [round(float(x), 3) for x in tab[:, 1]],
                            "sm_mhz": [float(x) for x in tab[:, 2]], "e2e_ms_per_step": [round(float(x), 3) for x in tab[:, 3]],
-                           "note": "ms_per_step: each rank's own CUDA-event time over the timed region / steps (includes waiting in the "
-                                   "step-end reduce-scatter for the slowest rank); value uses the max"}
-        rec["dw_reduce_scatter_check"] = rn.rs_check()
+                           "note": "ms_per_step: each rank's own CUDA-event time over the timed region / steps (includes waiting for the "
+                                   "slowest rank in the step-end d_W_lm sync: the NCCL reduce-scatter, or the barrier that is left of it when "
+                                   "the gradient is accumulated in the reduce-scattered layout); value uses the max"}
+        fused = rn.acc is not None and not save
+        rec["dw_sync"] = rn.acc_note if fused else "local fp32 accumulator + ncclReduceScatter once per step"
+        if fused:
+            rec["dw_sync_check"] = rn.dw_sync_check()
+            rn.main_grad.zero_()
+        else:
+            rec["dw_reduce_scatter_check"] = rn.rs_check()
     if with_breakdown and rank == 0:
         fam, vc = rn.breakdown(save)
         top = max(fam, key=lambda k: fam[k]["ms_per_launch"] * fam[k]["launches_per_mb"])
@@ -620,17 +681,21 @@ def run_b200(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": describe(wl, world), "tokens_per_gpu_per_step": n_mb * T,
                    "parallelism": f"token-sharded dp{world} (no data-path collective; "
-                   + ("d_W_lm fp32 reduce-scatter once per step)" if world > 1 else "single GPU)"),
+                   + (f"d_W_lm gradient sync: {head.get('dw_sync')})" if world > 1 else "single GPU)"),
                    "l2_policy": "inputs larger than L2 (W_lm 1.24 GB + 134 MB hidden per micro-batch, rotating micro-batches)",
                    "flops_per_token_algorithmic": 6.0 * H * V, "lm_head_backward": head["lm_head_backward"],
                    "headline_mode": head_mode},
         "per_gpu": head["per_gpu"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
         "tensor_tflops_algorithmic_per_gpu": head["tensor_tflops_algorithmic_per_gpu"], "frac_of_peak": head["frac_of_peak"],
     }
-    for k in ("roofline", "kernel_breakdown_ms_per_micro_batch", "kernel_tflops", "hbm_kernels", "per_rank", "dw_reduce_scatter_check"):
+    for k in ("roofline", "kernel_breakdown_ms_per_micro_batch", "kernel_tflops", "hbm_kernels", "per_rank", "dw_reduce_scatter_check", "dw_sync",
+              "dw_sync_check"):
         if k in head:
             result[k] = head[k]
     result["modes"] = {("saved_logits" if m == "saved" else m): recs[m] for m in modes}
+    if rn.acc is not None:
+        rn.acc.close()
+        rn.acc = None
     if dist is not None and not args.no_vocab_check:
         import prime_rl_cse_b200 as P_
 
@@ -1022,6 +1087,8 @@ def main():
     ap.add_argument("--lm-head-backward", default="both", choices=["both", "saved", "recompute"],
                     help="both (default): time the recompute backward (headline) and the saved-logits backward (modes.saved_logits); "
                          "recompute / saved: only that one")
+    ap.add_argument("--fused-dw-sync", type=int, default=1, help="N>1, recompute mode: 1 = accumulate d_W_lm in the reduce-scattered layout "
+                    "inside the GEMM epilogue over peer memory (no step-end collective), 0 = local accumulator + ncclReduceScatter")
     ap.add_argument("--fused-rs", type=int, default=1, help="vocab-sharded workload: 1 = d_hidden reduce-scatter fused into the GEMM "
                     "epilogue over peer memory, 0 = NCCL reduce-scatter after the GEMM")
     args = ap.parse_args()

@@ -174,7 +174,7 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
  * reduce-added (fp32, cp.reduce.async.bulk.tensor performed at the owner's L2, over NVLink for remote owners) into
  * d_hidden_peers[owner][row - owner * rows_per_peer, :H], owner = row / rows_per_peer.  d_hidden_peers is a HOST array of
  * n_peers device pointers to fp32 [rows_per_peer, H] accumulators that are mapped into this process (CUDA IPC / symmetric
- * memory; entry self_index is this rank's own buffer).  The caller zeroes its accumulator and synchronises the peers before
+ * memory; entry self_index is this rank's own buffer; rows_per_peer need not be a multiple of 32).  The caller zeroes its accumulator and synchronises the peers before
  * the call, and again before reading the result.  Replaces the NCCL reduce-scatter that follows the
  * GEMM in the unfused path; everything else (dlogits recompute, d_weight shard) is as in prl_lmhead_bwd. */
 int prl_lmhead_bwd_scatter(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp,
@@ -182,6 +182,22 @@ int prl_lmhead_bwd_scatter(const void* hidden, const void* weight, const int64_t
                            void* const* d_hidden_peers, int32_t n_peers, int64_t rows_per_peer, int32_t self_index,
                            void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk, int32_t phase_mask,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Token-sharded ranks (= FSDP ranks), gradient accumulation of d_W_lm straight INTO the reduce-scattered layout: instead of a
+ * local fp32 [V, H] accumulator that FSDP2 / NCCL reduce-scatters at the end of the step (src/prime_rl/trainer/model.py:100-135,
+ * reduce_dtype fp32), every tile of every micro-batch's d_weight GEMM is reduce-added (fp32, TMA, performed at the owner's L2,
+ * over NVLink for remote owners) into the shard of the rank that owns those vocab rows: d_weight_shards[j] is rank j's fp32
+ * [min(rows_per_peer, V - j * rows_per_peer), H] shard (rows_per_peer = ceil(V / n_peers): torch.chunk / FSDP2 dim-0 layout),
+ * mapped into this process (prl_ipc_*); a 32-row slab that straddles two owners is sent to both with the row range clipped by
+ * their tensor maps.  Ranks start at different vocab chunks so that they add into different owners at any time.  No step-end
+ * collective is left (a barrier before the shards are read), and no rank holds a full [V, H] gradient.  The order in which the
+ * ranks' addends reach a shard is not fixed: results are reproducible to fp32 rounding, not bit for bit.  d_hidden as in
+ * prl_lmhead_bwd (local).  The caller zeroes its shard and synchronises the ranks before the first micro-batch of a step. */
+int prl_lmhead_bwd_dw_scatter(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp,
+                              int64_t T, int32_t H, int64_t V, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden,
+                              int32_t d_hidden_f32, void* const* d_weight_shards, int32_t n_peers, int64_t rows_per_peer,
+                              int32_t self_index, int64_t vchunk, int32_t phase_mask, void* workspace, size_t workspace_bytes,
+                              void* stream);
 
 /* Peer memory for prl_lmhead_bwd_scatter (the ONLY entry points that own device memory: an accumulator that other processes
  * map has to be a whole allocation of its own).  prl_ipc_alloc: cudaMalloc `bytes` on the current device and export it

@@ -95,6 +95,7 @@ struct GemmParams {
   int32_t n_peers;
   int32_t peer_rows;
   int32_t m_rot;
+  int32_t peer_row0;  // global row of row 0 of this GEMM's C (a vocab chunk of the d_weight GEMM starts inside some owner's range)
   CUtensorMap tma_c_peer[8];
   EpiParams epi;
 };
@@ -697,10 +698,15 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
                 const int32_t col = (int32_t)(out_bf16 ? (n0 + (ch & ~1) * 32) : c0);
                 const bool reduce = (EPI == EPI_STORE) && (e.flags & ST_LOAD_F32);
                 if (EPI == EPI_STORE && p.n_peers > 0) {
-                  // fused reduce-scatter: this 32-row slab belongs to one owner (peer_rows % 32 == 0); add it into the owner's
-                  // fp32 accumulator (local or NVLink peer memory), rows beyond the owner's range are clipped by its map
-                  const int owner = row0_warp / p.peer_rows;
-                  if (owner < p.n_peers) ptx::tma_reduce_add_2d(&p.tma_c_peer[owner], src, col, row0_warp - owner * p.peer_rows);
+                  // fused reduce-scatter: add this 32-row slab into its owner's fp32 accumulator (local or NVLink peer memory).
+                  // Rows beyond the owner's range are clipped by its tensor map; a slab that straddles two owners (peer_rows not
+                  // a multiple of 32) is sent to both, the second time at a NEGATIVE row coordinate so that only its tail lands.
+                  const int g0 = p.peer_row0 + row0_warp;
+                  const int owner = g0 / p.peer_rows;
+                  const int local = g0 - owner * p.peer_rows;
+                  if (owner < p.n_peers) ptx::tma_reduce_add_2d(&p.tma_c_peer[owner], src, col, local);
+                  if (local + 32 > p.peer_rows && owner + 1 < p.n_peers)
+                    ptx::tma_reduce_add_2d(&p.tma_c_peer[owner + 1], src, col, local - p.peer_rows);
                 } else if (p.hint_c == 0) {
                   if (reduce)
                     ptx::tma_reduce_add_2d(&p.tma_c, src, col, row0_warp);

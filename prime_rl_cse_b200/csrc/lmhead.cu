@@ -548,7 +548,8 @@ struct PeerScatter {
   void* const* ptrs;      // host array of n DEVICE pointers: every peer's fp32 [rows_per_peer, H] accumulator (own one included)
   int32_t n;
   int64_t rows_per_peer;
-  int32_t self;           // this rank's index (sets the m-tile rotation)
+  int32_t self;           // this rank's index (sets the m-tile / vocab-chunk rotation)
+  int64_t total_rows;     // d_weight scatter: rows of the whole matrix (the last owners may hold fewer than rows_per_peer)
 };
 
 // Fused reduce-scatter: rows [j * rows_per_peer, ..) of the output belong to peer j; rank `self` starts at the tiles of the NEXT
@@ -564,7 +565,7 @@ static void set_scatter_rotation(GemmParams& p, int n_peers, int64_t rows_per_pe
 static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __nv_bfloat16* dz, int64_t vc, int64_t c0, int64_t vce,
                             int64_t T, int32_t H, void* d_hidden, int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype,
                             int32_t accumulate_dw, int32_t phase_mask, bool first, bool last, int64_t nchunks, float* dh_acc,
-                            int band, cudaStream_t st, const PeerScatter* peers = nullptr) {
+                            int band, cudaStream_t st, const PeerScatter* peers = nullptr, const PeerScatter* dw_peers = nullptr) {
   const int64_t vc_full = nchunks > 1 ? vc : vce;  // every chunk of one backward takes the same k-split decision
   // ---- K2: d_hidden[T,H] += dz[T,vce] x W[c0:c0+vce, :]   (A K-major, B MN-major) ----
   if (peers && (phase_mask & 2)) {
@@ -648,7 +649,7 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
     }
   }
   // ---- K3: d_weight[c0:c0+vce, H] (+)= dz^T x hidden   (both MN-major) ----
-  if (d_weight && (phase_mask & 4)) {
+  if ((d_weight || dw_peers) && (phase_mask & 4)) {
     GemmParams p;
     memset(&p, 0, sizeof(p));
     int rc = make_operand_map(&p.tma_a, dz, true, vce, T, vc, BLOCK_M);
@@ -661,7 +662,24 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
     p.epi.m_rows = vce;
     p.epi.n_cols = H;
     p.epi.ldc = H;
-    if (d_weight_dtype == PRL_DT_F32) {
+    if (dw_peers) {
+      // gradient accumulation straight into the reduce-scattered layout: the rows of this chunk are reduce-added (fp32) into the
+      // shards of the ranks that own them; a chunk spans at most a few owners
+      p.epi.flags = ST_STORE_F32 | ST_LOAD_F32 | ST_TMA;
+      p.n_peers = dw_peers->n;
+      p.peer_rows = (int32_t)dw_peers->rows_per_peer;
+      p.peer_row0 = (int32_t)c0;
+      for (int j = 0; j < dw_peers->n; ++j) {
+        const int64_t rows_j = dw_peers->total_rows - (int64_t)j * dw_peers->rows_per_peer;
+        const int64_t rows_here = rows_j < dw_peers->rows_per_peer ? rows_j : dw_peers->rows_per_peer;
+        if (rows_here <= 0) {  // FSDP's trailing ranks may own nothing (torch.chunk semantics)
+          p.n_peers = j;
+          break;
+        }
+        rc = make_output_map(&p.tma_c_peer[j], dw_peers->ptrs[j], rows_here, H, H, true);
+        if (rc) return rc;
+      }
+    } else if (d_weight_dtype == PRL_DT_F32) {
       p.epi.c_f32 = reinterpret_cast<float*>(d_weight) + c0 * H;
       p.epi.flags = ST_STORE_F32 | (accumulate_dw ? ST_LOAD_F32 : 0);
       if (epi_tma_enabled()) {
@@ -704,7 +722,8 @@ size_t prl_lmhead_bwd_workspace_bytes(int64_t T, int32_t H, int64_t V, int64_t v
 static int lmhead_bwd_impl(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T,
                            int32_t H, int64_t V, int64_t v_offset, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden,
                            int32_t d_hidden_f32, void* d_weight, int32_t d_weight_dtype, int32_t accumulate_dw, int64_t vchunk,
-                           int32_t phase_mask, void* workspace, size_t workspace_bytes, void* stream, const PeerScatter* peers) {
+                           int32_t phase_mask, void* workspace, size_t workspace_bytes, void* stream, const PeerScatter* peers,
+                           const PeerScatter* dw_peers = nullptr) {
   PRL_REQUIRE(T >= 0 && H >= 1 && V >= 1, PRL_ERR_BAD_ARG, "lmhead_bwd: bad sizes");
   PRL_REQUIRE(shift == 0 || shift == 1, PRL_ERR_BAD_ARG, "lmhead_bwd: shift must be 0 or 1");
   PRL_REQUIRE(inv_temp > 0.f && inv_temp < INFINITY, PRL_ERR_BAD_ARG, "lmhead_bwd: temperature must be positive and finite");
@@ -716,13 +735,16 @@ static int lmhead_bwd_impl(const void* hidden, const void* weight, const int64_t
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t vc = pick_vchunk(V, vchunk);
   const int64_t nchunks = (V + vc - 1) / vc;
+  // d_weight scatter: every rank starts at a different vocab chunk, so that at any time the ranks add into different owners' shards
+  const int64_t chunk_rot = dw_peers ? ((int64_t)dw_peers->self * nchunks) / dw_peers->n : 0;
   const int64_t t_pad = round_up(T, BLOCK_M);
   __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(workspace);
   float* dh_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + round_up(t_pad * vc * 2, 1024));
   const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(weight);
 
   if ((phase_mask & 7) == 0) phase_mask = 7;
-  for (int64_t c = 0; c < nchunks; ++c) {
+  for (int64_t ci = 0; ci < nchunks; ++ci) {
+    const int64_t c = (ci + chunk_rot) % nchunks;
     const int64_t c0 = c * vc;
     const int64_t vce = (V - c0) < vc ? (V - c0) : vc;
     // ---- K1: recompute the logits tile by tile, emit dlogits (bf16) for this vocab chunk ----
@@ -760,7 +782,7 @@ static int lmhead_bwd_impl(const void* hidden, const void* weight, const int64_t
     }
     {
       const int rc = lmhead_bwd_gemms(hidden, W, dz, vc, c0, vce, T, H, d_hidden, d_hidden_f32, d_weight, d_weight_dtype, accumulate_dw,
-                                      phase_mask, c == 0, c == nchunks - 1, nchunks, dh_acc, 8, st, peers);
+                                      phase_mask, ci == 0, ci == nchunks - 1, nchunks, dh_acc, 8, st, peers, dw_peers);
       if (rc) return rc;
     }
   }
@@ -787,9 +809,25 @@ int prl_lmhead_bwd_scatter(const void* hidden, const void* weight, const int64_t
   PRL_REQUIRE(T == rows_per_peer * n_peers, PRL_ERR_BAD_ARG, "lmhead_bwd_scatter: T must be n_peers * rows_per_peer");
   PRL_REQUIRE(epi_tma_enabled(), PRL_ERR_UNSUPPORTED, "lmhead_bwd_scatter needs the TMA-store epilogue (PRL_EPI_TMA=1)");
   for (int j = 0; j < n_peers; ++j) PRL_REQUIRE(d_hidden_peers[j], PRL_ERR_BAD_ARG, "lmhead_bwd_scatter: null peer pointer");
-  PeerScatter ps = {d_hidden_peers, n_peers, rows_per_peer, self_index};
+  PeerScatter ps = {d_hidden_peers, n_peers, rows_per_peer, self_index, T};
   return lmhead_bwd_impl(hidden, weight, ids, lse, dlogp, T, H, V, v_offset, inv_temp, shift, round_bf16, nullptr, 1, d_weight, d_weight_dtype,
                          accumulate_dw, vchunk, phase_mask, workspace, workspace_bytes, stream, &ps);
+}
+
+int prl_lmhead_bwd_dw_scatter(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T,
+                              int32_t H, int64_t V, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden, int32_t d_hidden_f32,
+                              void* const* d_weight_shards, int32_t n_peers, int64_t rows_per_peer, int32_t self_index, int64_t vchunk,
+                              int32_t phase_mask, void* workspace, size_t workspace_bytes, void* stream) {
+  PRL_REQUIRE(d_weight_shards && n_peers >= 1 && n_peers <= 8 && self_index >= 0 && self_index < n_peers, PRL_ERR_BAD_ARG,
+              "lmhead_bwd_dw_scatter: 1..8 peers");
+  PRL_REQUIRE(rows_per_peer >= 32 && rows_per_peer < ((int64_t)1 << 31) && rows_per_peer * n_peers >= V && V < ((int64_t)1 << 31),
+              PRL_ERR_BAD_ARG, "lmhead_bwd_dw_scatter: rows_per_peer must be ceil(V / n_peers) (>= 32)");
+  PRL_REQUIRE(epi_tma_enabled(), PRL_ERR_UNSUPPORTED, "lmhead_bwd_dw_scatter needs the TMA-store epilogue (PRL_EPI_TMA=1)");
+  for (int j = 0; j < n_peers; ++j)
+    PRL_REQUIRE(d_weight_shards[j] || (int64_t)j * rows_per_peer >= V, PRL_ERR_BAD_ARG, "lmhead_bwd_dw_scatter: null shard pointer");
+  PeerScatter ps = {d_weight_shards, n_peers, rows_per_peer, self_index, V};
+  return lmhead_bwd_impl(hidden, weight, ids, lse, dlogp, T, H, V, 0, inv_temp, shift, round_bf16, d_hidden, d_hidden_f32, nullptr, PRL_DT_F32, 1,
+                         vchunk, phase_mask, workspace, workspace_bytes, stream, nullptr, &ps);
 }
 
 size_t prl_lmhead_bwd_saved_workspace_bytes(int64_t T, int32_t H, int64_t V) {

@@ -198,6 +198,31 @@ def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, 
     return dh, dweight
 
 
+def lm_head_backward_dw_scatter_raw(hidden, weight, ids, lse, dlogp, inv_temp, acc, shift=True, round_bf16=True, want_dhidden=True,
+                                    vchunk=0, dhidden_f32=False, phase_mask=0, workspace=None):
+    """Recompute backward whose d_weight GEMM adds its tiles straight into the ranks' shards of `acc` (a
+    `peer.ShardedGradAccumulator`: d_W_lm accumulated in the reduce-scattered layout, no step-end collective).  Returns d_hidden."""
+    _check_operands(hidden, weight, ids, "lm_head_backward_dw_scatter_raw", lse=lse, dlogp=dlogp)
+    lib = _lib.load()
+    T, H = hidden.shape
+    V = weight.shape[0]
+    if V != acc.V or H != acc.H:
+        raise ValueError(f"accumulator is for a [{acc.V}, {acc.H}] gradient, the weight is [{V}, {H}]")
+    dh = torch.empty(T, H, dtype=torch.float32 if dhidden_f32 else torch.bfloat16, device=hidden.device) if want_dhidden else None
+    nb = lib.prl_lmhead_bwd_workspace_bytes(T, H, V, vchunk)
+    ws = workspace if workspace is not None and workspace.numel() >= nb else _ws(nb, hidden.device)
+    rc = lib.prl_lmhead_bwd_dw_scatter(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), _lib.ptr(lse), _lib.ptr(dlogp), T, H, V,
+                                       float(inv_temp), 1 if shift else 0, 1 if round_bf16 else 0, _lib.ptr(dh), 1 if dhidden_f32 else 0,
+                                       acc.buf.ptrs, acc.world, acc.rows_per_peer, acc.rank, vchunk, phase_mask, _lib.ptr(ws), ws.numel(),
+                                       _lib.stream())
+    _lib.check(rc, "prl_lmhead_bwd_dw_scatter")
+    return dh
+
+
+def _is_sharded_accumulator(main_grad) -> bool:
+    return main_grad is not None and not torch.is_tensor(main_grad) and hasattr(main_grad, "rows_per_peer")
+
+
 def _forward_any(h, w, i, inv_temp, shift, round_bf16, save):
     """(logp, ent, lse, saved|None): saved-logits forward when asked for and possible, else the plain one."""
     if save and round_bf16 and h.shape[0] > 0:
@@ -223,6 +248,10 @@ class _FusedLMHead(torch.autograd.Function):
         ctx.saved_logits = None   # bf16 logits kept for the backward (consumed by it)
         ctx.had_saved = False
         needs_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        if _is_sharded_accumulator(main_grad):
+            if save_logits:
+                _warn_fallback("d_W_lm is accumulated in a ShardedGradAccumulator, which the recompute backward feeds")
+            save_logits = False
         # Masked positions get no gradient (loss.py:104): with a partition of the row (active positions first, rows.py) the
         # backward -- and optionally the forward -- only visits the first n_active slots.  Nothing to gain when every
         # position is active, or when no backward will follow and the forward has to cover the whole row anyway.
@@ -269,6 +298,8 @@ class _FusedLMHead(torch.autograd.Function):
         dw_target = main_grad if (main_grad is not None and need_w) else None
 
         def run(h, i, l, gg, sh, block):
+            if _is_sharded_accumulator(dw_target):  # tiles go straight into the owners' shards (no local [V, H] gradient)
+                return lm_head_backward_dw_scatter_raw(h, w2, i, l, gg, inv_temp, dw_target, sh, round_bf16, want_dhidden=need_h), None
             kw = dict(want_dhidden=need_h, dweight=dw_target, dweight_accumulate=dw_target is not None, want_dweight=need_w)
             if block is not None:
                 return lm_head_backward_saved_raw(h, w2, i, l, gg, inv_temp, block, sh, **kw)
@@ -316,7 +347,9 @@ def fused_lm_head_logprobs_entropy(
     (rl/train.py:285-288,302-303) for one packed row.  `shift` applies to the whole flattened row as the
     reference's `shift_logits` does for batch size 1 (packed micro-batches, rl/data.py:13-23).
     `main_grad`: optional fp32/bf16 [V,H] buffer; the weight gradient is then ACCUMULATED into it by the
-    kernel and `weight.grad` is left untouched (fused gradient accumulation across micro-batches).
+    kernel and `weight.grad` is left untouched (fused gradient accumulation across micro-batches).  It may also be a
+    `peer.ShardedGradAccumulator`: the gradient is then accumulated directly in the reduce-scattered layout across the ranks of
+    the node, inside the d_weight GEMM's epilogue (recompute backward only; no step-end reduce-scatter is left).
     `loss_mask`: optional bool [..., T] tensor (the micro-batch's `loss_mask`) or a `rows.Partition` built from it: positions
     with mask False receive no gradient from the loss (rl/loss.py:104), so the backward skips their rows (prompt / environment
     tokens) — identical gradients, proportionally less work; the row is reordered "active positions first" by the library's own

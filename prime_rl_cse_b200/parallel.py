@@ -17,6 +17,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .peer import PeerBuffer, ShardedGradAccumulator  # noqa: F401  (re-exported)
 from .lm_head import (lm_head_backward_raw, lm_head_backward_saved_raw, lm_head_forward_raw, lm_head_forward_save_raw,
                       saved_logits_policy)
 
@@ -302,68 +303,17 @@ class VocabShardedLMHead:
 
     # -- fused reduce-scatter: peer-mapped fp32 accumulators, one per rank, written by every rank's d_hidden epilogue
     def _peer_accumulator(self, T: int, dev) -> torch.Tensor:
-        if self._sym is not None and self._sym["T"] == T:
-            return self._sym["acc"]
+        if self._sym is not None and self._sym.rows == T:
+            return self._sym.local
         if self._sym is not None:
             self.close()
         if T % 32 != 0:
-            raise ValueError("fused reduce-scatter needs T % 32 == 0 (an epilogue slab must not straddle two token owners)")
-        import ctypes
-
-        lib = _lib.load()
-        # the accumulator is a cudaMalloc allocation of its own (exportable as a whole), wrapped as a torch tensor.  Every step
-        # that can fail on one rank only is followed by an agreement (all-reduce of a flag), so that ALL ranks raise together
-        # instead of leaving the others inside a collective.
-        base, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
-        err = None
+            raise ValueError("fused reduce-scatter needs T % 32 == 0")
         try:
-            _lib.check(lib.prl_ipc_alloc(T * self.H * 4, ctypes.byref(base), handle), "prl_ipc_alloc")
-        except Exception as e:  # noqa: BLE001
-            err = e
-        if not self._agree(err is None, dev, None):
-            if base.value:
-                lib.prl_ipc_free(base)
-            raise RuntimeError(f"fused reduce-scatter unavailable: prl_ipc_alloc failed on a rank ({err}); use fused_rs=False")
-
-        class _Buf:  # zero-copy view for torch (CUDA array interface v2)
-            __cuda_array_interface__ = {"shape": (T, self.H), "typestr": "<f4", "data": (int(base.value), False), "version": 2}
-
-        acc = torch.as_tensor(_Buf(), device=dev)
-        acc.zero_()
-        infos = [None] * self.world
-        dist.all_gather_object(infos, bytes(handle.raw), group=self.group)
-        ptrs, opened = [], []
-        try:
-            for j, h in enumerate(infos):
-                if j == self.rank:
-                    ptrs.append(int(base.value))
-                    continue
-                peer = ctypes.c_void_p()
-                _lib.check(lib.prl_ipc_open(ctypes.c_char_p(h), ctypes.byref(peer)), "prl_ipc_open")
-                opened.append(peer.value)
-                ptrs.append(peer.value)
-        except Exception as e:  # noqa: BLE001
-            err = e
-        if not self._agree(err is None, dev, None):
-            for p_ in opened:
-                lib.prl_ipc_close(p_)
-            dist.barrier(group=self.group)
-            del acc
-            lib.prl_ipc_free(base)
-            raise RuntimeError(f"fused reduce-scatter unavailable: mapping a peer's accumulator failed on a rank ({err}); use fused_rs=False")
-        arr = (ctypes.c_void_p * self.world)(*ptrs)
-        self._sym = dict(T=T, acc=acc, ptrs=arr, opened=opened, own=int(base.value), flag=torch.zeros(1, dtype=torch.float32, device=dev))
-        dist.barrier(group=self.group)  # every rank has mapped every buffer before anyone uses them
-        return acc
-
-    def _agree(self, ok: bool, dev, message):
-        """True iff `ok` on every rank; with a `message`, raises it on ALL ranks otherwise"""
-        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        good = bool(flag.item())
-        if not good and message is not None:
-            raise RuntimeError(message)
-        return good
+            self._sym = PeerBuffer(T, self.H, dev, self.group)
+        except RuntimeError as e:
+            raise RuntimeError(f"fused reduce-scatter unavailable ({e}); use fused_rs=False") from e
+        return self._sym.local
 
     def _backward_fused(self, gathered, inv, lse_all, g_all, vchunk, ws):
         lib = _lib.load()
@@ -373,27 +323,20 @@ class VocabShardedLMHead:
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dt = _lib.PRL_DT_F32 if self.main_grad.dtype == torch.float32 else _lib.PRL_DT_BF16
         rc = lib.prl_lmhead_bwd_scatter(_lib.ptr(h_all), _lib.ptr(self.W), _lib.ptr(i_all), _lib.ptr(lse_all), _lib.ptr(g_all), W * T, self.H,
-                                        self.v1 - self.v0, self.v0, float(inv), 1, 1 if self.round_bf16 else 0, sym["ptrs"], W, T, self.rank,
+                                        self.v1 - self.v0, self.v0, float(inv), 1, 1 if self.round_bf16 else 0, sym.ptrs, W, T, self.rank,
                                         _lib.ptr(self.main_grad), dt, 1, vchunk, 0, _lib.ptr(ws), ws.numel(), _lib.stream())
         _lib.check(rc, "prl_lmhead_bwd_scatter")
         # all ranks' epilogues must have landed before the accumulator is read: a 4-byte all-reduce is the cross-rank barrier
         r0.record()
-        dist.all_reduce(sym["flag"], group=self.group)
+        sym.barrier()
         r1.record()
         self.timings["d_hidden_reduce_scatter"] = (r0, r1)  # fused: what is left of it outside the GEMM = the barrier
-        return sym["acc"].to(torch.bfloat16)
+        return sym.local.to(torch.bfloat16)
 
     def close(self):
         """unmap the peers' accumulators (fused reduce-scatter)"""
         if self._sym is not None:
-            torch.cuda.synchronize()
-            dist.barrier(group=self.group)
-            lib = _lib.load()
-            for p in self._sym["opened"]:
-                lib.prl_ipc_close(p)
-            dist.barrier(group=self.group)  # nobody maps the buffer any more
-            own, self._sym["acc"] = self._sym["own"], None
-            lib.prl_ipc_free(own)
+            self._sym.close()
             self._sym = None
 
     def micro_step(self, hidden_local, micro_batch, loss_config, loss_scale, gathered=None):

@@ -998,6 +998,39 @@ def test_row_partition_gather_scatter_kernels(P, T, shift, p_active):
         assert torch.equal(dh.cpu(), want_dh)
 
 
+@pytest.mark.parametrize("T,H,V,peers,self_index,vchunk", [(300, 64, 5000, 3, 1, 1024), (512, 256, 151936, 8, 5, 0), (200, 128, 4096, 2, 0, 0),
+                                                            (129, 64, 1000, 8, 7, 256), (64, 64, 321, 8, 3, 0)])
+def test_d_weight_scatter_into_owner_shards_emulated_on_one_gpu(P, T, H, V, peers, self_index, vchunk):
+    """prl_lmhead_bwd_dw_scatter with the owners' shards as separate buffers on ONE GPU: the concatenated shards must equal the
+    classic fp32 d_W accumulator bit for bit (one adder per element here), for shard sizes that are not multiples of the
+    32-row epilogue slab (slabs that straddle two owners are sent to both, clipped by the tensor maps), trailing owners
+    with fewer rows (torch.chunk layout), rotated vocab-chunk order, and accumulation over two micro-batches."""
+    import ctypes
+    from types import SimpleNamespace
+
+    from prime_rl_cse_b200 import lm_head_backward_dw_scatter_raw, lm_head_backward_raw, lm_head_forward_raw
+
+    hidden, weight, ids = _mk(T, H, V, T + V + peers)
+    h, w, i = hidden.cuda(), weight.cuda(), ids.cuda()
+    per = -(-V // peers)
+    shards = [torch.zeros(max(min(per, V - j * per), 0), H, device="cuda") for j in range(peers)]
+    guard = [torch.full((64, H), 7.0, device="cuda") for _ in range(peers)]  # canaries: nothing may be written past a shard
+    bufs = [torch.cat([s_, g_]) for s_, g_ in zip(shards, guard)]
+    ptrs = (ctypes.c_void_p * peers)(*[b.data_ptr() if shards[j].shape[0] > 0 else 0 for j, b in enumerate(bufs)])
+    acc = SimpleNamespace(V=V, H=H, world=peers, rank=self_index, rows_per_peer=per, buf=SimpleNamespace(ptrs=ptrs))
+    want = torch.zeros(V, H, device="cuda")
+    for step in range(2):
+        g = torch.randn(T, device="cuda") / T
+        _, _, lse, _ = lm_head_forward_raw(h, w, i, 1.0)
+        dh = lm_head_backward_dw_scatter_raw(h, w, i, lse, g, 1.0, acc, vchunk=vchunk)
+        dh_ref, _ = lm_head_backward_raw(h, w, i, lse, g, 1.0, dweight=want, dweight_accumulate=True, vchunk=vchunk)
+        assert ((dh.float() - dh_ref.float()).norm() / dh_ref.float().norm()).item() < 2e-3  # chunk order differs: fp32 summation order
+    got = torch.cat([b[: shards[j].shape[0]] for j, b in enumerate(bufs)])
+    assert got.shape == want.shape and torch.equal(got, want)
+    for j, b in enumerate(bufs):
+        assert float((b[shards[j].shape[0]:] - 7.0).abs().max()) == 0.0, f"shard {j} overrun"
+
+
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
 def test_masked_micro_step_edge_masks(P, save):
     """all-masked rows (the orchestrator's padding batches, batch.py:153-161), a single active token, and an all-active row
