@@ -96,6 +96,8 @@ struct GemmParams {
   int32_t peer_rows;
   int32_t m_rot;
   int32_t peer_row0;  // global row of row 0 of this GEMM's C (a vocab chunk of the d_weight GEMM starts inside some owner's range)
+  int32_t peer_nrows[8];  // rows owner j holds (the last owners of a torch.chunk layout may hold fewer than peer_rows)
+  float* peer_ptr[8];     // the same accumulators as raw pointers: slabs that straddle two owners leave through red.global
   CUtensorMap tma_c_peer[8];
   EpiParams epi;
 };
@@ -656,6 +658,28 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
             } else {
               if (row_ok && !(e.flags & ST_DEBUG_SKIP)) store_chunk(v, e, row, c0, n_valid);
             }
+          } else if (EPI == EPI_STORE && p.n_peers > 0 && (p.peer_row0 + row0_warp) % p.peer_rows + 32 > p.peer_rows &&
+                     (p.peer_row0 + row0_warp) / p.peer_rows + 1 < p.n_peers) {
+            // ---- fused reduce-scatter, a 32-row slab that straddles two owners (peer_rows not a multiple of 32; at most one slab
+            // per owner boundary and column chunk): every lane adds its own row into whichever owner holds it, 16 bytes per
+            // red.global (a TMA box cannot be split, and negative box coordinates are not accepted by the reduce form)
+            const int g = p.peer_row0 + row0_warp + lane;
+            const int own = g / p.peer_rows;
+            const int loc = g - own * p.peer_rows;
+            if (own < p.n_peers && loc < p.peer_nrows[own]) {
+              float* dst = p.peer_ptr[own] + (int64_t)loc * e.ldc + c0;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                if (4 * q + 3 < n_valid) {
+                  ptx::red_add_v4_f32(dst + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                      __uint_as_float(v[4 * q + 3]));
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (4 * q + k < n_valid) atomicAdd(dst + 4 * q + k, __uint_as_float(v[4 * q + k]));
+                }
+              }
+            }
           } else if (C::kStaging > 0) {
             // ---- registers -> 128B-swizzled smem staging -> TMA store / reduce-add (full-line writes, no SM-side reads)
             // fp32: one 32 x 32 box per chunk.  bf16: two chunks share one 64 x 32 box (128 B per row).
@@ -698,15 +722,12 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
                 const int32_t col = (int32_t)(out_bf16 ? (n0 + (ch & ~1) * 32) : c0);
                 const bool reduce = (EPI == EPI_STORE) && (e.flags & ST_LOAD_F32);
                 if (EPI == EPI_STORE && p.n_peers > 0) {
-                  // fused reduce-scatter: add this 32-row slab into its owner's fp32 accumulator (local or NVLink peer memory).
-                  // Rows beyond the owner's range are clipped by its tensor map; a slab that straddles two owners (peer_rows not
-                  // a multiple of 32) is sent to both, the second time at a NEGATIVE row coordinate so that only its tail lands.
+                  // fused reduce-scatter: add this 32-row slab into its owner's fp32 accumulator (local or NVLink peer memory);
+                  // rows beyond the owner's range are clipped by its tensor map (slabs that straddle two owners took the
+                  // red.global path above)
                   const int g0 = p.peer_row0 + row0_warp;
                   const int owner = g0 / p.peer_rows;
-                  const int local = g0 - owner * p.peer_rows;
-                  if (owner < p.n_peers) ptx::tma_reduce_add_2d(&p.tma_c_peer[owner], src, col, local);
-                  if (local + 32 > p.peer_rows && owner + 1 < p.n_peers)
-                    ptx::tma_reduce_add_2d(&p.tma_c_peer[owner + 1], src, col, local - p.peer_rows);
+                  if (owner < p.n_peers) ptx::tma_reduce_add_2d(&p.tma_c_peer[owner], src, col, g0 - owner * p.peer_rows);
                 } else if (p.hint_c == 0) {
                   if (reduce)
                     ptx::tma_reduce_add_2d(&p.tma_c, src, col, row0_warp);

@@ -586,6 +586,8 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
     for (int j = 0; j < peers->n; ++j) {
       rc = make_output_map(&p.tma_c_peer[j], peers->ptrs[j], peers->rows_per_peer, H, H, true);
       if (rc) return rc;
+      p.peer_nrows[j] = (int32_t)peers->rows_per_peer;
+      p.peer_ptr[j] = reinterpret_cast<float*>(peers->ptrs[j]);
     }
     set_scatter_rotation(p, peers->n, peers->rows_per_peer, peers->self);
     set_hints(p, "DH", 0, 0, 0);
@@ -678,6 +680,8 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
         }
         rc = make_output_map(&p.tma_c_peer[j], dw_peers->ptrs[j], rows_here, H, H, true);
         if (rc) return rc;
+        p.peer_nrows[j] = (int32_t)rows_here;
+        p.peer_ptr[j] = reinterpret_cast<float*>(dw_peers->ptrs[j]);
       }
     } else if (d_weight_dtype == PRL_DT_F32) {
       p.epi.c_f32 = reinterpret_cast<float*>(d_weight) + c0 * H;

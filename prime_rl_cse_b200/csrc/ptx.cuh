@@ -125,6 +125,10 @@ __device__ __forceinline__ void tma_reduce_add_2d_hint(const CUtensorMap* map, c
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(policy)
                : "memory");
 }
+// 16-byte fp32 reduction into global memory (local or NVLink peer), no return value
+__device__ __forceinline__ void red_add_v4_f32(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
