@@ -293,8 +293,12 @@ class Runner:
         self.acc, self.acc_note = None, "local fp32 accumulator + ncclReduceScatter once per step"
         if dist is not None and world <= 8 and getattr(args, "fused_dw_sync", 1):
             try:
-                self.acc = P.ShardedGradAccumulator(V, H, dev)
-                self.acc_note = "accumulated in the reduce-scattered layout inside the d_weight GEMM epilogue (TMA reduce-add into the owner's shard over NVLink), barrier at step end"
+                every = int(args.fused_dw_sync) == 2
+                self.acc = P.ShardedGradAccumulator(V, H, dev, every_micro_batch=every, local=None if every else self.main_grad)
+                self.acc_note = ("every micro-batch's d_weight GEMM epilogue adds its tiles straight into the owner's shard (TMA reduce-add over NVLink; no "
+                                 "rank holds a [V, H] gradient), barrier at step end" if every else
+                                 "local fp32 accumulation; the LAST micro-batch's d_weight GEMM epilogue sends (local total + its tiles) straight into the "
+                                 "owner's shard (TMA reduce-add over NVLink, hidden behind that micro-batch's GEMMs), barrier at step end")
             except RuntimeError as e:
                 self.acc_note += f" (fused accumulation unavailable: {e})"[:200]
 
@@ -331,7 +335,7 @@ class Runner:
         last = None
         fused = self.acc is not None and not save
         if fused:
-            self.acc.begin_step()
+            self.acc.begin_step(self.n_mb)
         if save:
             self.ensure_saved_block()
         for i in range(self.n_mb):
@@ -350,7 +354,7 @@ class Runner:
                 P.lm_head_backward_saved_raw(hid, self.Wd, ids, lse, dlogp, inv, self.saved_blk, dweight=self.main_grad,
                                              dweight_accumulate=True, workspace=self.ws_bs)
             elif fused:
-                P.lm_head_backward_dw_scatter_raw(hid, self.Wd, ids, lse, dlogp, inv, self.acc, workspace=self.ws_b)
+                self.acc.accumulate(hid, self.Wd, ids, lse, dlogp, inv, workspace=self.ws_b)
             else:
                 P.lm_head_backward_raw(hid, self.Wd, ids, lse, dlogp, inv, dweight=self.main_grad, dweight_accumulate=True,
                                        workspace=self.ws_b)
@@ -367,7 +371,7 @@ class Runner:
         cur = torch.cuda.current_stream()
         fused = self.acc is not None and not save
         if fused:
-            self.acc.begin_step()
+            self.acc.begin_step(self.n_mb)
 
         def upload(i):
             src = wl["mbs"][i % len(wl["mbs"])]
@@ -436,10 +440,15 @@ class Runner:
         self.step_resident(False)
         torch.cuda.synchronize()
         got = self.acc.shard
-        t = torch.stack([(got - ref).norm() / ref.norm().clamp_min(1e-30), (got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)]).double()
+        vals = [(got - ref).norm() / ref.norm().clamp_min(1e-30), (got - ref).abs().max() / ref.abs().max().clamp_min(1e-30)]
+        self.step_e2e(False)  # the same step through the public API (rl_micro_step with main_grad=<the accumulator>)
+        torch.cuda.synchronize()
+        vals.append((self.acc.shard - ref).norm() / ref.norm().clamp_min(1e-30))
+        t = torch.stack(vals).double()
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return {"rel_l2": float(t[0]), "max_abs_over_max": float(t[1]), "ok": bool(float(t[0]) < 1e-5 and float(t[1]) < 1e-5),
-                "what": "every rank's shard after one step of the fused accumulation vs local fp32 accumulator + ncclReduceScatter on the same micro-batches (max over ranks)"}
+        return {"rel_l2": float(t[0]), "max_abs_over_max": float(t[1]), "rel_l2_public_api": float(t[2]),
+                "ok": bool(float(t[0]) < 1e-5 and float(t[1]) < 1e-5 and float(t[2]) < 1e-5),
+                "what": "every rank's shard after one step of the fused accumulation (raw C-ABI loop, and rl_micro_step) vs local fp32 accumulator + ncclReduceScatter on the same micro-batches (max over ranks)"}
 
     def step_resident_classic(self):
         """one step with the local fp32 accumulator and the NCCL reduce-scatter (reference for dw_sync_check)"""
@@ -1087,8 +1096,9 @@ def main():
     ap.add_argument("--lm-head-backward", default="both", choices=["both", "saved", "recompute"],
                     help="both (default): time the recompute backward (headline) and the saved-logits backward (modes.saved_logits); "
                          "recompute / saved: only that one")
-    ap.add_argument("--fused-dw-sync", type=int, default=1, help="N>1, recompute mode: 1 = accumulate d_W_lm in the reduce-scattered layout "
-                    "inside the GEMM epilogue over peer memory (no step-end collective), 0 = local accumulator + ncclReduceScatter")
+    ap.add_argument("--fused-dw-sync", type=int, default=1, help="N>1, recompute mode: 1 = the last micro-batch's d_weight GEMM epilogue sends "
+                    "(local total + its tiles) into the owners' shards over peer memory (no step-end collective), 2 = every micro-batch adds "
+                    "straight into the owners' shards (no [V, H] gradient per rank), 0 = local accumulator + ncclReduceScatter")
     ap.add_argument("--fused-rs", type=int, default=1, help="vocab-sharded workload: 1 = d_hidden reduce-scatter fused into the GEMM "
                     "epilogue over peer memory, 0 = NCCL reduce-scatter after the GEMM")
     args = ap.parse_args()

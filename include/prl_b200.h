@@ -192,12 +192,15 @@ int prl_lmhead_bwd_scatter(const void* hidden, const void* weight, const int64_t
  * their tensor maps.  Ranks start at different vocab chunks so that they add into different owners at any time.  No step-end
  * collective is left (a barrier before the shards are read), and no rank holds a full [V, H] gradient.  The order in which the
  * ranks' addends reach a shard is not fixed: results are reproducible to fp32 rounding, not bit for bit.  d_hidden as in
- * prl_lmhead_bwd (local).  The caller zeroes its shard and synchronises the ranks before the first micro-batch of a step. */
+ * prl_lmhead_bwd (local).  The caller zeroes its shard and synchronises the ranks before the first scattering micro-batch.
+ * local_accumulator (fp32 [V, H], may be NULL): added tile by tile to what is sent -- so a trainer can accumulate the first
+ * n - 1 micro-batches of a step locally (prl_lmhead_bwd, accumulate_dw) and let the LAST micro-batch's d_weight GEMM send
+ * (local total + its own tiles): the NVLink traffic of one reduce-scatter per step, hidden behind that micro-batch's GEMMs. */
 int prl_lmhead_bwd_dw_scatter(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp,
                               int64_t T, int32_t H, int64_t V, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden,
                               int32_t d_hidden_f32, void* const* d_weight_shards, int32_t n_peers, int64_t rows_per_peer,
-                              int32_t self_index, int64_t vchunk, int32_t phase_mask, void* workspace, size_t workspace_bytes,
-                              void* stream);
+                              int32_t self_index, const float* local_accumulator, int64_t vchunk, int32_t phase_mask,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Peer memory for prl_lmhead_bwd_scatter (the ONLY entry points that own device memory: an accumulator that other processes
  * map has to be a whole allocation of its own).  prl_ipc_alloc: cudaMalloc `bytes` on the current device and export it

@@ -66,7 +66,7 @@ _SIGNATURES = {
     "prl_lmhead_bwd_dw_scatter": (
         c_int32,
         [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, c_int32, c_int32, c_void_p, c_int32,
-         c_void_p, c_int32, c_int64, c_int32, c_int64, c_int32, c_void_p, c_size_t, c_void_p],
+         c_void_p, c_int32, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_size_t, c_void_p],
     ),
     "prl_ipc_alloc": (c_int32, [c_size_t, c_void_p, c_void_p]),
     "prl_ipc_free": (c_int32, [c_void_p]),

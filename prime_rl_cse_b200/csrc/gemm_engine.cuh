@@ -41,6 +41,8 @@ constexpr int ST_STORE_F32 = 2;   // write fp32 to c_f32
 constexpr int ST_STORE_BF16 = 4;  // write bf16 to c_bf16
 constexpr int ST_LOAD_BF16 = 8;   // C += existing bf16 at c_bf16
 constexpr int ST_TMA = 16;         // epilogue writes through smem staging + TMA store / reduce-add (tma_c)
+constexpr int ST_ADD_LOCAL = 32;   // fused scatter: add the caller's LOCAL fp32 accumulator tile (c_f32, ldc) to the tile before it
+                                   // leaves for its owner (the last micro-batch of a step sends local total + its own contribution)
 // Profiling aids, compiled in only with -DPRL_DEBUG_KNOBS (they give WRONG results by design); in the release build the flags are
 // 0 and every branch on them folds away.
 #ifdef PRL_DEBUG_KNOBS
@@ -637,6 +639,23 @@ __global__ void __launch_bounds__(Cfg<CG, MS, EPI>::kThreads, 1) gemm_kernel(con
           ptx::tmem_ld_wait();
           const int64_t tj64 = tcol - c0;
           const int tj = (tj64 >= 0 && tj64 < 32) ? (int)tj64 : -1;
+          if (EPI == EPI_STORE && (e.flags & ST_ADD_LOCAL) && row_ok) {
+            const float* src = e.c_f32 + row * e.ldc + c0;
+            if (n_valid == 32) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 x = __ldcs(reinterpret_cast<const float4*>(src) + q);  // read once, streaming
+                v[4 * q + 0] = __float_as_uint(__uint_as_float(v[4 * q + 0]) + x.x);
+                v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + x.y);
+                v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + x.z);
+                v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + x.w);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < n_valid) v[j] = __float_as_uint(__uint_as_float(v[j]) + src[j]);
+            }
+          }
           if (EPI == EPI_STATS) {
             if (e.flags & ST_DEBUG_SKIP) {
               st.s += __uint_as_float(v[0]) + __uint_as_float(v[31]);  // profiling aid: keep the TMEM load alive, skip the statistics

@@ -550,6 +550,7 @@ struct PeerScatter {
   int64_t rows_per_peer;
   int32_t self;           // this rank's index (sets the m-tile / vocab-chunk rotation)
   int64_t total_rows;     // d_weight scatter: rows of the whole matrix (the last owners may hold fewer than rows_per_peer)
+  const float* local_add; // d_weight scatter: this rank's local fp32 [total_rows, H] accumulator to add on the way out (or NULL)
 };
 
 // Fused reduce-scatter: rows [j * rows_per_peer, ..) of the output belong to peer j; rank `self` starts at the tiles of the NEXT
@@ -668,6 +669,10 @@ static int lmhead_bwd_gemms(const void* hidden, const __nv_bfloat16* W, const __
       // gradient accumulation straight into the reduce-scattered layout: the rows of this chunk are reduce-added (fp32) into the
       // shards of the ranks that own them; a chunk spans at most a few owners
       p.epi.flags = ST_STORE_F32 | ST_LOAD_F32 | ST_TMA;
+      if (dw_peers->local_add) {  // send (local accumulator + this micro-batch's tile): the step's total leaves in ONE pass
+        p.epi.flags |= ST_ADD_LOCAL;
+        p.epi.c_f32 = const_cast<float*>(dw_peers->local_add) + c0 * H;
+      }
       p.n_peers = dw_peers->n;
       p.peer_rows = (int32_t)dw_peers->rows_per_peer;
       p.peer_row0 = (int32_t)c0;
@@ -813,15 +818,16 @@ int prl_lmhead_bwd_scatter(const void* hidden, const void* weight, const int64_t
   PRL_REQUIRE(T == rows_per_peer * n_peers, PRL_ERR_BAD_ARG, "lmhead_bwd_scatter: T must be n_peers * rows_per_peer");
   PRL_REQUIRE(epi_tma_enabled(), PRL_ERR_UNSUPPORTED, "lmhead_bwd_scatter needs the TMA-store epilogue (PRL_EPI_TMA=1)");
   for (int j = 0; j < n_peers; ++j) PRL_REQUIRE(d_hidden_peers[j], PRL_ERR_BAD_ARG, "lmhead_bwd_scatter: null peer pointer");
-  PeerScatter ps = {d_hidden_peers, n_peers, rows_per_peer, self_index, T};
+  PeerScatter ps = {d_hidden_peers, n_peers, rows_per_peer, self_index, T, nullptr};
   return lmhead_bwd_impl(hidden, weight, ids, lse, dlogp, T, H, V, v_offset, inv_temp, shift, round_bf16, nullptr, 1, d_weight, d_weight_dtype,
                          accumulate_dw, vchunk, phase_mask, workspace, workspace_bytes, stream, &ps);
 }
 
 int prl_lmhead_bwd_dw_scatter(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp, int64_t T,
                               int32_t H, int64_t V, float inv_temp, int32_t shift, int32_t round_bf16, void* d_hidden, int32_t d_hidden_f32,
-                              void* const* d_weight_shards, int32_t n_peers, int64_t rows_per_peer, int32_t self_index, int64_t vchunk,
-                              int32_t phase_mask, void* workspace, size_t workspace_bytes, void* stream) {
+                              void* const* d_weight_shards, int32_t n_peers, int64_t rows_per_peer, int32_t self_index,
+                              const float* local_accumulator, int64_t vchunk, int32_t phase_mask, void* workspace, size_t workspace_bytes,
+                              void* stream) {
   PRL_REQUIRE(d_weight_shards && n_peers >= 1 && n_peers <= 8 && self_index >= 0 && self_index < n_peers, PRL_ERR_BAD_ARG,
               "lmhead_bwd_dw_scatter: 1..8 peers");
   PRL_REQUIRE(rows_per_peer >= 32 && rows_per_peer < ((int64_t)1 << 31) && rows_per_peer * n_peers >= V && V < ((int64_t)1 << 31),
@@ -829,7 +835,8 @@ int prl_lmhead_bwd_dw_scatter(const void* hidden, const void* weight, const int6
   PRL_REQUIRE(epi_tma_enabled(), PRL_ERR_UNSUPPORTED, "lmhead_bwd_dw_scatter needs the TMA-store epilogue (PRL_EPI_TMA=1)");
   for (int j = 0; j < n_peers; ++j)
     PRL_REQUIRE(d_weight_shards[j] || (int64_t)j * rows_per_peer >= V, PRL_ERR_BAD_ARG, "lmhead_bwd_dw_scatter: null shard pointer");
-  PeerScatter ps = {d_weight_shards, n_peers, rows_per_peer, self_index, V};
+  PRL_REQUIRE((reinterpret_cast<uintptr_t>(local_accumulator) & 15) == 0, PRL_ERR_BAD_ARG, "lmhead_bwd_dw_scatter: local accumulator must be 16-byte aligned");
+  PeerScatter ps = {d_weight_shards, n_peers, rows_per_peer, self_index, V, local_accumulator};
   return lmhead_bwd_impl(hidden, weight, ids, lse, dlogp, T, H, V, 0, inv_temp, shift, round_bf16, d_hidden, d_hidden_f32, nullptr, PRL_DT_F32, 1,
                          vchunk, phase_mask, workspace, workspace_bytes, stream, nullptr, &ps);
 }

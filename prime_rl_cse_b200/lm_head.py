@@ -199,22 +199,25 @@ def lm_head_backward_raw(hidden, weight, ids, lse, dlogp, inv_temp, shift=True, 
 
 
 def lm_head_backward_dw_scatter_raw(hidden, weight, ids, lse, dlogp, inv_temp, acc, shift=True, round_bf16=True, want_dhidden=True,
-                                    vchunk=0, dhidden_f32=False, phase_mask=0, workspace=None):
+                                    vchunk=0, dhidden_f32=False, phase_mask=0, workspace=None, local_add=None):
     """Recompute backward whose d_weight GEMM adds its tiles straight into the ranks' shards of `acc` (a
-    `peer.ShardedGradAccumulator`: d_W_lm accumulated in the reduce-scattered layout, no step-end collective).  Returns d_hidden."""
+    `peer.ShardedGradAccumulator`: d_W_lm delivered in the reduce-scattered layout, no step-end collective).  `local_add`
+    (fp32 [V, H]): a local accumulator whose tiles are added to what is sent.  Returns d_hidden."""
     _check_operands(hidden, weight, ids, "lm_head_backward_dw_scatter_raw", lse=lse, dlogp=dlogp)
     lib = _lib.load()
     T, H = hidden.shape
     V = weight.shape[0]
     if V != acc.V or H != acc.H:
         raise ValueError(f"accumulator is for a [{acc.V}, {acc.H}] gradient, the weight is [{V}, {H}]")
+    if local_add is not None and (local_add.dtype != torch.float32 or tuple(local_add.shape) != (V, H) or not local_add.is_contiguous()):
+        raise ValueError("local_add must be a contiguous fp32 [V, H] tensor")
     dh = torch.empty(T, H, dtype=torch.float32 if dhidden_f32 else torch.bfloat16, device=hidden.device) if want_dhidden else None
     nb = lib.prl_lmhead_bwd_workspace_bytes(T, H, V, vchunk)
     ws = workspace if workspace is not None and workspace.numel() >= nb else _ws(nb, hidden.device)
     rc = lib.prl_lmhead_bwd_dw_scatter(_lib.ptr(hidden), _lib.ptr(weight), _lib.ptr(ids), _lib.ptr(lse), _lib.ptr(dlogp), T, H, V,
                                        float(inv_temp), 1 if shift else 0, 1 if round_bf16 else 0, _lib.ptr(dh), 1 if dhidden_f32 else 0,
-                                       acc.buf.ptrs, acc.world, acc.rows_per_peer, acc.rank, vchunk, phase_mask, _lib.ptr(ws), ws.numel(),
-                                       _lib.stream())
+                                       acc.buf.ptrs, acc.world, acc.rows_per_peer, acc.rank, _lib.ptr(local_add), vchunk, phase_mask,
+                                       _lib.ptr(ws), ws.numel(), _lib.stream())
     _lib.check(rc, "prl_lmhead_bwd_dw_scatter")
     return dh
 
@@ -298,8 +301,8 @@ class _FusedLMHead(torch.autograd.Function):
         dw_target = main_grad if (main_grad is not None and need_w) else None
 
         def run(h, i, l, gg, sh, block):
-            if _is_sharded_accumulator(dw_target):  # tiles go straight into the owners' shards (no local [V, H] gradient)
-                return lm_head_backward_dw_scatter_raw(h, w2, i, l, gg, inv_temp, dw_target, sh, round_bf16, want_dhidden=need_h), None
+            if _is_sharded_accumulator(dw_target):  # d_weight goes to the owners' shards (directly, or through the local total)
+                return dw_target.accumulate(h, w2, i, l, gg, inv_temp, sh, round_bf16, want_dhidden=need_h), None
             kw = dict(want_dhidden=need_h, dweight=dw_target, dweight_accumulate=dw_target is not None, want_dweight=need_w)
             if block is not None:
                 return lm_head_backward_saved_raw(h, w2, i, l, gg, inv_temp, block, sh, **kw)
@@ -315,6 +318,8 @@ class _FusedLMHead(torch.autograd.Function):
                 dh_c, dw = run(h2[:n], i2[:n], lse[:n], g_p, False, saved)
             elif need_w and dw_target is None:
                 dw = torch.zeros_like(w2)
+            elif _is_sharded_accumulator(dw_target):
+                dw_target.skip(w2)  # nothing to add, but the micro-batch counts towards the accumulator's step schedule
             if need_h:
                 dh = rows.scatter_rows(dh_c if n > 0 else None, part, n, w2.shape[1])
             if dw_target is not None:

@@ -1029,6 +1029,18 @@ def test_d_weight_scatter_into_owner_shards_emulated_on_one_gpu(P, T, H, V, peer
     assert got.shape == want.shape and torch.equal(got, want)
     for j, b in enumerate(bufs):
         assert float((b[shards[j].shape[0]:] - 7.0).abs().max()) == 0.0, f"shard {j} overrun"
+    # the "last micro-batch sends the local total" schedule: the shards receive local accumulator + this micro-batch's tiles
+    for b, s_ in zip(bufs, shards):
+        b[: s_.shape[0]].zero_()
+    local = want.clone()  # stands for the first n - 1 micro-batches of a step
+    g = torch.randn(T, device="cuda") / T
+    _, _, lse, _ = lm_head_forward_raw(h, w, i, 1.0)
+    lm_head_backward_dw_scatter_raw(h, w, i, lse, g, 1.0, acc, vchunk=vchunk, local_add=local, want_dhidden=False)
+    lm_head_backward_raw(h, w, i, lse, g, 1.0, dweight=want, dweight_accumulate=True, vchunk=vchunk, want_dhidden=False)
+    got = torch.cat([b[: shards[j].shape[0]] for j, b in enumerate(bufs)])
+    assert ((got - want).abs().max() / want.abs().max()).item() < 1e-6  # (local + tile) + 0 vs local + tile: same sum, fp32
+    for j, b in enumerate(bufs):
+        assert float((b[shards[j].shape[0]:] - 7.0).abs().max()) == 0.0, f"shard {j} overrun"
 
 
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
