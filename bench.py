@@ -654,7 +654,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
-    if world > 1:
+    # the vocab-sharded workload also runs as a single torchrun rank (one shard = the whole vocabulary): its exchange steps,
+    # the peer-memory epilogue and the ragged-row padding are then exercised on a one-GPU box too
+    if world > 1 or (args.workload == "qwen3-32b-vocab8" and "RANK" in os.environ):
         import torch.distributed as dist_mod
 
         dist = dist_mod
@@ -740,7 +742,8 @@ def run_vocab_sharded(args, rank, world, dev, dist):
     from prime_rl_cse_b200.parallel import VocabShardedLMHead
 
     if dist is None:
-        raise SystemExit("--workload qwen3-32b-vocab8 needs torchrun with >= 2 ranks (python bench.py --gpus N --workload qwen3-32b-vocab8)")
+        raise SystemExit("--workload qwen3-32b-vocab8 runs under torchrun (python bench.py --gpus N --workload qwen3-32b-vocab8, N >= 2; "
+                         "or one rank: python -m torch.distributed.run --nproc-per-node 1 bench.py --workload qwen3-32b-vocab8)")
     H, V, T, nseg, n_mb, group, ratio_type = SHAPES[args.workload]
     n_mb = args.micro_batches if args.micro_batches > 0 else n_mb
     peaks = measured_peaks()
@@ -769,6 +772,8 @@ def run_vocab_sharded(args, rank, world, dev, dist):
     loss_host = torch.empty(n_mb, dtype=torch.float32).pin_memory()
 
     parity = vocab_sharded_parity(P, dist, head, mbs[0], W_full, seg, world, dev)
+    parity["ragged_rows"] = vocab_sharded_parity(P, dist, head, mbs[0], W_full, seg, world, dev, ragged=True)
+    parity["ok"] = bool(parity["ok"] and parity["ragged_rows"]["ok"])
     main_grad.zero_()
     torch.cuda.empty_cache()
 
@@ -858,25 +863,37 @@ def run_vocab_sharded(args, rank, world, dev, dist):
     }
 
 
-def vocab_sharded_parity(P, dist, head, mb, W_full, seg, world, dev):
+def vocab_sharded_parity(P, dist, head, mb, W_full, seg, world, dev, ragged: bool = False):
     """One round of the vocab-sharded head from a zeroed d_W accumulator against the UNSHARDED fused path on this GPU (same
-    kernels, full W): every rank checks its own tokens' log-probs / entropy / d_hidden and its d_W shard; max over ranks."""
+    kernels, full W): every rank checks its own tokens' log-probs / entropy / d_hidden and its d_W shard; max over ranks.
+    `ragged`: every rank keeps a different number of tokens of its row (packed rows are not padded, batch.py:115-116) and the
+    head pads them to the common length (`pad_to`)."""
     from prime_rl_cse_b200.loss import _loss_packed_raw
 
     T, V, H = mb["input_ids"].shape[1], W_full.shape[0], W_full.shape[1]
+    n, pad_to = T, None
+    if ragged:
+        n, pad_to = max(T - 96 * (dist.get_rank() + 1) - 5, 2), T
+        mb = {k: (v[:, :n].contiguous() if torch.is_tensor(v) else v) for k, v in mb.items()}
+        mb["position_ids"] = torch.arange(n, device=dev).unsqueeze(0)
+        seg = [n]
     tau = float(mb["temperature"])
     head.main_grad.zero_()
     cfg = P.LossConfig(ratio_type="token", ratio_length_norm=False, clip_ratio=8.0)
-    out = head.micro_step(mb["hidden"], mb, cfg, T)
-    gathered = head.gather_inputs(mb["hidden"], mb["input_ids"])
+    out = head.micro_step(mb["hidden"], mb, cfg, n, pad_to=pad_to)
+    gathered = head.gather_inputs(mb["hidden"], mb["input_ids"], pad_to)
     torch.cuda.current_stream().wait_event(gathered["ready"])
     lp_u, ent_u, lse_u, _ = P.lm_head_forward_raw(mb["hidden"][0], W_full, mb["input_ids"][0], 1.0 / tau)
     cu = torch.tensor([0] + list(torch.tensor(seg).cumsum(0)), dtype=torch.int32, device=dev)
     _, _, _, _, g_u = _loss_packed_raw(lp_u, mb["logprobs"][0], mb["advantages"][0], mb["loss_mask"][0].view(torch.uint8), cu, len(seg), 0,
-                                       False, 8.0, T)
+                                       False, 8.0, n)
     dh_u, _ = P.lm_head_backward_raw(mb["hidden"][0], W_full, mb["input_ids"][0], lse_u, g_u, 1.0 / tau, want_dweight=False)
     # unsharded d_W needs every rank's tokens: gather (lse, dlogp) of all ranks, run the unsharded backward over world*T tokens
-    pair = torch.stack([lse_u, g_u], dim=1).contiguous()
+    # (padded positions of a ragged row: zero hidden rows with dlogp = 0, which add exact zeros)
+    pair = torch.zeros(T, 2, device=dev)
+    pair[:, 0] = math.log(V)
+    pair[:n, 0] = lse_u
+    pair[:n, 1] = g_u
     pair[0, 1] = 0.0
     pair_all = torch.empty(world * T, 2, device=dev)
     dist.all_gather_into_tensor(pair_all, pair)
@@ -892,7 +909,8 @@ def vocab_sharded_parity(P, dist, head, mb, W_full, seg, world, dev):
     dist.all_reduce(par, op=dist.ReduceOp.MAX)
     return {"max_abs_dlogp": float(par[0]), "max_abs_dentropy": float(par[1]), "rel_l2_d_hidden": float(par[2]), "rel_l2_d_weight_shard": float(par[3]),
             "ok": bool(par[0] < 1e-3 and par[1] < 1e-3 and par[2] < 1e-2 and par[3] < 1e-2),
-            "what": f"{world}-rank vocab-sharded round vs the unsharded fused path on each rank's own tokens (max over ranks)"}
+            "what": f"{world}-rank vocab-sharded round vs the unsharded fused path on each rank's own tokens (max over ranks)"
+                    + (f"; ragged rows: rank r keeps {T} - 96 (r + 1) - 5 tokens, padded to {T} inside the head" if ragged else "")}
 
 
 def vocab_sharded_check(P, dist, rn, world, rank, dev, T=2048):

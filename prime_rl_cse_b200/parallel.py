@@ -19,7 +19,13 @@ import torch.distributed as dist
 from . import _lib
 from .peer import PeerBuffer, ShardedGradAccumulator  # noqa: F401  (re-exported)
 from .lm_head import (lm_head_backward_raw, lm_head_backward_saved_raw, lm_head_forward_raw, lm_head_forward_save_raw,
-                      saved_logits_policy)
+                      saved_logits_policy, _warn_fallback)
+from .rows import first_row_values
+
+
+def rows_first_lse(V: int) -> float:
+    """lse of a position whose logits are all zero (zero hidden row): ln V"""
+    return first_row_values(V)[2]
 
 
 # --------------------------------------------------------------------------- token sharding (host logic)
@@ -78,6 +84,7 @@ class _VocabParallelLMHead(torch.autograd.Function):
                 _, _, _, parts, ctx.saved_logits = lm_head_forward_save_raw(h2, w2, i2, inv_temp, shift, v_offset=v_offset,
                                                                             v_total=v_total, want_partials=True)
             except torch.OutOfMemoryError:
+                _warn_fallback(f"no room for the {T} x {w2.shape[0]} bf16 logits block of this vocab shard")
                 save = False
         if w2.shape[0] > 0 and not save:
             _, _, _, parts = lm_head_forward_raw(h2, w2, i2, inv_temp, shift, round_bf16, v_offset=v_offset, v_total=v_total,
@@ -188,7 +195,10 @@ class VocabShardedLMHead:
                         the GEMM (fused_rs=False) or inside the d_hidden GEMM's epilogue, tile by tile, as TMA reduce-adds into
                         the owner's symmetric-memory accumulator over NVLink (fused_rs=True).
 
-    Every rank must bring the same number of tokens T per round (packed rows of `seq_len`)."""
+    The exchanges need the same row length on every rank.  Packed rows are NOT padded by the orchestrator (batch.py:115-116:
+    T = sum of the sample lengths <= seq_len), so `gather_inputs(..., pad_to=seq_len)` pads this rank's row to the common length
+    with zero hidden rows whose d loss / d logp is 0: they add exact zeros to d_W and d_hidden, and `forward` / `backward` /
+    `micro_step` return the local T tokens only.  Without `pad_to` every rank must bring the same T."""
 
     def __init__(self, weight_shard: torch.Tensor, vocab_size: int, group: dist.ProcessGroup | None = None, *,
                  main_grad: torch.Tensor | None = None, fused_rs: bool = False, round_bf16: bool = True):
@@ -213,11 +223,20 @@ class VocabShardedLMHead:
         self.timings = {}     # CUDA events of the last round's exchanges
 
     # -- inputs: all-gather of hidden and ids (can run ahead of the previous round's compute on the comm stream)
-    def gather_inputs(self, hidden_local: torch.Tensor, ids_local: torch.Tensor):
-        T, H = hidden_local.shape[-2], hidden_local.shape[-1]
+    def gather_inputs(self, hidden_local: torch.Tensor, ids_local: torch.Tensor, pad_to: int | None = None):
+        T_local, H = hidden_local.shape[-2], hidden_local.shape[-1]
         dev = hidden_local.device
-        h = hidden_local.detach().reshape(T, H).contiguous()
-        i = ids_local.detach().reshape(T).contiguous().to(torch.int64)
+        h = hidden_local.detach().reshape(T_local, H).contiguous()
+        i = ids_local.detach().reshape(T_local).contiguous().to(torch.int64)
+        T = T_local if pad_to is None else int(pad_to)
+        if T < T_local:
+            raise ValueError(f"pad_to = {T} is shorter than this rank's row of {T_local} tokens")
+        if T > T_local:  # ragged rows: zero hidden rows / token id 0 up to the common length (their dlogp is 0 in the backward)
+            h_pad = torch.zeros(T, H, dtype=h.dtype, device=dev)
+            h_pad[:T_local] = h
+            i_pad = torch.zeros(T, dtype=torch.int64, device=dev)
+            i_pad[:T_local] = i
+            h, i = h_pad, i_pad
         h_all = torch.empty(self.world * T, H, dtype=torch.bfloat16, device=dev)
         i_all = torch.empty(self.world * T, dtype=torch.int64, device=dev)
         cur = torch.cuda.current_stream()
@@ -229,7 +248,7 @@ class VocabShardedLMHead:
             ev.record(self.comm)
         for t in (h, i, h_all, i_all):
             t.record_stream(self.comm)
-        return dict(h_all=h_all, i_all=i_all, T=T, ready=ev)
+        return dict(h_all=h_all, i_all=i_all, T=T, T_local=T_local, ready=ev)
 
     def _workspace(self, key, nbytes, dev):
         ws = self._ws.get(key)
@@ -266,6 +285,10 @@ class VocabShardedLMHead:
         lse = torch.empty(T, dtype=torch.float32, device=dev)
         rc = lib.prl_lmhead_merge_partials(_lib.ptr(mine), W, T, _lib.ptr(logp), _lib.ptr(ent), _lib.ptr(lse), _lib.stream())
         _lib.check(rc, "prl_lmhead_merge_partials")
+        n = gathered.get("T_local", T)
+        if n < T:
+            gathered["lse_row"] = lse  # the padded positions' lse (ln V: zero logits) is what the backward sweep reads for them
+            return logp[:n], ent[:n], lse[:n]
         return logp, ent, lse
 
     def backward(self, gathered, temperature: float, lse_local: torch.Tensor, dlogp_local: torch.Tensor, vchunk: int = 0):
@@ -274,6 +297,17 @@ class VocabShardedLMHead:
         h_all, i_all = gathered["h_all"], gathered["i_all"]
         dev = h_all.device
         inv = 1.0 / float(temperature)
+        n = gathered.get("T_local", T)
+        if lse_local.numel() != n or dlogp_local.numel() != n:
+            raise ValueError(f"lse / dlogp must cover this rank's {n} tokens")
+        if n < T:  # ragged row: padded positions carry dlogp = 0 (exact-zero dlogits rows) and the forward's own lse
+            g_row = torch.zeros(T, dtype=torch.float32, device=dev)
+            g_row[:n] = dlogp_local.reshape(-1)
+            lse_row = gathered.get("lse_row")
+            if lse_row is None:
+                lse_row = torch.full((T,), rows_first_lse(self.V), dtype=torch.float32, device=dev)
+                lse_row[:n] = lse_local.reshape(-1)
+            lse_local, dlogp_local = lse_row, g_row
         if self.fused_rs:
             # the owner's accumulator must be zero before any peer's d_hidden GEMM adds into it: zeroed HERE, i.e. before this
             # rank enters the all-gather below, which no rank can leave before every rank has entered it
@@ -290,7 +324,7 @@ class VocabShardedLMHead:
         if self.main_grad is None:
             self.main_grad = torch.zeros(self.v1 - self.v0, self.H, dtype=torch.float32, device=dev)
         if self.fused_rs:
-            return self._backward_fused(gathered, inv, lse_all, g_all, vchunk, ws)
+            return self._backward_fused(gathered, inv, lse_all, g_all, vchunk, ws)[:n]
         dh_part, _ = lm_head_backward_raw(h_all, self.W, i_all, lse_all, g_all, inv, True, self.round_bf16, v_offset=self.v0,
                                           dweight=self.main_grad, dweight_accumulate=True, vchunk=vchunk, dhidden_f32=True, workspace=ws)
         dh_local = torch.empty(T, self.H, dtype=torch.float32, device=dev)
@@ -299,7 +333,7 @@ class VocabShardedLMHead:
         dist.reduce_scatter_tensor(dh_local, dh_part, group=self.group)  # partial sums over vocab shards -> token owners
         r1.record()
         self.timings["d_hidden_reduce_scatter"] = (r0, r1)
-        return dh_local.to(torch.bfloat16)
+        return dh_local[:n].to(torch.bfloat16)
 
     # -- fused reduce-scatter: peer-mapped fp32 accumulators, one per rank, written by every rank's d_hidden epilogue
     def _peer_accumulator(self, T: int, dev) -> torch.Tensor:
@@ -339,15 +373,16 @@ class VocabShardedLMHead:
             self._sym.close()
             self._sym = None
 
-    def micro_step(self, hidden_local, micro_batch, loss_config, loss_scale, gathered=None):
+    def micro_step(self, hidden_local, micro_batch, loss_config, loss_scale, gathered=None, pad_to=None):
         """One round from this rank's point of view (train.py:285-310 with the head vocab-sharded): returns loss, logprobs,
-        entropy, d_hidden of the LOCAL micro-batch; the d_W shard is accumulated into `main_grad`."""
+        entropy, d_hidden of the LOCAL micro-batch; the d_W shard is accumulated into `main_grad`.  `pad_to` (= seq_len): the
+        common row length when the ranks' packed rows differ in length (see the class docstring)."""
         from .loss import compute_loss
         from .segments import get_response_lengths
 
         ids = micro_batch["input_ids"]
         if gathered is None:
-            gathered = self.gather_inputs(hidden_local, ids)
+            gathered = self.gather_inputs(hidden_local, ids, pad_to)
         lengths = get_response_lengths(micro_batch["position_ids"])
         tau = micro_batch["temperature"]
         logp, ent, lse = self.forward(gathered, tau)

@@ -261,8 +261,30 @@ def test_vocab_sharded_rounds_two_gpus(fused):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
-    assert d["parity_vs_unsharded"]["ok"], d["parity_vs_unsharded"]
+    assert d["parity_vs_unsharded"]["ok"] and d["parity_vs_unsharded"]["ragged_rows"]["ok"], d["parity_vs_unsharded"]
     assert d["value"] > 0 and d["n_gpus"] == 2
+
+
+@pytest.mark.parametrize("fused", [0, 1], ids=["nccl-reduce-scatter", "fused-epilogue-reduce-scatter"])
+def test_vocab_sharded_rounds_single_rank(fused):
+    """The same rounds as ONE torchrun rank (the shard is the whole vocabulary), so that a one-GPU box also runs
+    VocabShardedLMHead end to end: the exchange steps, the peer-memory accumulator of the fused epilogue, and the ragged-row
+    padding (`pad_to`: packed rows are not padded by the orchestrator, batch.py:115-116) -- bench.py's parity records against the
+    unsharded path, equal and ragged rows, must be green."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1", "--master-addr", "127.0.0.1",
+           "--master-port", "29573", os.path.join(root, "bench.py"), "--gpus", "1", "--workload", "qwen3-32b-vocab8", "--fused-rs", str(fused),
+           "--micro-batches", "1", "--steps", "1", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["parity_vs_unsharded"]["ok"] and d["parity_vs_unsharded"]["ragged_rows"]["ok"], d["parity_vs_unsharded"]
+    assert d["value"] > 0 and d["n_gpus"] == 1
 
 
 def test_micro_step_vs_torch_reference_chain_on_gpu(P):
