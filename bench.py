@@ -8,8 +8,9 @@ A "step" is one pass of the hot path over one rank's share of a training batch a
 (configs[2], the config the metric is quoted on): 32 packed micro-batches of [1, 16384] tokens (4 x 4096-token rollouts
 each), hidden 4096, vocab 151936, bf16 -- per micro-batch: fused LM-head forward (log-probs + entropy), packed clipped-ratio
 loss, backward to d_hidden and d_W_lm (fp32 accumulation across micro-batches), plus the step's group advantages.  Weak
-scaling: every rank processes its own 32 micro-batches (token shards = FSDP ranks); for N > 1 the accumulated d_W_lm is
-reduce-scattered once per step over NCCL as FSDP2 does.
+scaling: every rank processes its own 32 micro-batches (token shards = FSDP ranks); for N > 1 the step also delivers d_W_lm in
+FSDP2's reduce-scattered layout -- by the last micro-batch's d_weight GEMM epilogue over NVLink peer memory in the recompute mode
+(`--fused-dw-sync`), by one ncclReduceScatter per step in the saved-logits mode.
 
 ONE run times BOTH backward modes of the LM head:
   * recompute (the HEADLINE: top-level `value`, `e2e`, `roofline`): BASELINE.json north_star's design -- the [T, V] logits
@@ -85,7 +86,7 @@ def algorithmic_bytes(kernel, T, H, V, vc):
 
 def ncu_traffic(mode: str, kernel: str, workload: str):
     """DRAM read+write bytes per launch of `kernel` from the newest committed ncu capture (profiles/*traffic.json, written by
-    tools/ncu_traffic.py from `ncu --set full` reports): {"bytes": ..., "source": ...} or None."""
+    tools/make_evidence.py from `ncu --set full` reports): {"bytes": ..., "source": ...} or None."""
     best = None
     pdir = os.path.join(ROOT, "profiles")
     if os.path.isdir(pdir):
