@@ -174,7 +174,8 @@ int prl_lmhead_bwd(const void* hidden, const void* weight, const int64_t* ids, c
  * reduce-added (fp32, cp.reduce.async.bulk.tensor performed at the owner's L2, over NVLink for remote owners) into
  * d_hidden_peers[owner][row - owner * rows_per_peer, :H], owner = row / rows_per_peer.  d_hidden_peers is a HOST array of
  * n_peers device pointers to fp32 [rows_per_peer, H] accumulators that are mapped into this process (CUDA IPC / symmetric
- * memory; entry self_index is this rank's own buffer; rows_per_peer need not be a multiple of 32).  The caller zeroes its accumulator and synchronises the peers before
+ * memory; entry self_index is this rank's own buffer; rows_per_peer must be a multiple of 32, so that a 32-row epilogue slab never
+ * straddles two owners: PRL_ERR_UNSUPPORTED otherwise).  The caller zeroes its accumulator and synchronises the peers before
  * the call, and again before reading the result.  Replaces the NCCL reduce-scatter that follows the
  * GEMM in the unfused path; everything else (dlogits recompute, d_weight shard) is as in prl_lmhead_bwd. */
 int prl_lmhead_bwd_scatter(const void* hidden, const void* weight, const int64_t* ids, const float* lse, const float* dlogp,

@@ -1043,6 +1043,53 @@ def test_d_weight_scatter_into_owner_shards_emulated_on_one_gpu(P, T, H, V, peer
         assert float((b[shards[j].shape[0]:] - 7.0).abs().max()) == 0.0, f"shard {j} overrun"
 
 
+@pytest.mark.parametrize("rows_per_peer,H,Vs,peers,self_index,vchunk", [(96, 64, 1000, 4, 1, 0), (32, 128, 640, 8, 7, 256), (544, 256, 18992, 3, 0, 0),
+                                                                          (160, 64, 333, 2, 1, 128)])
+def test_d_hidden_reduce_scatter_into_owner_buffers_emulated_on_one_gpu(P, rows_per_peer, H, Vs, peers, self_index, vchunk):
+    """prl_lmhead_bwd_scatter (config 4: the reduce-scatter of d_hidden fused into the GEMM epilogue) with the owners'
+    accumulators as separate buffers on ONE GPU: rows [j * rows_per_peer, (j + 1) * rows_per_peer) of the concatenated sweep must
+    land in owner j's buffer and nowhere else (canary rows behind every buffer), equal to the plain backward's fp32 d_hidden
+    partial of this vocab shard; the d_W shard is the plain one bit for bit; a second call accumulates (the owners zero their
+    buffers per round, not the kernel)."""
+    import ctypes
+
+    from prime_rl_cse_b200 import _lib, lm_head_backward_raw, lm_head_forward_raw
+
+    lib = _lib.load()
+    M, v0 = peers * rows_per_peer, 4096  # the shard covers vocab rows [v0, v0 + Vs) of a larger vocabulary
+    hidden, weight, _ = _mk(M, H, Vs, M + Vs + peers)
+    h, w = hidden.cuda(), weight.cuda()
+    ids = torch.randint(0, v0 + Vs + 500, (M,), generator=torch.Generator().manual_seed(5)).cuda()  # targets inside and outside the shard
+    g = (torch.randn(M, generator=torch.Generator().manual_seed(6)) / M).cuda()
+    g[::rows_per_peer] = 0.0  # position 0 of every owner's packed row (parallel.gather_token_scalars)
+    _, _, lse, _ = lm_head_forward_raw(h, w, ids, 1.0, v_offset=v0, v_total=v0 + Vs + 500)
+    lse = lse + 0.5  # stands for the merged lse over all shards (any value >= the shard's own)
+    want_dw = torch.zeros(Vs, H, device="cuda")
+    vc = vchunk if vchunk > 0 else (Vs + 255) // 256 * 256  # 0: the whole shard in one chunk, as VocabShardedLMHead.backward does
+    want_dh, _ = lm_head_backward_raw(h, w, ids, lse, g, 1.0, v_offset=v0, dweight=want_dw, dweight_accumulate=True, vchunk=vc, dhidden_f32=True)
+    bufs = [torch.cat([torch.zeros(rows_per_peer, H), torch.full((32, H), 7.0)]).cuda() for _ in range(peers)]
+    ptrs = (ctypes.c_void_p * peers)(*[b.data_ptr() for b in bufs])
+    dw = torch.zeros(Vs, H, device="cuda")
+    nb = lib.prl_lmhead_bwd_workspace_bytes(M, H, Vs, vc)
+    ws = torch.empty(max(int(nb), 16), dtype=torch.uint8, device="cuda")
+    for rep in (1, 2):
+        rc = lib.prl_lmhead_bwd_scatter(_lib.ptr(h), _lib.ptr(w), _lib.ptr(ids), _lib.ptr(lse), _lib.ptr(g), M, H, Vs, v0, 1.0, 1, 1, ptrs, peers,
+                                        rows_per_peer, self_index, _lib.ptr(dw), _lib.PRL_DT_F32, 1, vc, 0, _lib.ptr(ws), ws.numel(), _lib.stream())
+        _lib.check(rc, "prl_lmhead_bwd_scatter")
+        got = torch.cat([b[:rows_per_peer] for b in bufs])
+        # same products, but the fp32 addends of an element are combined in another order (the plain path may split K in two for
+        # few output tiles, vocab chunks arrive in tile order, and the tensor core truncates its accumulator per K = 16 step):
+        # equal to accumulation rounding -- a mis-routed slab would be an O(1) error
+        assert ((got - rep * want_dh).norm() / want_dh.norm().clamp_min(1e-30)).item() < 1e-4
+        for j, b in enumerate(bufs):
+            assert float((b[rows_per_peer:] - 7.0).abs().max()) == 0.0, f"owner {j} overrun"
+    assert ((dw - 2 * want_dw).abs().max() / want_dw.abs().max().clamp_min(1e-30)).item() < 1e-5
+    # a row count that is not a multiple of the 32-row epilogue slab is refused, not mis-routed
+    rc = lib.prl_lmhead_bwd_scatter(_lib.ptr(h), _lib.ptr(w), _lib.ptr(ids), _lib.ptr(lse), _lib.ptr(g), peers * 40, H, Vs, v0, 1.0, 1, 1, ptrs, peers, 40,
+                                    self_index, _lib.ptr(dw), _lib.PRL_DT_F32, 1, vc, 0, _lib.ptr(ws), ws.numel(), _lib.stream())
+    assert rc != 0
+
+
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
 def test_masked_micro_step_edge_masks(P, save):
     """all-masked rows (the orchestrator's padding batches, batch.py:153-161), a single active token, and an all-active row
