@@ -4,7 +4,7 @@
     python tools/make_evidence.py --tag r2 [--reports gpurun_out/r2_*.ncu-rep]
 
   profiles/<tag>_sass_mnemonics.txt      per-kernel SASS mnemonic counts of libprl_b200.so (tools/sass_mnemonics.py)
-  profiles/<tag>_sass/<kernel>.sass      full SASS listing of every kernel on the hot path (the GEMM instantiations the defaults
+  profiles/<tag>_sass/<kernel>.sass.gz   full SASS listing (gzip: 100-400 KB of text each) of every kernel on the hot path (the GEMM instantiations the defaults
                                          select, the saved-logits pass, loss / advantage / segment / row kernels)
   profiles/<tag>_ncu_<report>.txt        one line per captured launch: duration, tensor-pipe activity, DRAM bytes, L2 hit rate, ...
   profiles/<tag>_traffic.json            {workload: {mode: {kernel: {dram_bytes_per_launch, achieved_gbs, source}}}} per launch
@@ -12,6 +12,8 @@
 import argparse
 import csv
 import glob
+import gzip
+import io
 import json
 import os
 import re
@@ -52,6 +54,12 @@ def friendly(name: str):
     return m.group(1) if m else name
 
 
+def _gz_text(path):
+    """text file inside a gzip member without a timestamp or file name, so that regenerating identical content gives identical bytes"""
+    raw = open(path, "wb")
+    return io.TextIOWrapper(gzip.GzipFile(filename="", fileobj=raw, mode="wb", compresslevel=9, mtime=0), encoding="utf-8")
+
+
 def write_sass(tag):
     out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
     chunks = re.split(r"(?=\t\tFunction : )", out)
@@ -77,7 +85,7 @@ def write_sass(tag):
         # keep address + instruction, drop the hex encodings (they double the size and carry nothing a reader needs)
         body = [re.sub(r"\s*/\* 0x[0-9a-f]{16} \*/\s*$", "", ln) for ln in ch.splitlines()]
         body = [ln for ln in body if ln.strip()]
-        with open(os.path.join(d, short + ".sass"), "w") as f:
+        with _gz_text(os.path.join(d, short + ".sass.gz")) as f:
             f.write(f"// cuobjdump -sass prime_rl_cse_b200/libprl_b200.so, function {mangled} (instruction encodings stripped)\n" + "\n".join(body) + "\n")
         written.append(short)
     with open(os.path.join(ROOT, "profiles", f"{tag}_sass_mnemonics.txt"), "w") as f:
