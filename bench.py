@@ -937,6 +937,10 @@ def vocab_sharded_check(P, dist, rn, world, rank, dev, T=2048):
     for fused in (False, True):
         head = VocabShardedLMHead(W_full[v0:v1].clone(), V, main_grad=torch.zeros(v1 - v0, H, dtype=torch.float32, device=dev), fused_rs=fused)
         rec = vocab_sharded_parity(P, dist, head, mb, W_full, seg, world, dev)
+        rag = vocab_sharded_parity(P, dist, head, mb, W_full, seg, world, dev, ragged=True)  # unpadded packed rows of different lengths
+        rec["ragged_rows"] = {k: rag[k] for k in ("max_abs_dlogp", "max_abs_dentropy", "rel_l2_d_hidden", "rel_l2_d_weight_shard", "ok")}
+        rec["ok"] = bool(rec["ok"] and rag["ok"])
+        head.main_grad.zero_()
         cfg = P.LossConfig()
         dist.barrier()
         torch.cuda.synchronize()
