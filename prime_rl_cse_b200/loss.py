@@ -4,6 +4,7 @@
 
 from __future__ import annotations
 
+from collections import OrderedDict
 from typing import Any, Sequence
 
 import torch
@@ -32,6 +33,30 @@ def _pack(items: Sequence[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
             total = off - first.storage_offset()
             return first.detach().as_strided((total,), (1,), first.storage_offset())
     return torch.cat([t.detach().reshape(-1).to(dtype) for t in items])
+
+
+_CU_CACHE: "OrderedDict[tuple, tuple[torch.Tensor, torch.Tensor]]" = OrderedDict()
+_CU_CACHE_ENTRIES = 256
+
+
+def _cu_seqlens(lens: Sequence[int], dev: torch.device) -> torch.Tensor:
+    """int32 [n + 1] segment bounds on the device.  The host copy is PINNED and the upload asynchronous (a pageable source would
+    make the copy synchronous and cannot be captured in a CUDA graph); both tensors stay in a small LRU keyed by the lengths, so
+    a repeated packing costs no copy at all and a copy captured in a graph keeps a live source."""
+    key = (dev.type, dev.index, tuple(lens))
+    hit = _CU_CACHE.get(key)
+    if hit is not None:
+        _CU_CACHE.move_to_end(key)
+        return hit[1]
+    bounds = [0]
+    for ln in lens:
+        bounds.append(bounds[-1] + ln)
+    host = torch.tensor(bounds, dtype=torch.int32).pin_memory()
+    cu = host.to(dev, non_blocking=True)
+    _CU_CACHE[key] = (host, cu)
+    if len(_CU_CACHE) > _CU_CACHE_ENTRIES:
+        _CU_CACHE.popitem(last=False)
+    return cu
 
 
 def _loss_packed_raw(logp, old, adv, mask_u8, cu_seqlens, nseg, mode, length_norm, clip, loss_scale):
@@ -111,10 +136,7 @@ def compute_loss(
     adv = _pack(advantages, torch.float32)
     mask = _pack(loss_mask, torch.bool).view(torch.uint8)
     dev = old.device
-    bounds = [0]
-    for ln in lens:
-        bounds.append(bounds[-1] + ln)
-    cu = torch.tensor(bounds, dtype=torch.int32).to(dev, non_blocking=True)
+    cu = _cu_seqlens(lens, dev)
     mode = _lib.PRL_RATIO[loss_config.ratio_type]
     loss, ratio, clipped, is_clipped = _PackedLoss.apply(
         tuple(lens), old, adv, mask, cu, mode, bool(loss_config.ratio_length_norm), float(loss_config.clip_ratio),

@@ -1090,6 +1090,72 @@ def test_d_hidden_reduce_scatter_into_owner_buffers_emulated_on_one_gpu(P, rows_
     assert rc != 0
 
 
+def test_micro_step_is_cuda_graph_capturable(P):
+    """With the host-side segment lengths and active count attached by the loader (rollout_io.upload_micro_batches) the whole
+    micro-step -- partition, gather, fused forward, packed loss, autograd backward through the recompute GEMMs, fp32 d_W
+    accumulation -- issues no device-to-host synchronisation and no allocation outside torch's caching allocator, so it can be
+    captured in a CUDA graph and replayed on new data in the same buffers: the replay must reproduce the eager results."""
+    from prime_rl_cse_b200.segments import response_lengths_host
+
+    T, H, V, tau = 640, 256, 4096, 0.8
+    lens = [200, 248, 192]
+    pos = torch.cat([torch.arange(n) for n in lens])
+    mask = torch.ones(T, dtype=torch.bool)
+    mask[:50] = False
+    mask[200:260] = False
+    mask[448:470] = False
+    extra = {"response_lengths": response_lengths_host(pos.unsqueeze(0)), "n_active": int(mask[1:].sum())}
+    assert extra["response_lengths"] == lens
+
+    def data(seed):
+        hidden, weight, ids = _mk(T, H, V, seed)
+        g = torch.Generator().manual_seed(seed)
+        adv = torch.cat([torch.full((n,), float(a)) for n, a in zip(lens, torch.randn(3, generator=g))])
+        old = -torch.rand(T, generator=g) * 2
+        return hidden, weight, ids, adv, old
+
+    static = {k: v.cuda() for k, v in zip(("hidden", "weight", "ids", "adv", "old"), data(1))}
+    h = static["hidden"].clone().requires_grad_(True)
+    w = static["weight"]
+    acc = torch.zeros(V, H, device="cuda")
+    mb = dict(input_ids=static["ids"].unsqueeze(0), position_ids=pos.cuda().unsqueeze(0), advantages=static["adv"].unsqueeze(0),
+              logprobs=static["old"].unsqueeze(0), loss_mask=mask.cuda().unsqueeze(0), temperature=tau, **extra)
+    cfg, scale = P.LossConfig(), int(mask.sum())
+
+    def step():
+        h.grad = None
+        out = P.rl_micro_step(h.unsqueeze(0), w.requires_grad_(True), mb, cfg, scale, main_grad=acc)
+        return out["loss"], out["logprobs"], out["entropy"], h.grad
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # warm-up outside the capture (library knobs, function attributes, autograd's buffers)
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_loss, g_lp, g_ent, g_dh = step()
+    for seed in (2, 3):
+        new = data(seed)
+        with torch.no_grad():
+            for k, v in zip(("hidden", "ids", "adv", "old"), (new[0], new[2], new[3], new[4])):
+                static[k].copy_(v.cuda())
+            w.copy_(new[1].cuda())
+            h.copy_(static["hidden"])
+        acc.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        got = (g_loss.clone(), g_lp.clone(), g_ent.clone(), g_dh.clone(), acc.clone())
+        acc.zero_()
+        e_loss, e_lp, e_ent, e_dh = step()
+        torch.cuda.synchronize()
+        assert got[0].item() == e_loss.item() and torch.equal(got[1], e_lp) and torch.equal(got[2], e_ent)
+        assert torch.equal(got[3], e_dh) and torch.equal(got[4], acc)
+        assert float(got[3][:49].abs().max()) == 0.0 and float(got[3].abs().max()) > 0.0  # masked prompt rows: exact zeros
+
+
 @pytest.mark.parametrize("save", [False, True], ids=["recompute", "saved-logits"])
 def test_masked_micro_step_edge_masks(P, save):
     """all-masked rows (the orchestrator's padding batches, batch.py:153-161), a single active token, and an all-active row
