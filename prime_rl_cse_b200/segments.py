@@ -16,8 +16,8 @@ def segments_from_position_ids(position_ids: torch.Tensor, max_segments: int | N
     T = pos.numel()
     if max_segments is None:
         max_segments = max(T // 2 + 1, 1)
-    cu = torch.empty(max_segments + 1, dtype=torch.int32, device=pos.device)
-    nseg = torch.empty(1, dtype=torch.int32, device=pos.device)
+    buf = torch.empty(max_segments + 2, dtype=torch.int32, device=pos.device)  # one buffer: the count sits right behind the bounds
+    cu, nseg = buf[: max_segments + 1], buf[max_segments + 1 :]
     rc = lib.prl_segments_from_position_ids(_lib.ptr(pos), T, _lib.ptr(cu), _lib.ptr(nseg), max_segments, _lib.stream())
     _lib.check(rc, "prl_segments_from_position_ids")
     return cu, nseg
@@ -27,12 +27,22 @@ def get_response_lengths(position_ids: torch.Tensor) -> list[int]:
     """Drop-in for the reference function: python list of segment lengths (one D2H copy, one sync)."""
     if position_ids.numel() == 0:
         return [0]
-    cu, nseg = segments_from_position_ids(position_ids)
-    n = int(nseg.item())
-    if n < 0:
-        raise RuntimeError("segment table overflow")
-    b = cu[: n + 1].cpu().tolist()
-    return [b[i + 1] - b[i] for i in range(n)]
+    T = position_ids.numel()
+    # a boundary needs pos[i-1] != 0 and pos[i+1] == 1, so there are at most T // 2 + 1 segments; rows with more than 4095 of them
+    # (never seen: a packed row holds a handful of rollouts) take a second, full-size pass
+    for cap in (min(T // 2 + 1, 4095), T // 2 + 1):
+        cu, nseg = segments_from_position_ids(position_ids, cap)
+        table = torch.cat([nseg, cu])  # views of one device buffer -> ONE device-to-host copy, one synchronisation
+        host = torch.empty(table.shape, dtype=torch.int32, pin_memory=True)
+        host.copy_(table, non_blocking=True)
+        torch.cuda.current_stream(table.device).synchronize()
+        b = host.tolist()
+        n = b[0]
+        if n >= 0:
+            return [b[i + 2] - b[i + 1] for i in range(n)]
+        if cap == T // 2 + 1:
+            break
+    raise RuntimeError("segment table overflow")
 
 
 def response_lengths_host(position_ids: torch.Tensor) -> list[int]:

@@ -146,6 +146,17 @@ def test_segments_long_rows(P):
         assert P.get_response_lengths(cu(pos).unsqueeze(0)) == oracle.response_lengths(pos)
 
 
+def test_segments_more_than_the_first_pass_holds(P):
+    """get_response_lengths fetches a table of at most 4095 segments in its one D2H copy and falls back to a full-size pass
+    for rows with more (9000 two-token rollouts here; also the exact limit, and T < 3)"""
+    for nseg in (4094, 4095, 4096, 9000):
+        pos = np.tile(np.array([0, 1], dtype=np.int64), nseg)
+        want = oracle.response_lengths(pos)
+        assert len(want) == nseg and P.get_response_lengths(cu(pos).unsqueeze(0)) == want
+    for pos in ([0], [0, 1], [0, 0]):
+        assert P.get_response_lengths(cu(np.array(pos, dtype=np.int64)).unsqueeze(0)) == oracle.response_lengths(np.array(pos))
+
+
 # ------------------------------------------------------------------------------- loss
 CFG = {
     "token": ("token", False, 8.0),
