@@ -141,9 +141,20 @@ def stream() -> c_void_p:
 
 
 def require_cuda(*tensors: torch.Tensor) -> None:
+    """Every operand on the CURRENT CUDA device: the kernels are launched on torch's current stream of the current device
+    (one process per GPU, as in the reference), so a tensor that lives on another GPU is refused instead of being addressed
+    from the wrong device."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("prime_rl_cse_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: call torch.cuda.set_device "
+                               "(one process per GPU) before using prime_rl_cse_b200")
 
 
 def set_knob(name: str, value: int) -> None:
