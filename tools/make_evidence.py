@@ -130,7 +130,7 @@ def summarise(rep, tag, traffic):
     name = base if base.startswith(tag) else f"{tag}_{base}"
     lines = ["# " + " | ".join(["kernel"] + [f"{n}[{units[i]}]" for i, n in idx]), f"# source: ncu --set full --clock-control none, report {os.path.basename(rep)}"]
     # workload / mode are encoded in the report name: <tag>_<workload>__<mode>.ncu-rep; anything else goes under "misc"
-    m = re.match(rf"{tag}_(.+)__(recompute|saved|hbm)$", base)
+    m = re.match(rf"{tag}_(.+)__(recompute|saved|hbm|scatter)$", base)
     workload, mode = (m.group(1), m.group(2)) if m else ("misc", "misc")
     for r in data:
         fn = friendly(r[iname])
