@@ -95,6 +95,22 @@ def test_argument_validation_needs_no_gpu(lib):
     assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 8, 16, 100, 0, 1.0, 1, None, 104, None, 0, None, 0, 0, 0, None, 0, None) == -1
     assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 8, 16, 100, 0, 0.0, 1, None, 104, None, 0, None, 0, 0, 0, None, 0, None) == -1
     assert L.prl_lmhead_bwd_saved(None, None, None, None, None, 0, 16, 100, 0, 1.0, 1, None, 104, None, 0, None, 0, 0, 0, None, 0, None) == 0
+    # fused compute + collective entry points: the peer tables are validated on the host before anything is launched
+    import ctypes
+
+    two = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    scat = lambda T, rows, self_idx=0, peers=2, tab=two: L.prl_lmhead_bwd_scatter(  # noqa: E731
+        None, None, None, None, None, T, 64, 1000, 0, 1.0, 1, 1, tab, peers, rows, self_idx, None, 1, 1, 0, 0, None, 0, None)
+    assert scat(80, 40) == -2            # a 32-row epilogue slab must not straddle two owners: PRL_ERR_UNSUPPORTED
+    assert scat(96, 32) == -1            # T != n_peers * rows_per_peer
+    assert scat(64, 32, self_idx=2) == -1 and scat(64, 32, tab=None) == -1 and scat(288, 32, peers=9) == -1
+    assert scat(64, 32, tab=(ctypes.c_void_p * 2)(0x1000, 0)) == -1   # a peer that was never mapped
+    dws = lambda V, rows, peers=2, tab=two, local=None: L.prl_lmhead_bwd_dw_scatter(  # noqa: E731
+        None, None, None, None, None, 8, 64, V, 1.0, 1, 1, None, 0, tab, peers, rows, 0, local, 0, 0, None, 0, None)
+    assert dws(1000, 400) == -1          # rows_per_peer * n_peers must cover V (ceil(V / n_peers) rows per owner)
+    assert dws(40, 20) == -1             # fewer than 32 vocab rows per owner
+    assert dws(1000, 500, tab=(ctypes.c_void_p * 2)(0x1000, 0)) == -1
+    assert dws(1000, 500, local=ctypes.c_void_p(0x1004)) == -1        # the local accumulator is read with 16-byte loads
     # the optional workspace is only asked for where a K-split of the d_hidden GEMM pays off (few output tiles)
     assert L.prl_lmhead_bwd_saved_workspace_bytes(16384, 4096, 151936) == 0
     assert L.prl_lmhead_bwd_saved_workspace_bytes(4096, 1024, 151936) >= 4096 * 1024 * 4
